@@ -1,0 +1,86 @@
+"""ctypes binding of ``libopp_b200.so`` (C ABI declared in ``include/opp_b200.h``).
+
+There is no fallback: if the shared library is missing or a call fails, a ``RuntimeError`` is
+raised.  Tensors are passed as raw device pointers; the current torch CUDA stream is used.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libopp_b200.so")
+
+_lib = None
+
+
+def _sig(fn, argtypes):
+    fn.argtypes = argtypes
+    fn.restype = c_int
+
+
+P, I, L, F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argtypes; must mirror include/opp_b200.h exactly (tests check every symbol resolves)
+SIGNATURES = {
+    "opp_conv1_7x7": [P, P, P, P, I, I, I, I, P],
+    "opp_conv2d_nhwc": [P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, P],
+    "opp_upsample2x_add": [P, P, P, I, I, I, I, P],
+    "opp_kpt_stats": [P, P, I, I, P],
+    "opp_kpt_encode": [P] * 13 + [I, I, P],
+    "opp_linear_act_f16": [P, I, P, I, P, P, L, I, I, I, P],
+    "opp_linear_q_f16": [P, P, P, P, I, I, I, F, F, P],
+    "opp_linear_ln": [P, I, P, I, P, I, P, P, F, P, P, P, P, I, I, L, I, P],
+    "opp_kv_partial": [P, P, I, I, I, P],
+    "opp_kv_finalize": [P, P, P, P, I, I, I, F, P],
+    "opp_sim_lse": [P, P, P, P, I, I, I, I, F, P],
+    "opp_lse_finalize": [P, P, P, L, I, P],
+    "opp_sim_conf": [P, P, P, P, I, P, P, P, I, I, I, I, F, P],
+    "opp_best_finalize": [P, P, P, P, L, I, P],
+    "opp_match_select": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, P],
+    "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, P],
+    "opp_fine_attention": [P, P, I, I, F, P],
+    "opp_fine_match": [P, P, P, P, P, P, I, F, P],
+}
+PLAIN = {"opp_version": ([], c_int), "opp_num_sms": ([], c_int), "opp_sim_tiles": ([I], c_int),
+         "opp_last_error": ([], ctypes.c_char_p)}
+
+
+def load():
+    """Load the shared library (once). Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). There is no CPU/PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        _sig(getattr(lib, name), argtypes)
+    for name, (argtypes, restype) in PLAIN.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.opp_last_error()
+        raise RuntimeError(f"{name} failed (status {rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,300 @@
+// opp_gemm.cu — host launchers (C-ABI) for the tcgen05 GEMM / implicit-GEMM conv engine.
+//
+// Every entry point takes raw device pointers + sizes + a cudaStream_t, builds the TMA tensor
+// maps for the call, and launches one persistent kernel.  No allocation, no synchronisation.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/opp_b200.h"
+#include "opp_gemm.cuh"
+
+namespace opp {
+
+static thread_local char g_last_error[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_last_error; }
+
+// ---------------------------------------------------------------------------------------------
+// driver entry point for cuTensorMapEncodeTiled (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+  }
+  return n;
+}
+
+// fp16 tensor map, 128B swizzle, zero OOB fill. dims/strides fastest-first; strides in elements
+// for dims 1..rank-1.
+static int make_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                    const uint64_t* strides_elems, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return OPP_ERR_CUDA;
+  }
+  OPP_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base pointer not 16B aligned");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    OPP_REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_elems[i] * 2;
+    OPP_REQUIRE((gstr[i] & 15) == 0, "TMA stride %d (%llu B) not a multiple of 16", i,
+                (unsigned long long)gstr[i]);
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(ptr), gdim, gstr,
+                  bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu)",
+                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                   (unsigned long long)(rank > 2 ? dims[2] : 0));
+    return OPP_ERR_CUDA;
+  }
+  return OPP_OK;
+}
+
+// A / W operand as [batch][rows][K] with row stride ld (elements)
+static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long rows,
+                    long long batches, long long ld, long long batch_stride, int box_rows) {
+  uint64_t dims[3] = {(uint64_t)k, (uint64_t)rows, (uint64_t)batches};
+  uint64_t str[2] = {(uint64_t)ld, (uint64_t)batch_stride};
+  uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)box_rows, 1};
+  return make_map(map, ptr, 3, dims, str, box);
+}
+
+template <int A_MODE, class Epi>
+static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
+                  cudaStream_t stream) {
+  s.stages = gemm_pick_stages(s.block_n, s.k_chunks);
+  const int smem = gemm_smem_bytes(s.stages, s.block_n);
+  auto kern = gemm_kernel<A_MODE, Epi>;
+  static bool attr_set = false;  // one per template instantiation
+  if (!attr_set) {
+    OPP_CHECK_CUDA(
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long long total = (long long)s.batches * s.m_tiles * s.n_tiles;
+  if (total == 0) return OPP_OK;
+  const int grid = (int)(total < num_sms() ? total : num_sms());
+  kern<<<grid, kGemmThreads, smem, stream>>>(maps, s, ep);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+static int pick_block_n(int n) {
+  if (n <= 256) return (n + 15) & ~15;  // single tile (UMMA N is a multiple of 16)
+  if (n % 256 == 0) return 256;
+  if (n % 128 == 0) return 128;
+  return 256;
+}
+
+// common shape / map setup for token-row GEMMs
+static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, const void* a1,
+                      int k1, const void* w, int w_batched, int batches, long long rows, int n,
+                      int n_align = 16) {
+  OPP_REQUIRE(a0 && w, "null operand");
+  OPP_REQUIRE(k0 > 0 && k0 % 64 == 0 && k1 % 64 == 0, "K (%d,%d) must be multiples of 64", k0,
+              k1);
+  OPP_REQUIRE(n > 0 && n % n_align == 0, "N=%d must be a multiple of %d", n, n_align);
+  OPP_REQUIRE(batches > 0 && rows > 0, "empty GEMM");
+  memset(&s, 0, sizeof(s));
+  s.batches = batches;
+  s.rows = (int)rows;
+  s.m_tiles = (int)((rows + kBlockM - 1) / kBlockM);
+  s.block_n = pick_block_n(n);
+  OPP_REQUIRE(s.block_n % 16 == 0 && s.block_n <= 256, "bad block_n %d", s.block_n);
+  s.n_tiles = (n + s.block_n - 1) / s.block_n;
+  s.n_total = n;
+  s.k_chunks_a0 = k0 / 64;
+  s.k_chunks = (k0 + k1) / 64;
+  s.b_batched = w_batched;
+  int rc = map_rows(&maps.a[0], a0, k0, rows, batches, k0, rows * (long long)k0, kBlockM);
+  if (rc) return rc;
+  if (k1 > 0) {
+    OPP_REQUIRE(a1, "null second A operand");
+    rc = map_rows(&maps.a[1], a1, k1, rows, batches, k1, rows * (long long)k1, kBlockM);
+    if (rc) return rc;
+  } else {
+    maps.a[1] = maps.a[0];
+  }
+  maps.a[2] = maps.a[0];
+  maps.a[3] = maps.a[0];
+  const long long kt = k0 + k1;
+  return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt, s.block_n);
+}
+
+}  // namespace opp
+
+using namespace opp;
+
+extern "C" {
+
+const char* opp_last_error(void) { return opp::last_error(); }
+
+int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
+                       long long rows, int n, int act, int act_cols, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n);
+  if (rc) return rc;
+  OPP_REQUIRE(out, "null output");
+  EpiStoreF16::Params ep{(__half*)out, (long long)n, act, act_cols};
+  return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
+                     int rows, int d_model, float v_len, float eps, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  OPP_REQUIRE(d_model == 256, "opp_linear_q_f16 supports d_model 256 (8 heads x 32), got %d",
+              d_model);
+  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model);
+  if (rc) return rc;
+  OPP_REQUIRE(ksum && out, "null pointer");
+  EpiQ::Params ep{(__half*)out, (long long)d_model, ksum, v_len, eps};
+  return launch<A_ROWS, EpiQ>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w, int w_batched,
+                  const float* gamma, const float* beta, float eps, const float* resid,
+                  float* out32, void* out16, void* split, int split_kind, int batches,
+                  long long rows, int n, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  OPP_REQUIRE(n == 128 || n == 256, "LayerNorm epilogue needs N in {128,256}, got %d", n);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, w_batched, batches, rows, n);
+  if (rc) return rc;
+  OPP_REQUIRE(gamma && beta, "null LayerNorm parameters");
+  OPP_REQUIRE(split == nullptr || split_kind == 1 || split_kind == 2, "bad split_kind");
+  EpiLN::Params ep{gamma, beta, eps, resid, out32, (__half*)out16, (long long)n, (__half*)split,
+                   split_kind};
+  return launch<A_ROWS, EpiLN>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void* resid,
+                    void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
+                    int ksize, int stride, int act, float slope, float* tok32, void* tok16,
+                    const float* pe, opp_stream_t stream) {
+  OPP_REQUIRE(in && w && bias, "null operand");
+  OPP_REQUIRE(ksize == 1 || ksize == 3, "kernel size %d unsupported (1 or 3)", ksize);
+  OPP_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
+  OPP_REQUIRE(c_in_pad % 16 == 0 && c_out_pad % 16 == 0 && c_out_pad <= 256,
+              "channel counts must be padded to multiples of 16 (got %d -> %d)", c_in_pad,
+              c_out_pad);
+  OPP_REQUIRE(stride == 1 || (in_h % 2 == 0 && in_w % 2 == 0), "stride 2 needs even H, W");
+  OPP_REQUIRE(out || tok32, "no output requested");
+  const int pad = ksize / 2;
+  const int out_h = (in_h + 2 * pad - ksize) / stride + 1;
+  const int out_w = (in_w + 2 * pad - ksize) / stride + 1;
+  TensorMaps maps;
+  GemmShape s;
+  memset(&s, 0, sizeof(s));
+  s.batches = batch;
+  s.rows = out_h * out_w;
+  s.tile_w = 16;
+  s.tile_h = 8;
+  s.tiles_x = (out_w + s.tile_w - 1) / s.tile_w;
+  s.tiles_y = (out_h + s.tile_h - 1) / s.tile_h;
+  s.m_tiles = s.tiles_x * s.tiles_y;
+  s.block_n = c_out_pad;
+  s.n_tiles = 1;
+  s.n_total = c_out_pad;
+  s.conv_c = c_in_pad;
+  s.conv_cchunks = (c_in_pad + 63) / 64;
+  s.k_chunks = ksize * ksize * s.conv_cchunks;
+  s.conv_kw = ksize;
+  s.conv_pad = pad;
+  s.conv_stride = stride;
+  s.out_w = out_w;
+  s.out_h = out_h;
+  const long long C = c_in_pad;
+  const __half* base = (const __half*)in;
+  int rc;
+  if (stride == 1) {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)in_w, (uint64_t)in_h, (uint64_t)batch};
+    uint64_t str[3] = {(uint64_t)C, (uint64_t)(in_w * C), (uint64_t)((long long)in_h * in_w * C)};
+    uint32_t box[4] = {64, (uint32_t)s.tile_w, (uint32_t)s.tile_h, 1};
+    rc = make_map(&maps.a[0], base, 4, dims, str, box);
+    if (rc) return rc;
+    maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        uint64_t dims[4] = {(uint64_t)C, (uint64_t)(in_w / 2), (uint64_t)(in_h / 2),
+                            (uint64_t)batch};
+        uint64_t str[3] = {(uint64_t)(2 * C), (uint64_t)(2LL * in_w * C),
+                           (uint64_t)((long long)in_h * in_w * C)};
+        uint32_t box[4] = {64, (uint32_t)s.tile_w, (uint32_t)s.tile_h, 1};
+        rc = make_map(&maps.a[py * 2 + px], base + ((long long)py * in_w + px) * C, 4, dims, str,
+                      box);
+        if (rc) return rc;
+      }
+  }
+  const long long kt = (long long)ksize * ksize * c_in_pad;
+  rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n);
+  if (rc) return rc;
+  EpiConv::Params ep{(__half*)out, (long long)c_out_pad, bias, (const __half*)resid, act, slope,
+                     tok32,        (__half*)tok16,       pe};
+  return launch<A_CONV, EpiConv>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_sim_lse(const void* a, const void* b, float* part_m, float* part_s, int batches, int rows,
+                int cols, int k, float scale, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, 1);
+  if (rc) return rc;
+  EpiLse::Params ep{part_m, part_s, scale};
+  return launch<A_ROWS, EpiLse>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float* lse_other,
+                 int own_is_pt, float* conf, float* part_val, int* part_idx, int batches,
+                 int rows, int cols, int k, float scale, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, 1);
+  if (rc) return rc;
+  EpiConf::Params ep{lse_own, lse_other, scale, own_is_pt, conf, part_val, part_idx};
+  return launch<A_ROWS, EpiConf>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_sim_tiles(int cols) { return (cols + pick_block_n(cols) - 1) / pick_block_n(cols); }
+
+}  // extern "C"

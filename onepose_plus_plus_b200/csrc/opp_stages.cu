@@ -1,0 +1,809 @@
+// opp_stages.cu — the bandwidth / latency bound stages of the 2D-3D matcher that are not GEMMs:
+// first 7x7 conv (C_in = 1), bilinear x2 upsample + add, 3D keypoint encoding MLP, the
+// linear-attention KV state, dual-softmax finalisers, mutual-NN selection + ordered compaction,
+// fine-window gather, per-match linear attention and the correlation soft-argmax.
+// Each kernel cites the reference code it replaces (paths relative to zju3dv/OnePose_Plus_Plus).
+#include <cstdio>
+
+#include "../../include/opp_b200.h"
+#include "opp_common.cuh"
+
+namespace opp {
+int num_sms();
+
+// =============================================================================================
+// conv1: 7x7 stride 2 pad 3, 1 -> C channels, folded BN + ReLU   (backbone/resnet.py:101-103,143)
+// One thread per output pixel, all C channels; the 49-tap patch lives in registers, the
+// tap-major weights in shared memory (broadcast reads), output NHWC fp16.
+// =============================================================================================
+constexpr int kC1Tile = 16;  // 16x16 output pixels per CTA
+
+__global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict__ img,
+                                                        const float* __restrict__ w_t,
+                                                        const float* __restrict__ bias,
+                                                        __half* __restrict__ out, int H, int W,
+                                                        int C) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                 // [49][C]
+  float* b_s = w_s + 49 * C;       // [C]
+  float* p_s = b_s + C;            // [37][37] input patch
+  constexpr int P = 2 * kC1Tile + 5;
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
+  const int OH = H / 2, OW = W / 2;
+  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
+  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
+  const float* im = img + (long long)b * H * W;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < P * P; i += 256) {
+    const int py = i / P, px = i - py * P;
+    const int y = iy0 + py, x = ix0 + px;
+    p_s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kC1Tile, lx = threadIdx.x % kC1Tile;
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  float x[49];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) x[ky * 7 + kx] = p_s[(2 * ly + ky) * P + 2 * lx + kx];
+  if (oy >= OH || ox >= OW) return;
+  __half* dst = out + (((long long)b * OH + oy) * OW + ox) * C;
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = b_s[c0 + j];
+#pragma unroll
+    for (int t = 0; t < 49; ++t) {
+      const float4 wa = *reinterpret_cast<const float4*>(w_s + t * C + c0);
+      const float4 wb = *reinterpret_cast<const float4*>(w_s + t * C + c0 + 4);
+      acc[0] = fmaf(x[t], wa.x, acc[0]);
+      acc[1] = fmaf(x[t], wa.y, acc[1]);
+      acc[2] = fmaf(x[t], wa.z, acc[2]);
+      acc[3] = fmaf(x[t], wa.w, acc[3]);
+      acc[4] = fmaf(x[t], wb.x, acc[4]);
+      acc[5] = fmaf(x[t], wb.y, acc[5]);
+      acc[6] = fmaf(x[t], wb.z, acc[6]);
+      acc[7] = fmaf(x[t], wb.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    store_half8(dst + c0, acc);
+  }
+}
+
+// =============================================================================================
+// out = a + bilinear_x2(b), align_corners=True   (backbone/resnet.py:151-152,155-156)
+// torch semantics: src = dst * (in-1)/(out-1); i0 = floor(src); i1 = min(i0+1, in-1)
+// =============================================================================================
+__global__ void __launch_bounds__(256) upsample2x_add_kernel(const __half* __restrict__ a,
+                                                             const __half* __restrict__ bsrc,
+                                                             __half* __restrict__ out, int B,
+                                                             int h, int w, int C) {
+  const int cg = C / 8;
+  const long long total = (long long)B * (2 * h) * (2 * w) * cg;
+  const float sy = (float)(h - 1) / (float)(2 * h - 1);
+  const float sx = (float)(w - 1) / (float)(2 * w - 1);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    long long p = i / cg;
+    const int x = (int)(p % (2 * w));
+    p /= (2 * w);
+    const int y = (int)(p % (2 * h));
+    const int b = (int)(p / (2 * h));
+    const float fy = sy * (float)y, fx = sx * (float)x;
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    const __half* base = bsrc + (long long)b * h * w * C + c8 * 8;
+    float v00[8], v01[8], v10[8], v11[8], va[8], r[8];
+    load_half8(base + ((long long)y0 * w + x0) * C, v00);
+    load_half8(base + ((long long)y0 * w + x1) * C, v01);
+    load_half8(base + ((long long)y1 * w + x0) * C, v10);
+    load_half8(base + ((long long)y1 * w + x1) * C, v11);
+    const long long off = (((long long)b * 2 * h + y) * (2 * w) + x) * C + c8 * 8;
+    load_half8(a + off, va);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      r[j] = va[j] + (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]));
+    store_half8(out + off, r);
+  }
+}
+
+// =============================================================================================
+// 3D keypoint normalisation statistics   (utils/normalize.py:16-26)
+// stats[b] = (mean xyz over points of batch b, 0.6 * max extent of batch element 0)
+// =============================================================================================
+__global__ void __launch_bounds__(256) kpt_stats_kernel(const float* __restrict__ kpts,
+                                                        float* __restrict__ stats, int n) {
+  __shared__ float red[9][256];
+  const int b = blockIdx.x;
+  const float* k0 = kpts;                        // batch element 0 for the extents
+  const float* kb = kpts + (long long)b * n * 3;
+  float s[3] = {0.f, 0.f, 0.f}, mn[3] = {INFINITY, INFINITY, INFINITY},
+        mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = threadIdx.x; i < n; i += 256) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      s[a] += kb[i * 3 + a];
+      const float v = k0[i * 3 + a];
+      mn[a] = fminf(mn[a], v);
+      mx[a] = fmaxf(mx[a], v);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    red[a][threadIdx.x] = s[a];
+    red[3 + a][threadIdx.x] = mn[a];
+    red[6 + a][threadIdx.x] = mx[a];
+  }
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        red[a][threadIdx.x] += red[a][threadIdx.x + st];
+        red[3 + a][threadIdx.x] = fminf(red[3 + a][threadIdx.x], red[3 + a][threadIdx.x + st]);
+        red[6 + a][threadIdx.x] = fmaxf(red[6 + a][threadIdx.x], red[6 + a][threadIdx.x + st]);
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float ext = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      stats[b * 4 + a] = red[a][0] / (float)n;
+      ext = fmaxf(ext, red[6 + a][0] - red[3 + a][0]);
+    }
+    stats[b * 4 + 3] = ext * 0.6f;
+  }
+}
+
+// =============================================================================================
+// KeypointEncoding_linear   (utils/position_encoding.py:46-79 with norm_method "instancenorm":
+// InstanceNorm1d on [B, N, C] normalises over the C features of each point, biased variance,
+// eps 1e-5, no affine), then  tokens = descriptors^T + encoding.
+// 32 points per CTA; activations ping-pong through shared memory; weights read transposed.
+// =============================================================================================
+constexpr int kKeP = 16;
+
+template <int CIN, int COUT>
+__device__ __forceinline__ void kpt_layer(const float* __restrict__ in_s,  // [kKeP][CIN]
+                                          float* __restrict__ out_s,       // [kKeP][COUT+1]
+                                          const float* __restrict__ w_t,   // [CIN][COUT]
+                                          const float* __restrict__ bias, bool norm_relu) {
+  // thread -> output channel c = tid % COUT, point group g = tid / COUT
+  constexpr int PG = 256 / COUT > 0 ? 256 / COUT : 1;          // point groups in flight
+  constexpr int CPT = COUT > 256 ? COUT / 256 : 1;             // channels per thread (COUT<=256)
+  static_assert(CPT == 1, "COUT <= 256");
+  const int c = threadIdx.x % COUT;
+  const int g = threadIdx.x / COUT;
+  if (g < PG) {
+    for (int p = g; p < kKeP; p += PG) {
+      float acc = bias[c];
+      for (int k = 0; k < CIN; ++k) acc = fmaf(in_s[p * CIN + k], w_t[k * COUT + c], acc);
+      out_s[p * (COUT + 1) + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (norm_relu) {
+    // one warp per point at a time: mean / biased variance over COUT channels
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int p = warp; p < kKeP; p += 8) {
+      float* row = out_s + p * (COUT + 1);
+      float s = 0.f;
+      for (int k = lane; k < COUT; k += 32) s += row[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)COUT;
+      float q = 0.f;
+      for (int k = lane; k < COUT; k += 32) {
+        const float d = row[k] - mean;
+        q = fmaf(d, d, q);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.f / sqrtf(q / (float)COUT + 1e-5f);
+      for (int k = lane; k < COUT; k += 32) row[k] = fmaxf((row[k] - mean) * rstd, 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stats,
+                  const float* __restrict__ desc, const float* __restrict__ w1_t,
+                  const float* __restrict__ b1, const float* __restrict__ w2_t,
+                  const float* __restrict__ b2, const float* __restrict__ w3_t,
+                  const float* __restrict__ b3, const float* __restrict__ w4_t,
+                  const float* __restrict__ b4, float* __restrict__ tok32,
+                  __half* __restrict__ tok16, int n) {
+  __shared__ float buf_a[kKeP * 129];   // holds [P][3], [P][64+1] ... reused
+  __shared__ float buf_b[kKeP * 257];
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * kKeP;
+  const float cx = stats[b * 4 + 0], cy = stats[b * 4 + 1], cz = stats[b * 4 + 2];
+  const float sc = stats[b * 4 + 3];
+  // normalised keypoints -> buf_b as [P][3]
+  if (threadIdx.x < kKeP * 3) {
+    const int p = threadIdx.x / 3, a = threadIdx.x % 3;
+    const int gp = p0 + p;
+    float v = 0.f;
+    if (gp < n) {
+      const float c = a == 0 ? cx : (a == 1 ? cy : cz);
+      v = (kpts[((long long)b * n + gp) * 3 + a] - c) / sc;
+    }
+    buf_b[p * 3 + a] = v;
+  }
+  __syncthreads();
+  // layer outputs are stored with row stride COUT+1; the next layer reads with stride CIN, so
+  // compact in place between layers.
+  kpt_layer<3, 32>(buf_b, buf_a, w1_t, b1, true);     // buf_a [P][33]
+  for (int i = threadIdx.x; i < kKeP * 32; i += 256) buf_b[i] = buf_a[(i / 32) * 33 + (i % 32)];
+  __syncthreads();
+  kpt_layer<32, 64>(buf_b, buf_a, w2_t, b2, true);    // buf_a [P][65]
+  for (int i = threadIdx.x; i < kKeP * 64; i += 256) buf_b[i] = buf_a[(i / 64) * 65 + (i % 64)];
+  __syncthreads();
+  kpt_layer<64, 128>(buf_b, buf_a, w3_t, b3, true);   // buf_a [P][129]
+  __syncthreads();
+  // last layer reads buf_a with stride 129
+  {
+    const int c = threadIdx.x;  // 256 output channels
+    for (int p = 0; p < kKeP; ++p) {
+      float acc = b4[c];
+      const float* row = buf_a + p * 129;
+      for (int k = 0; k < 128; ++k) acc = fmaf(row[k], w4_t[k * 256 + c], acc);
+      buf_b[p * 257 + c] = acc;
+    }
+  }
+  __syncthreads();
+  // add descriptors (read [B][256][N] coalesced along n), then write token-major
+  {
+    const int pl = threadIdx.x % kKeP, cgp = threadIdx.x / kKeP;  // 256/kKeP channel groups
+    const int gp = p0 + pl;
+    if (gp < n)
+      for (int c = cgp; c < 256; c += 256 / kKeP)
+        buf_b[pl * 257 + c] += desc[((long long)b * 256 + c) * n + gp];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kKeP * 256; i += 256) {
+    const int p = i / 256, c = i % 256;
+    const int gp = p0 + p;
+    if (gp < n) {
+      const float v = buf_b[p * 257 + c];
+      const long long o = ((long long)b * n + gp) * 256 + c;
+      tok32[o] = v;
+      tok16[o] = __float2half_rn(v);
+    }
+  }
+}
+
+// =============================================================================================
+// Linear-attention source state   (loftr_module/linear_attention.py:55-57)
+// part[b][chunk][h][d][v] = sum_{s in chunk} K'[s,h,d] V[s,h,v];  row d = 32 holds sum_s K'[s,h,:]
+// =============================================================================================
+constexpr int kKvChunk = 256;
+
+__global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restrict__ kv16,
+                                                         float* __restrict__ part, int S, int d) {
+  __shared__ __half k_s[kKvChunk][32];
+  __shared__ __half v_s[kKvChunk][32];
+  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int chunks = gridDim.x, H = gridDim.y;
+  const int s0 = chunk * kKvChunk;
+  const int cnt = min(kKvChunk, S - s0);
+  const __half* src = kv16 + ((long long)b * S + s0) * (2 * d);
+  // 256 tokens x (32 K' + 32 V) halves; 4 threads per token row move 8 halves each per operand
+  for (int i = threadIdx.x; i < kKvChunk * 4; i += 256) {
+    const int t = i >> 2, part4 = i & 3;
+    uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+    if (t < cnt) {
+      kq = *reinterpret_cast<const uint4*>(src + (long long)t * 2 * d + h * 32 + part4 * 8);
+      vq = *reinterpret_cast<const uint4*>(src + (long long)t * 2 * d + d + h * 32 + part4 * 8);
+    }
+    *reinterpret_cast<uint4*>(&k_s[t][part4 * 8]) = kq;
+    *reinterpret_cast<uint4*>(&v_s[t][part4 * 8]) = vq;
+  }
+  __syncthreads();
+  const int dd = threadIdx.x >> 3, v0 = (threadIdx.x & 7) * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, ks = 0.f;
+  for (int t = 0; t < kKvChunk; ++t) {
+    const float k = __half2float(k_s[t][dd]);
+    const __half2* vp = reinterpret_cast<const __half2*>(&v_s[t][v0]);
+    const float2 va = __half22float2(vp[0]), vb = __half22float2(vp[1]);
+    acc[0] = fmaf(k, va.x, acc[0]);
+    acc[1] = fmaf(k, va.y, acc[1]);
+    acc[2] = fmaf(k, vb.x, acc[2]);
+    acc[3] = fmaf(k, vb.y, acc[3]);
+    ks += k;
+  }
+  float* dst = part + ((((long long)b * chunks + chunk) * H + h) * 33) * 32;
+  *reinterpret_cast<float4*>(dst + dd * 32 + v0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if ((threadIdx.x & 7) == 0) dst[32 * 32 + dd] = ks;
+}
+
+// mt[b][c][h*32+dd] = sum_v merge_w[c][h*32+v] * KV[b][h][dd][v] / v_len ; ksum[b][h*32+dd]
+// (transformer.py:85 `merge` folded into the per-image KV state)
+__global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restrict__ part,
+                                                          const float* __restrict__ merge_w,
+                                                          __half* __restrict__ mt,
+                                                          float* __restrict__ ksum, int chunks,
+                                                          int d, float inv_vlen) {
+  __shared__ float kv_s[33][33];
+  const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
+  for (int i = threadIdx.x; i < 33 * 32; i += 256) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += part[((((long long)b * chunks + c) * H + h) * 33) * 32 + i];
+    kv_s[i / 32][i % 32] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) ksum[(long long)b * d + h * 32 + threadIdx.x] = kv_s[32][threadIdx.x];
+  for (int c = threadIdx.x; c < d; c += 256) {
+    float w[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) w[v] = merge_w[(long long)c * d + h * 32 + v];
+    float o[32];
+#pragma unroll
+    for (int dd = 0; dd < 32; ++dd) {
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < 32; ++v) s = fmaf(w[v], kv_s[dd][v], s);
+      o[dd] = s * inv_vlen;
+    }
+    __half* dst = mt + ((long long)b * d + c) * d + h * 32;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) store_half8(dst + g * 8, o + g * 8);
+  }
+}
+
+// =============================================================================================
+// dual-softmax finalisers   (utils/coarse_matching.py:115,157-165)
+// =============================================================================================
+__global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
+                                    float* __restrict__ lse, long long rows, int tiles) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int t = 0; t < tiles; ++t) m = fmaxf(m, pm[r * tiles + t]);
+  float s = 0.f;
+  for (int t = 0; t < tiles; ++t) s += ps[r * tiles + t] * expf(pm[r * tiles + t] - m);
+  lse[r] = m + logf(s);
+}
+
+__global__ void best_finalize_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
+                                     float* __restrict__ bv, int* __restrict__ bi, long long rows,
+                                     int tiles) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float best = pv[r * tiles];
+  int idx = pi[r * tiles];
+  for (int t = 1; t < tiles; ++t) {
+    const float v = pv[r * tiles + t];
+    if (v > best) {
+      best = v;
+      idx = pi[r * tiles + t];
+    }
+  }
+  bv[r] = best;
+  bi[r] = idx;
+}
+
+// =============================================================================================
+// match selection + ordered compaction   (utils/coarse_matching.py:142-172, 223-239)
+//   keep (b, l) iff conf_max > thr, argmax cell j not in the top/left border (mask_border only
+//   clears rows < b and cols < b: coarse_matching.py:10-20), and l is the column argmax of j.
+// =============================================================================================
+__device__ __forceinline__ bool match_flag(const float* pt_val, const int* pt_idx,
+                                           const int* px_idx, long long r, int l, int s, int wc,
+                                           float thr, int border) {
+  const float v = pt_val[r];
+  if (!(v > thr)) return false;
+  const int j = pt_idx[r];
+  const int jy = j / wc, jx = j - jy * wc;
+  if (jy < border || jx < border) return false;
+  const long long b = r / l;
+  const int i = (int)(r - b * l);
+  return px_idx[b * s + j] == i;
+}
+
+__global__ void __launch_bounds__(1024) match_count_kernel(const float* pt_val, const int* pt_idx,
+                                                           const int* px_idx, long long rows,
+                                                           int l, int s, int wc, float thr,
+                                                           int border, int* block_counts) {
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
+  const int c = __syncthreads_count(f);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+// single block: exclusive scan of block_counts in place; total -> counts[nblocks] and count_out
+__global__ void __launch_bounds__(1024) match_scan_kernel(int* counts, int nblocks,
+                                                          int* count_out) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int w = warp_sums[threadIdx.x];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (threadIdx.x >= o) w += y;
+      }
+      warp_sums[threadIdx.x] = w;
+    }
+    __syncthreads();
+    const int warp_off = (threadIdx.x >> 5) > 0 ? warp_sums[(threadIdx.x >> 5) - 1] : 0;
+    const int incl = x + warp_off + carry_s;
+    if (i < nblocks) counts[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    counts[nblocks] = carry_s;
+    *count_out = carry_s;
+  }
+}
+
+__global__ void __launch_bounds__(1024)
+match_scatter_kernel(const float* pt_val, const int* pt_idx, const int* px_idx, const float* kpts,
+                     const float* img_scale, long long rows, int l, int s, int wc, float thr,
+                     int border, float cell, const int* block_offsets, long long* b_ids,
+                     long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
+                     float* mkpts_c) {
+  __shared__ int warp_sums[32];
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
+  const unsigned ballot = __ballot_sync(0xffffffffu, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  if (!f) return;
+  const int pos = block_offsets[blockIdx.x] + (warp > 0 ? warp_sums[warp - 1] : 0) +
+                  __popc(ballot & ((1u << lane) - 1u));
+  const long long b = r / l;
+  const int i = (int)(r - b * l);
+  const int j = pt_idx[r];
+  b_ids[pos] = b;
+  i_ids[pos] = i;
+  j_ids[pos] = j;
+  mconf[pos] = pt_val[r];
+  const float* kp = kpts + (b * l + i) * 3;
+  mkpts3d[pos * 3 + 0] = kp[0];
+  mkpts3d[pos * 3 + 1] = kp[1];
+  mkpts3d[pos * 3 + 2] = kp[2];
+  // coarse_matching.py:223-229: [j % w, j // w] * (scale * query_image_scale[b][[1, 0]])
+  float sx = cell, sy = cell;
+  if (img_scale) {
+    sx = cell * img_scale[b * 2 + 1];
+    sy = cell * img_scale[b * 2 + 0];
+  }
+  mkpts_c[pos * 2 + 0] = (float)(j % wc) * sx;
+  mkpts_c[pos * 2 + 1] = (float)(j / wc) * sy;
+}
+
+// =============================================================================================
+// fine window gather   (loftr_module/fine_preprocess.py:41-55)
+// =============================================================================================
+__global__ void __launch_bounds__(128) fine_gather_kernel(
+    const __half* __restrict__ fine, const float* __restrict__ desc3d,
+    const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
+    const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
+    int wf, int wc, int stride, int n) {
+  const int m = blockIdx.x, c = threadIdx.x;
+  const long long b = b_ids[m], i = i_ids[m], j = j_ids[m];
+  const int jy = (int)(j / wc), jx = (int)(j - (long long)jy * wc);
+  const long long row0 = (long long)m * 26;
+  const float d = desc3d[(b * 128 + c) * n + i];
+  x32[row0 * 128 + c] = d;
+  x16[row0 * 128 + c] = __float2half_rn(d);
+  const __half* fb = fine + b * hf * wf * 128;
+  for (int ww = 0; ww < 25; ++ww) {
+    const int y = jy * stride + ww / 5 - 2, x = jx * stride + ww % 5 - 2;
+    __half hv = __float2half_rn(0.f);
+    if (y >= 0 && y < hf && x >= 0 && x < wf) hv = fb[((long long)y * wf + x) * 128 + c];
+    x32[(row0 + 1 + ww) * 128 + c] = __half2float(hv);
+    x16[(row0 + 1 + ww) * 128 + c] = hv;
+  }
+}
+
+// =============================================================================================
+// per-match linear attention, 1 + 25 tokens, 8 heads x 16   (linear_attention.py:29-61)
+// The v/v_length ... * v_length pair of the reference cancels exactly and is omitted.
+// =============================================================================================
+__global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __restrict__ qkv,
+                                                             __half* __restrict__ msg, int cross,
+                                                             float eps) {
+  __shared__ __half q_s[26][128];
+  __shared__ __half k_s[26][128];
+  __shared__ __half v_s[26][128];
+  __shared__ float kv2[8][16][16];   // state of the 25 window tokens
+  __shared__ float ks2[128];
+  const int m = blockIdx.x, c = threadIdx.x;
+  const __half* src = qkv + (long long)m * 26 * 384;
+  for (int t = 0; t < 26; ++t) {
+    q_s[t][c] = src[t * 384 + c];
+    k_s[t][c] = src[t * 384 + 128 + c];
+    v_s[t][c] = src[t * 384 + 256 + c];
+  }
+  __syncthreads();
+  const int h = c >> 4, v = c & 15;
+  // window state: thread (h, v) owns column v of head h
+  float col[16];
+#pragma unroll
+  for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
+  float ksum_c = 0.f;  // thread c also owns ks2[c]
+  for (int t = 1; t < 26; ++t) {
+    const float vv = __half2float(v_s[t][c]);
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(__half2float(k_s[t][h * 16 + dd]), vv, col[dd]);
+    ksum_c += __half2float(k_s[t][c]);
+  }
+#pragma unroll
+  for (int dd = 0; dd < 16; ++dd) kv2[h][dd][v] = col[dd];
+  ks2[c] = ksum_c;
+  __syncthreads();
+  __half* dst = msg + (long long)m * 26 * 128;
+  for (int t = 0; t < 26; ++t) {
+    // which source state does token t read?  self: own sequence; cross: the other one
+    const bool use_window = cross ? (t == 0) : (t > 0);
+    float num = 0.f, den = 0.f;
+    if (use_window) {
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd) {
+        const float q = __half2float(q_s[t][h * 16 + dd]);
+        num = fmaf(q, kv2[h][dd][v], num);
+        den = fmaf(q, ks2[h * 16 + dd], den);
+      }
+    } else {
+      // source is the single 3D token (row 0): KV = k0^T v0, Ksum = k0
+      float qk = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd)
+        qk = fmaf(__half2float(q_s[t][h * 16 + dd]), __half2float(k_s[0][h * 16 + dd]), qk);
+      num = qk * __half2float(v_s[0][c]);
+      den = qk;
+    }
+    dst[t * 128 + c] = __float2half_rn(num / (den + eps));
+  }
+}
+
+// =============================================================================================
+// fine matching   (utils/fine_matching.py:78-110): one warp per match
+// =============================================================================================
+__global__ void __launch_bounds__(128) fine_match_kernel(
+    const float* __restrict__ x32, const float* __restrict__ mkpts_c,
+    const long long* __restrict__ b_ids, const float* __restrict__ img_scale,
+    float* __restrict__ expec_f, float* __restrict__ mkpts_f, int M, float fine_scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const float* f0 = x32 + (long long)m * 26 * 128;
+  const float4 a = reinterpret_cast<const float4*>(f0)[lane];
+  float my_sim = -INFINITY;
+  for (int r = 0; r < 25; ++r) {
+    const float4 w = reinterpret_cast<const float4*>(f0 + (1 + r) * 128)[lane];
+    float d = a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if (lane == r) my_sim = d * 0.08838834764831845f;  // 1/sqrt(128)
+  }
+  float mx = my_sim;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e = lane < 25 ? expf(my_sim - mx) : 0.f;
+  float sum = e;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float p = e / sum;
+  // grid: linspace(-1, 1, 5), x fastest (kornia create_meshgrid + spatial_expectation2d)
+  const float gx = lane < 25 ? -1.f + 0.5f * (float)(lane % 5) : 0.f;
+  const float gy = lane < 25 ? -1.f + 0.5f * (float)(lane / 5) : 0.f;
+  float ex = gx * p, ey = gy * p, exx = gx * gx * p, eyy = gy * gy * p;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    ey += __shfl_xor_sync(0xffffffffu, ey, o);
+    exx += __shfl_xor_sync(0xffffffffu, exx, o);
+    eyy += __shfl_xor_sync(0xffffffffu, eyy, o);
+  }
+  if (lane == 0) {
+    const float vx = exx - ex * ex, vy = eyy - ey * ey;
+    const float sd = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
+    expec_f[m * 3 + 0] = ex;
+    expec_f[m * 3 + 1] = ey;
+    expec_f[m * 3 + 2] = sd;
+    float sx = fine_scale, sy = fine_scale;
+    if (img_scale) {
+      const long long b = b_ids[m];
+      sx = fine_scale * img_scale[b * 2 + 1];
+      sy = fine_scale * img_scale[b * 2 + 0];
+    }
+    // fine_matching.py:104-105: mkpts_query_c + coords * (W // 2) * scale
+    mkpts_f[m * 2 + 0] = mkpts_c[m * 2 + 0] + ex * 2.f * sx;
+    mkpts_f[m * 2 + 1] = mkpts_c[m * 2 + 1] + ey * 2.f * sy;
+  }
+}
+
+}  // namespace opp
+
+using namespace opp;
+
+static inline int grid_for(long long n, int block) {
+  long long g = (n + block - 1) / block;
+  const long long cap = (long long)opp::num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+extern "C" {
+
+int opp_version(void) { return 100; }
+int opp_num_sms(void) { return opp::num_sms(); }
+
+int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
+                  int h, int w, int c_out, opp_stream_t stream) {
+  OPP_REQUIRE(image && w_t && bias && out, "null pointer");
+  OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
+  const int smem = (49 * c_out + c_out + 37 * 37) * 4;
+  static bool attr = false;
+  if (!attr) {
+    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr = true;
+  }
+  dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
+  conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
+                                                              c_out);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
+                       opp_stream_t stream) {
+  OPP_REQUIRE(a && b && out, "null pointer");
+  OPP_REQUIRE(c % 8 == 0 && h > 1 && w > 1, "bad upsample shape");
+  const long long total = (long long)batch * 4 * h * w * (c / 8);
+  upsample2x_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_kpt_stats(const float* kpts, float* stats, int batch, int n, opp_stream_t stream) {
+  OPP_REQUIRE(kpts && stats && batch > 0 && n > 0, "bad kpt_stats arguments");
+  kpt_stats_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(kpts, stats, n);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, const float* w1_t,
+                   const float* b1, const float* w2_t, const float* b2, const float* w3_t,
+                   const float* b3, const float* w4_t, const float* b4, float* tok32, void* tok16,
+                   int batch, int n, opp_stream_t stream) {
+  OPP_REQUIRE(kpts && stats && desc && tok32 && tok16, "null pointer");
+  dim3 grid((n + kKeP - 1) / kKeP, batch);
+  kpt_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kpts, stats, desc, w1_t, b1, w2_t, b2,
+                                                            w3_t, b3, w4_t, b4, tok32,
+                                                            (__half*)tok16, n);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, opp_stream_t stream) {
+  OPP_REQUIRE(kv16 && part, "null pointer");
+  OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
+  dim3 grid((s + kKvChunk - 1) / kKvChunk, d / 32, batch);
+  kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ksum, int batch,
+                    int chunks, int d, float v_len, opp_stream_t stream) {
+  OPP_REQUIRE(part && merge_w && mt && ksum, "null pointer");
+  OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
+  dim3 grid(d / 32, batch);
+  kv_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(part, merge_w, (__half*)mt, ksum,
+                                                             chunks, d, 1.f / v_len);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long long rows,
+                     int tiles, opp_stream_t stream) {
+  OPP_REQUIRE(part_m && part_s && lse, "null pointer");
+  lse_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      part_m, part_s, lse, rows, tiles);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_best_finalize(const float* part_val, const int* part_idx, float* best_val, int* best_idx,
+                      long long rows, int tiles, opp_stream_t stream) {
+  OPP_REQUIRE(part_val && part_idx && best_val && best_idx, "null pointer");
+  best_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      part_val, part_idx, best_val, best_idx, rows, tiles);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, const float* kpts,
+                     const float* img_scale, int batch, int l, int hc, int wc, float thr,
+                     int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
+                     long long* j_ids, float* mconf, float* mkpts3d, float* mkpts_c,
+                     int* count_out, opp_stream_t stream) {
+  OPP_REQUIRE(pt_val && pt_idx && px_idx && kpts && scratch && count_out, "null pointer");
+  const long long rows = (long long)batch * l;
+  const int nblocks = (int)((rows + 1023) / 1024);
+  const int s = hc * wc;
+  cudaStream_t st = (cudaStream_t)stream;
+  match_count_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, rows, l, s, wc, thr, border,
+                                               scratch);
+  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
+  match_scatter_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, kpts, img_scale, rows, l,
+                                                 s, wc, thr, border, cell, scratch, b_ids, i_ids,
+                                                 j_ids, mconf, mkpts3d, mkpts_c);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
+                    const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
+                    int hf, int wf, int wc, int stride, int n, opp_stream_t stream) {
+  if (m == 0) return OPP_OK;
+  OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x32 && x16, "null pointer");
+  fine_gather_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)fine, desc3d, b_ids,
+                                                          i_ids, j_ids, x32, (__half*)x16, hf, wf,
+                                                          wc, stride, n);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps,
+                       opp_stream_t stream) {
+  if (m == 0) return OPP_OK;
+  OPP_REQUIRE(qkv && msg, "null pointer");
+  fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
+                                                             cross, eps);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_ids,
+                   const float* img_scale, float* expec_f, float* mkpts_f, int m, float fine_scale,
+                   opp_stream_t stream) {
+  if (m == 0) return OPP_OK;
+  OPP_REQUIRE(x32 && mkpts_c && b_ids && expec_f && mkpts_f, "null pointer");
+  fine_match_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts_c, b_ids, img_scale,
+                                                                   expec_f, mkpts_f, m, fine_scale);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+}  // extern "C"

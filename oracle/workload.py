@@ -1,0 +1,162 @@
+"""Synthetic checkpoint + planted 2D-3D workload — TEST INFRASTRUCTURE ONLY.
+
+The reference's pretrained weights and datasets are Google-Drive downloads (README.md:36,50) and
+are not available offline, and with random weights + random descriptors the matcher returns zero
+matches.  This module builds (i) a seeded synthetic ``state_dict`` with the
+reference's 195 keys and (ii) a workload whose 3D descriptors are *planted* from the image's own
+features so that the coarse stage finds real mutual matches and the fine stage has non-trivial
+sub-pixel offsets (recipe: SURVEY.md App. B).
+"""
+import math
+
+import torch
+
+from . import oracle
+
+
+def _kaiming_fan_out(g, shape):
+    fan_out = shape[0] * shape[2] * shape[3]
+    return torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+
+
+def _xavier(g, shape):
+    bound = math.sqrt(6.0 / (shape[0] + shape[1]))
+    return (torch.rand(shape, generator=g) * 2 - 1) * bound
+
+
+def synthetic_state_dict(seed=0, bn_perturb=True):
+    """Seeded weights with the reference layout.  Initialisers follow the
+    reference (kaiming fan_out convs resnet.py:126-131, xavier transformer transformer.py:128-131);
+    BatchNorm affine/running statistics are perturbed so that BN folding is actually exercised."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, co, ci, k):
+        sd[name + ".weight"] = _kaiming_fan_out(g, (co, ci, k, k))
+
+    def bn(name, c):
+        if bn_perturb:
+            sd[name + ".weight"] = 0.8 + 0.4 * torch.rand(c, generator=g)
+            sd[name + ".bias"] = 0.1 * torch.randn(c, generator=g)
+            sd[name + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+            sd[name + ".running_var"] = 0.6 + 0.8 * torch.rand(c, generator=g)
+        else:
+            sd[name + ".weight"] = torch.ones(c)
+            sd[name + ".bias"] = torch.zeros(c)
+            sd[name + ".running_mean"] = torch.zeros(c)
+            sd[name + ".running_var"] = torch.ones(c)
+        sd[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    def block(name, ci, co, stride):
+        conv(name + ".conv1", co, ci, 3)
+        conv(name + ".conv2", co, co, 3)
+        bn(name + ".bn1", co)
+        bn(name + ".bn2", co)
+        if stride != 1:
+            conv(name + ".downsample.0", co, ci, 1)
+            bn(name + ".downsample.1", co)
+
+    p = "backbone."
+    conv(p + "conv1", 128, 1, 7)
+    bn(p + "bn1", 128)
+    dims = [128, 196, 256]
+    cin = 128
+    for li, (d, s) in enumerate(zip(dims, (1, 2, 2)), start=1):
+        block(f"{p}layer{li}.0", cin, d, s)
+        block(f"{p}layer{li}.1", d, d, 1)
+        cin = d
+    conv(p + "layer3_outconv", 256, 256, 1)
+    conv(p + "layer2_outconv", 256, 196, 1)
+    conv(p + "layer2_outconv2.0", 256, 256, 3)
+    bn(p + "layer2_outconv2.1", 256)
+    conv(p + "layer2_outconv2.3", 196, 256, 3)
+    conv(p + "layer1_outconv", 196, 128, 1)
+    conv(p + "layer1_outconv2.0", 196, 196, 3)
+    bn(p + "layer1_outconv2.1", 196)
+    conv(p + "layer1_outconv2.3", 128, 196, 3)
+
+    chans = [3, 32, 64, 128, 256]
+    for i, idx in enumerate((0, 3, 6, 9)):
+        bound = 1.0 / math.sqrt(chans[i])
+        sd[f"kpt_3d_pos_encoding.encoder.{idx}.weight"] = \
+            (torch.rand(chans[i + 1], chans[i], generator=g) * 2 - 1) * bound
+        sd[f"kpt_3d_pos_encoding.encoder.{idx}.bias"] = \
+            torch.zeros(chans[i + 1]) if idx == 9 else (torch.rand(chans[i + 1], generator=g) * 2 - 1) * bound
+
+    for name, d, n_layers in (("loftr_coarse", 256, 6), ("loftr_fine", 128, 2)):
+        for i in range(n_layers):
+            q = f"{name}.layers.{i}."
+            for proj in ("q_proj", "k_proj", "v_proj", "merge"):
+                sd[q + proj + ".weight"] = _xavier(g, (d, d))
+            sd[q + "mlp.0.weight"] = _xavier(g, (2 * d, 2 * d))
+            sd[q + "mlp.2.weight"] = _xavier(g, (d, 2 * d))
+            for nrm in ("norm1", "norm2"):
+                sd[q + nrm + ".weight"] = 1.0 + 0.05 * torch.randn(d, generator=g)
+                sd[q + nrm + ".bias"] = 0.05 * torch.randn(d, generator=g)
+    return sd
+
+
+@torch.no_grad()
+def planted_workload(sd, h=512, w=512, n_points=5000, n_planted=3000, batch=1, alpha=20.0,
+                     beta=8.0, seed=1, image_noise=0.02, with_scale=True):
+    """Inputs for OnePosePlus_model.forward whose bank is planted from image 0's own features.
+
+    Images 1..batch-1 are image 0 plus a little noise (distinct inputs, matches still found);
+    the bank is the same for every batch element (BASELINE.json configs 3/4: shared cloud).
+    """
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(1, 1, h, w, generator=g)
+    imgs = [base]
+    for _ in range(batch - 1):
+        imgs.append((base + image_noise * torch.randn(1, 1, h, w, generator=g)).clamp(0, 1))
+    image = torch.cat(imgs, 0)
+    kpts = torch.rand(1, n_points, 3, generator=g) - 0.5
+
+    fc, ff = oracle.backbone(sd, base)
+    hc, wc = fc.shape[2:]
+    pe = oracle.position_encoding_sine(256, hc, wc)
+    qc = (fc + pe[None]).flatten(2).transpose(1, 2)[0]  # [S, 256]
+    mu = qc.mean(0)
+    r = qc - mu
+    mu_dir = mu / mu.norm()
+    r = r - (r @ mu_dir)[:, None] * mu_dir[None]
+    ys, xs = torch.meshgrid(torch.arange(2, hc), torch.arange(2, wc), indexing="ij")
+    interior = (ys * wc + xs).flatten()
+    n_planted = min(n_planted, interior.numel(), n_points)
+    cells = interior[torch.randperm(interior.numel(), generator=g)[:n_planted]]
+
+    kenc = oracle.keypoint_encoding(sd, oracle.normalize_3d_keypoints(kpts),
+                                    torch.zeros(1, 256, n_points))  # [1, 256, N]
+    dc = torch.randn(1, 256, n_points, generator=g) * r.std() * alpha / 4
+    dc[0, :, :n_planted] = alpha * r[cells].t() - kenc[0, :, :n_planted]
+
+    hf, wf = ff.shape[2:]
+    stride = hf // hc
+    ffc = ff[0] - ff[0].mean((1, 2), keepdim=True)
+    off = torch.randint(-2, 3, (n_planted, 2), generator=g)
+    fy = ((cells // wc) * stride + off[:, 0]).clamp(0, hf - 1)
+    fx = ((cells % wc) * stride + off[:, 1]).clamp(0, wf - 1)
+    df = torch.randn(1, 128, n_points, generator=g) * ff.std()
+    df[0, :, :n_planted] = beta * ffc[:, fy, fx]
+
+    data = {
+        "query_image": image,
+        "keypoints3d": kpts.expand(batch, -1, -1).contiguous(),
+        "descriptors3d_db": df.expand(batch, -1, -1).contiguous(),
+        "descriptors3d_coarse_db": dc.expand(batch, -1, -1).contiguous(),
+    }
+    if with_scale:
+        data["query_image_scale"] = torch.tensor([[1.25, 0.8]]).expand(batch, -1).contiguous()
+    meta = {"cells": cells, "offsets": off, "n_planted": n_planted}
+    return data, meta
+
+
+def random_workload(h=512, w=512, n_points=5000, batch=1, seed=1):
+    """BASELINE.json config 1 taken literally: random image, random descriptors (yields M = 0)."""
+    g = torch.Generator().manual_seed(seed)
+    return {
+        "query_image": torch.rand(batch, 1, h, w, generator=g),
+        "keypoints3d": (torch.rand(1, n_points, 3, generator=g) - 0.5).expand(batch, -1, -1).contiguous(),
+        "descriptors3d_db": torch.randn(1, 128, n_points, generator=g).expand(batch, -1, -1).contiguous(),
+        "descriptors3d_coarse_db": torch.randn(1, 256, n_points, generator=g).expand(batch, -1, -1).contiguous(),
+    }
