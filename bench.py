@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — query images/sec of the OnePose++ 2D-3D matcher hot path on B200.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3            # our CUDA path, one JSON line
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N > 1
+    python bench.py --impl reference --steps K --warmup W      # reference CPU arm (oracle port)
+
+A "step" is one forward of ``OnePosePlus_model`` over a batch of 512x512 query images against a
+5000-point planted descriptor bank (BASELINE.json configs[2]: batch 64 on one GPU; with N GPUs the
+image batch is sharded 64 per GPU = configs[3], weak scaling; the bank is NCCL-broadcast once).
+``value`` is whole-job images/s with inputs resident in HBM; ``e2e`` is the same metric through
+the public ``model(data)`` call with pinned-host inputs (H2D) and match results read back (D2H)
+inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H = W = 512
+N_POINTS = 5000
+N_PLANTED = 3000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-ops", action="store_true", help="print the per-op breakdown to stderr")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[2:6]):
+                if v == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the CPU implementation of the path on the host cores (oracle port)
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import oracle, workload
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    sd = workload.synthetic_state_dict(0)
+    data, _ = workload.planted_workload(sd, H, W, N_POINTS, N_PLANTED, batch=1)
+    sample = 1  # images per step: bounded sample of the batch-64 workload
+
+    def step():
+        d = {k: v.clone() for k, v in data.items()}
+        oracle.forward(sd, d)
+        return d
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d = step()
+    dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "query images/sec (512x512, 5k 3D pts)", "value": val,
+        "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (planted descriptors, seeded weights)",
+        "config": {"workload": "BASELINE configs[2] shape (512x512 images, 5000-pt bank); each step is "
+                               "a bounded sample of 1 image of the batch", "matches_per_image": int(d["b_ids"].numel())},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forwards of 1 image (oracle/oracle.py, torch CPU fp32)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def conv_flops_table(B):
+    """Algorithmic MACs of the tcgen05 conv launches of one backbone pass (true channel counts)."""
+    h2, h4, h8 = (H // 2) * (W // 2), (H // 4) * (W // 4), (H // 8) * (W // 8)
+    macs = 0
+    macs += 4 * h2 * 128 * 128 * 9                                   # layer1
+    macs += h4 * 196 * 128 * 9 + 3 * h4 * 196 * 196 * 9 + h4 * 196 * 128   # layer2 (+downsample)
+    macs += h8 * 256 * 196 * 9 + 3 * h8 * 256 * 256 * 9 + h8 * 256 * 196   # layer3
+    macs += h8 * 256 * 256 + h4 * 256 * 196 + h4 * 256 * 256 * 9 + h4 * 196 * 256 * 9   # fpn 1/4
+    macs += h2 * 196 * 128 + h2 * 196 * 196 * 9 + h2 * 128 * 196 * 9                   # fpn 1/2
+    return 2.0 * macs * B
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    from onepose_plus_plus_b200 import OnePosePlus_model, _lib, parallel
+    from oracle import oracle, workload  # checkpoint + workload generators and the cpu_baseline leg only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+
+    B = args.batch
+    sd = workload.synthetic_state_dict(0)
+    model = OnePosePlus_model(oracle.DEFAULT_CONFIG)
+    model.load_state_dict(sd, strict=True)
+    model = model.eval().to(dev)
+
+    # per-object descriptor bank: built on rank 0, NCCL-broadcast once; every rank
+    # derives its own image shard from the same base image (seeded per rank)
+    data, _ = workload.planted_workload(sd, H, W, N_POINTS, N_PLANTED, batch=1)
+    bank = {k: data[k].to(dev) for k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db")}
+    if world > 1:
+        for k in bank:
+            if rank != 0:
+                bank[k].zero_()          # prove the bank really arrives over NCCL
+        parallel.broadcast_bank(bank, src=0)
+    g = torch.Generator().manual_seed(100 + rank)
+    base = data["query_image"]
+    imgs_host = (base + 0.02 * torch.randn(B, 1, H, W, generator=g)).clamp(0, 1).pin_memory()
+    scale_host = data["query_image_scale"].expand(B, -1).contiguous().pin_memory()
+    bank_host = {k: v.cpu().pin_memory() for k, v in bank.items()}
+
+    def make_data(images, scale, bk):
+        return {"query_image": images, "query_image_scale": scale,
+                "keypoints3d": bk["keypoints3d"].expand(B, -1, -1),
+                "descriptors3d_db": bk["descriptors3d_db"].expand(B, -1, -1),
+                "descriptors3d_coarse_db": bk["descriptors3d_coarse_db"].expand(B, -1, -1)}
+
+    imgs_dev = imgs_host.to(dev)
+    scale_dev = scale_host.to(dev)
+
+    def step_resident():
+        d = make_data(imgs_dev, scale_dev, bank)
+        model(d)
+        return d
+
+    out_host = {}
+
+    def step_e2e():
+        im = imgs_host.to(dev, non_blocking=True)
+        sc = scale_host.to(dev, non_blocking=True)
+        bk = {k: v.to(dev, non_blocking=True) for k, v in bank_host.items()}
+        d = make_data(im, sc, bk)
+        model(d)
+        for k in ("mkpts_3d_db", "mkpts_query_f", "mconf", "m_bids"):
+            out_host[k] = d[k].cpu()
+        return d
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            d = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), d, t0, time.time()
+
+    for _ in range(max(args.warmup, 3)):
+        d = step_resident()
+    _lib.LAUNCHES = 0
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms, d, t0, t1 = timed(step_resident, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    launches = _lib.LAUNCHES
+    m_per_img = d["b_ids"].numel() / B
+
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, d2, _, _ = timed(step_e2e, args.steps)
+    h2d = imgs_host.numel() * 4 + scale_host.numel() * 4 + sum(v.numel() * 4 for v in bank_host.values())
+    d2h = sum(v.numel() * v.element_size() for v in out_host.values())
+
+    # dominant kernel: the tcgen05 implicit-GEMM conv engine (21 launches / forward), timed live
+    # with CUDA events around the backbone on the launching stream
+    conv_ms = None
+    if rank == 0:
+        img_f = imgs_dev.contiguous().float()
+        for _ in range(2):
+            model._backbone(img_f)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            model._backbone(img_f)
+        e1.record()
+        torch.cuda.synchronize()
+        conv_ms = e0.elapsed_time(e1) / 3
+        if args.profile_ops:
+            _lib.profile_ops(lambda: step_resident(), sys.stderr)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        d1, _ = workload.planted_workload(sd, H, W, N_POINTS, N_PLANTED, batch=1)
+        oracle.forward(sd, {k: v.clone() for k, v in d1.items()})
+        n_cpu = 8
+        t = time.perf_counter()
+        for _ in range(n_cpu):
+            oracle.forward(sd, {k: v.clone() for k, v in d1.items()})
+        dt = time.perf_counter() - t
+        cpu = {"value": n_cpu / dt, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_cpu} forwards of 1 image of the same workload (oracle/oracle.py, torch CPU fp32)"}
+
+    if rank == 0:
+        total_imgs = B * world * args.steps
+        flops = conv_flops_table(B)
+        ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+        passes = 3 if model.split else 1
+        line = {
+            "metric": "query images/sec (512x512, 5k 3D pts)",
+            "value": total_imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp16 hi+lo operand pairs, 3 tcgen05 MMAs per K-step, fp32 accumulate (fp32-grade)"
+                     if model.split else "f16",
+            "data": "synthetic (seeded weights, planted descriptor bank, noisy copies of one image)",
+            "config": {"workload": f"BASELINE configs[2]/[3]: batch {B} images 512x512 per GPU vs shared "
+                                   f"5000-pt bank (NCCL-broadcast once when N>1)",
+                       "global_batch": B * world, "matches_per_image": m_per_img,
+                       "l2": "per-step working set (activations >= 1 GB) exceeds the 126 MB L2; no explicit flush",
+                       "conf_matrix": "materialised fp32 every step (reference API)"},
+            "clocks": clocks,
+            "e2e": {"value": total_imgs / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<A_CONV,EpiConv> (21 launches/forward, "
+                         "timed with the conv1/upsample kernels of the backbone)",
+                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": ach / peak_tf if ach else None, "traffic": None, "peak_source": peak_src,
+                         "backbone_ms": conv_ms, "mma_passes": passes,
+                         "issued_tensor_tflops": ach * passes if ach else None,
+                         "issued_frac": ach * passes / peak_tf if ach else None,
+                         "note": "achieved counts ALGORITHMIC conv flops (reference fp32 math, true channel "
+                                 "counts); the fp32-grade mode issues mma_passes x that on the tensor pipe"},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,11 @@
  *     calling thread
  *   - feature maps are NHWC fp16 with the channel count padded to a multiple of 16
  *     (196 -> 208); token tensors are [batch][tokens][channels]
+ *   - `split`: every fp16 tensor that feeds a tensor-core GEMM is stored as two planes along its
+ *     channel axis, row = [hi(C) | lo(C)] with hi = fp16(x), lo = fp16(x - hi); GEMMs then issue
+ *     hi*hi + hi*lo + lo*hi into one fp32 accumulator (fp32-grade result, parity mode).  With
+ *     split = 0 rows are plain fp16 [C] (2^-11 operands; does not meet the 1e-3 parity bar).
+ *     All `ld`/channel counts below are per plane; split = 1 doubles the row length.
  */
 #ifndef OPP_B200_H_
 #define OPP_B200_H_
@@ -35,29 +40,29 @@ int opp_num_sms(void);
 /* conv1 7x7 stride 2 pad 3, 1 -> c_out channels, + folded bn1 + ReLU (resnet.py:101-103,143).
  * image fp32 [B][1][H][W]; w_t fp32 [49][c_out] (tap-major); out NHWC fp16 [B][H/2][W/2][c_out] */
 int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
-                  int h, int w, int c_out, opp_stream_t stream);
+                  int h, int w, int c_out, int split, opp_stream_t stream);
 
 /* 3x3 (pad 1) or 1x1 (pad 0) convolution, stride 1 or 2, as a tcgen05 implicit GEMM
  * (resnet.py:10-17 conv1x1/conv3x3; BasicBlock resnet.py:36-45; FPN heads resnet.py:109-124).
  *   in    NHWC fp16 [B][in_h][in_w][c_in_pad]
- *   w     fp16 [c_out_pad][ksize*ksize][c_in_pad]   (BN-folded, zero in the padding)
+ *   w     fp16 [c_out_pad][planes][ksize*ksize][c_in_pad]   (BN-folded, zero in the padding)
  *   bias  fp32 [c_out_pad]
  *   resid NHWC fp16 [B][out_h][out_w][c_out_pad] added before the activation, or NULL
  *   act   0 none, 1 ReLU, 2 LeakyReLU(slope)
  *   out   NHWC fp16 [B][out_h][out_w][c_out_pad], or NULL when only tokens are wanted
- *   tok32/tok16/pe: when tok32 != NULL also writes  out + pe  as coarse tokens
- *          [B][out_h*out_w][c_out_pad] in fp32 and fp16; pe is fp32 [out_h*out_w][c_out_pad]
+ *   tok/pe: when tok != NULL also writes  out + pe  as coarse tokens
+ *          [B][out_h*out_w][planes*c_out_pad]; pe is fp32 [out_h*out_w][c_out_pad]
  *          (PositionEncodingSine.forward position_encoding.py:37-42 + the 'n c h w -> n (h w) c'
  *          rearrange OnePosePlusModel.py:137-142) */
 int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void* resid,
                     void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
-                    int ksize, int stride, int act, float slope, float* tok32, void* tok16,
-                    const float* pe, opp_stream_t stream);
+                    int ksize, int stride, int act, float slope, void* tok, const float* pe,
+                    int split, opp_stream_t stream);
 
 /* out = a + bilinear_x2(b), align_corners=True (resnet.py:151-152,155-156).
  * a, out NHWC fp16 [B][2h][2w][c]; b NHWC fp16 [B][h][w][c]. out may alias a. */
 int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
-                       opp_stream_t stream);
+                       int split, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3D keypoint encoding — normalize_3d_keypoints (utils/normalize.py:16-26) +
@@ -69,11 +74,11 @@ int opp_kpt_stats(const float* kpts, float* stats, int batch, int n, opp_stream_
 
 /* tokens = desc^T + MLP(normalised kpts); MLP = Linear,IN,ReLU x3 + Linear with per-point
  * instance norm over channels (eps 1e-5).  wN_t are the transposed weights [in][out].
- * kpts fp32 [B][N][3]; desc fp32 [B][256][N]; tok32 fp32 / tok16 fp16 [B][N][256] */
+ * kpts fp32 [B][N][3]; desc fp32 [B][256][N]; tok fp16 [B][N][planes*256] */
 int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, const float* w1_t,
                    const float* b1, const float* w2_t, const float* b2, const float* w3_t,
-                   const float* b3, const float* w4_t, const float* b4, float* tok32, void* tok16,
-                   int batch, int n, opp_stream_t stream);
+                   const float* b3, const float* w4_t, const float* b4, void* tok, int batch, int n,
+                   int split, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Transformer — LoFTREncoderLayer.forward (loftr_module/transformer.py:65-94) and
@@ -85,34 +90,38 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
  * Used for [k_proj;v_proj] (transformer.py:78-79 + linear_attention.py:46), mlp.0 + ReLU
  * (transformer.py:41-45,91) and the fine-level q/k/v projections. a1 may be NULL (k1 = 0). */
 int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
-                       long long rows, int n, int act, int act_cols, opp_stream_t stream);
+                       long long rows, int n, int act, int act_cols, int split,
+                       opp_stream_t stream);
 
 /* q_proj + feature map + normaliser (transformer.py:77, linear_attention.py:45,58):
  * out = Q * v_len / (Q . ksum_head + eps), Q = elu(x @ wq^T) + 1, heads of 32 channels.
  * x fp16 [B][rows][256]; ksum fp32 [B][256]; out fp16 [B][rows][256] */
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
-                     int rows, int d_model, float v_len, float eps, opp_stream_t stream);
+                     int rows, int d_model, float v_len, float eps, int split,
+                     opp_stream_t stream);
 
 /* y = LayerNorm(concat_K(a0,a1) @ w^T) [+ resid]  (transformer.py:85-94).
- * w fp16 [n][k] or, when w_batched, [B][n][k] (the per-image  blockdiag(KV) @ merge^T  matrix).
- * out32 fp32 / out16 fp16 [B*rows][n] (either may be NULL); split (or NULL) receives the 2-term
- * fp16 split of y as [B*rows][3n]: kind 1 = [hi|hi|lo], kind 2 = [hi|lo|hi]. */
+ * w fp16 [n][planes*k] or, when w_batched, [B][n][planes*k] (the per-image
+ * blockdiag(KV) @ merge^T  matrix).  resid / out16 fp16 [B*rows][planes*n]; out32 fp32
+ * [B*rows][n]; either output may be NULL. */
 int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w, int w_batched,
-                  const float* gamma, const float* beta, float eps, const float* resid,
-                  float* out32, void* out16, void* split, int split_kind, int batches,
-                  long long rows, int n, opp_stream_t stream);
+                  const float* gamma, const float* beta, float eps, const void* resid,
+                  void* out16, float* out32, int batches, long long rows, int n, int split,
+                  opp_stream_t stream);
 
 /* Source side state of linear attention (linear_attention.py:55-57):
- * kv16 fp16 [B][S][2d] holds K' = elu(k)+1 in columns [0,d) and V in [d,2d).
- * part fp32 [B][chunks][H][33][32], chunks = ceil(S/256): per-chunk sum_s K'^T V (rows 0..31) and
- * sum_s K' (row 32) for each of the H = d/32 heads. */
-int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, opp_stream_t stream);
+ * kv16 fp16 [B][S][planes*2d] holds K' = elu(k)+1 in columns [0,d) and V in [d,2d) of each plane.
+ * part fp32 [B][chunks][H][33][32], chunks = opp_kv_chunks(S): per-chunk sum_s K'^T V (rows 0..31)
+ * and sum_s K' (row 32) for each of the H = d/32 heads. */
+int opp_kv_chunks(int s);
+int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
+                   opp_stream_t stream);
 
 /* Reduces the chunk partials, scales KV by 1/v_len and folds the merge projection
  * (transformer.py:85): mt[b][c][h*32+dd] = sum_v merge_w[c][h*32+v] * KV[b][h][dd][v] / v_len.
- * merge_w fp32 [d][d]; mt fp16 [B][d][d]; ksum fp32 [B][d]. */
+ * merge_w fp32 [d][d]; mt fp16 [B][d][planes*d]; ksum fp32 [B][d]. */
 int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ksum, int batch,
-                    int chunks, int d, float v_len, opp_stream_t stream);
+                    int chunks, int d, float v_len, int split, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Coarse matching — CoarseMatching.forward / get_coarse_match
@@ -122,9 +131,10 @@ int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ks
 int opp_sim_tiles(int cols); /* column tiles used by the two calls below */
 
 /* per-row partial (max, sum exp) of sim = scale * a @ b^T over each column tile.
- * a fp16 [B][rows][k], b fp16 [B][cols][k]; part_m/part_s fp32 [B*rows][opp_sim_tiles(cols)] */
+ * a fp16 [B][rows][planes*k], b fp16 [B][cols][planes*k];
+ * part_m/part_s fp32 [B*rows][opp_sim_tiles(cols)] */
 int opp_sim_lse(const void* a, const void* b, float* part_m, float* part_s, int batches, int rows,
-                int cols, int k, float scale, opp_stream_t stream);
+                int cols, int k, float scale, int split, opp_stream_t stream);
 
 /* lse[r] = logsumexp over tiles */
 int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long long rows,
@@ -134,7 +144,7 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
  * argmax); conf (or NULL) fp32 [B*rows][cols] is data["conf_matrix"] when rows are 3D points. */
 int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float* lse_other,
                  int own_is_pt, float* conf, float* part_val, int* part_idx, int batches,
-                 int rows, int cols, int k, float scale, opp_stream_t stream);
+                 int rows, int cols, int k, float scale, int split, opp_stream_t stream);
 
 /* best[r] = max over tiles (ties -> lowest index) */
 int opp_best_finalize(const float* part_val, const int* part_idx, float* best_val, int* best_idx,
@@ -160,16 +170,17 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
 
 /* For match m: row 26m = descriptors3d_db[b, :, i]; rows 26m+1+ww = the 5x5 window (ww = ky*5+kx)
  * of the fine map centred on fine pixel (stride*jy, stride*jx), zero outside the map.
- * fine NHWC fp16 [B][hf][wf][128]; desc3d fp32 [B][128][n]; x32 fp32 / x16 fp16 [26 M][128] */
+ * fine NHWC fp16 [B][hf][wf][planes*128]; desc3d fp32 [B][128][n];
+ * x32 fp32 [26 M][128] (may be NULL) / x16 fp16 [26 M][planes*128] */
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
-                    int hf, int wf, int wc, int stride, int n, opp_stream_t stream);
+                    int hf, int wf, int wc, int stride, int n, int split, opp_stream_t stream);
 
 /* Linear attention for the 1 + 25 tokens of each match (linear_attention.py:29-61 with
- * L,S in {1,25}).  qkv fp16 [26 M][384] = (elu(q)+1 | elu(k)+1 | v), 8 heads of 16.
+ * L,S in {1,25}).  qkv fp16 [26 M][planes*384] = (elu(q)+1 | elu(k)+1 | v), 8 heads of 16.
  * cross = 0: self layer (each sequence attends to itself); 1: cross layer, both directions from
- * the pre-update tensors (transformer.py:154-159).  msg fp16 [26 M][128] */
-int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps,
+ * the pre-update tensors (transformer.py:154-159).  msg fp16 [26 M][planes*128] */
+int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, int split,
                        opp_stream_t stream);
 
 /* Correlation softmax + expectation + std (fine_matching.py:78-94) and sub-pixel coordinates

@@ -1,0 +1,9 @@
+"""onepose_plus_plus_b200 — B200 (sm_100a) implementation of the OnePose++ 2D-3D matcher hot path.
+
+``OnePosePlus_model`` mirrors the reference class of the same name
+(src/models/OnePosePlus/OnePosePlusModel.py) and runs on hand-written CUDA kernels through the
+C ABI in ``include/opp_b200.h``.
+"""
+from .model import OnePosePlus_model, build_backbone  # noqa: F401
+
+__version__ = "0.1.0"

@@ -265,4 +265,39 @@ __device__ __forceinline__ void load_half8(const __half* src, float* v) {
 
 __device__ __forceinline__ float elu_plus_one(float x) { return x > 0.f ? x + 1.f : expf(x); }
 
+// ---------------------------------------------------------------------------------------------
+// split-precision activations.  Every tensor that feeds a tensor-core GEMM is stored as a pair of
+// fp16 planes along its channel axis: [hi(C) | lo(C)], hi = fp16(x), lo = fp16(x - hi), so that
+// hi + lo carries ~22 mantissa bits.  `lo_off` is the element offset of the lo plane inside a row
+// (0 = plain fp16 storage, no lo plane).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_split8(__half* row, int col, const float* v, int lo_off) {
+  store_half8(row + col, v);
+  if (lo_off) {
+    float lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lo[j] = v[j] - __half2float(__float2half_rn(v[j]));
+    store_half8(row + lo_off + col, lo);
+  }
+}
+__device__ __forceinline__ void load_split8(const __half* row, int col, float* v, int lo_off) {
+  load_half8(row + col, v);
+  if (lo_off) {
+    float lo[8];
+    load_half8(row + lo_off + col, lo);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += lo[j];
+  }
+}
+__device__ __forceinline__ float load_split1(const __half* row, int col, int lo_off) {
+  float v = __half2float(row[col]);
+  if (lo_off) v += __half2float(row[lo_off + col]);
+  return v;
+}
+__device__ __forceinline__ void store_split1(__half* row, int col, float v, int lo_off) {
+  const __half h = __float2half_rn(v);
+  row[col] = h;
+  if (lo_off) row[lo_off + col] = __float2half_rn(v - __half2float(h));
+}
+
 }  // namespace opp

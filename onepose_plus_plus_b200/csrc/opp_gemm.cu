@@ -100,8 +100,8 @@ static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long ro
 template <int A_MODE, class Epi>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream) {
-  s.stages = gemm_pick_stages(s.block_n, s.k_chunks);
-  const int smem = gemm_smem_bytes(s.stages, s.block_n);
+  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split);
+  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split);
   auto kern = gemm_kernel<A_MODE, Epi>;
   static bool attr_set = false;  // one per template instantiation
   if (!attr_set) {
@@ -124,15 +124,17 @@ static int pick_block_n(int n) {
   return 256;
 }
 
-// common shape / map setup for token-row GEMMs
+// common shape / map setup for token-row GEMMs.  With split, every operand row holds two planes:
+// A_i rows are [hi(k_i) | lo(k_i)], W rows are [hi(k0+k1) | lo(k0+k1)].
 static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, const void* a1,
                       int k1, const void* w, int w_batched, int batches, long long rows, int n,
-                      int n_align = 16) {
+                      int split, int n_align = 16) {
   OPP_REQUIRE(a0 && w, "null operand");
   OPP_REQUIRE(k0 > 0 && k0 % 64 == 0 && k1 % 64 == 0, "K (%d,%d) must be multiples of 64", k0,
               k1);
   OPP_REQUIRE(n > 0 && n % n_align == 0, "N=%d must be a multiple of %d", n, n_align);
   OPP_REQUIRE(batches > 0 && rows > 0, "empty GEMM");
+  const int planes = split ? 2 : 1;
   memset(&s, 0, sizeof(s));
   s.batches = batches;
   s.rows = (int)rows;
@@ -144,18 +146,23 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   s.k_chunks_a0 = k0 / 64;
   s.k_chunks = (k0 + k1) / 64;
   s.b_batched = w_batched;
-  int rc = map_rows(&maps.a[0], a0, k0, rows, batches, k0, rows * (long long)k0, kBlockM);
+  s.split = split ? 1 : 0;
+  s.a0_lo = k0;
+  s.a1_lo = k1;
+  s.b_lo = k0 + k1;
+  const long long ld0 = (long long)planes * k0, ld1 = (long long)planes * k1;
+  int rc = map_rows(&maps.a[0], a0, ld0, rows, batches, ld0, rows * ld0, kBlockM);
   if (rc) return rc;
   if (k1 > 0) {
     OPP_REQUIRE(a1, "null second A operand");
-    rc = map_rows(&maps.a[1], a1, k1, rows, batches, k1, rows * (long long)k1, kBlockM);
+    rc = map_rows(&maps.a[1], a1, ld1, rows, batches, ld1, rows * ld1, kBlockM);
     if (rc) return rc;
   } else {
     maps.a[1] = maps.a[0];
   }
   maps.a[2] = maps.a[0];
   maps.a[3] = maps.a[0];
-  const long long kt = k0 + k1;
+  const long long kt = (long long)planes * (k0 + k1);
   return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt, s.block_n);
 }
 
@@ -168,49 +175,53 @@ extern "C" {
 const char* opp_last_error(void) { return opp::last_error(); }
 
 int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
-                       long long rows, int n, int act, int act_cols, opp_stream_t stream) {
+                       long long rows, int n, int act, int act_cols, int split,
+                       opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, split);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
-  EpiStoreF16::Params ep{(__half*)out, (long long)n, act, act_cols};
+  EpiStoreF16::Params ep{(__half*)out, (long long)n * (split ? 2 : 1), split ? n : 0, act,
+                         act_cols};
   return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
 }
 
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
-                     int rows, int d_model, float v_len, float eps, opp_stream_t stream) {
+                     int rows, int d_model, float v_len, float eps, int split,
+                     opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(d_model == 256, "opp_linear_q_f16 supports d_model 256 (8 heads x 32), got %d",
               d_model);
-  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model);
+  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model, split);
   if (rc) return rc;
   OPP_REQUIRE(ksum && out, "null pointer");
-  EpiQ::Params ep{(__half*)out, (long long)d_model, ksum, v_len, eps};
+  EpiQ::Params ep{(__half*)out, (long long)d_model * (split ? 2 : 1), split ? d_model : 0, ksum,
+                  v_len, eps};
   return launch<A_ROWS, EpiQ>(maps, s, ep, (cudaStream_t)stream);
 }
 
 int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w, int w_batched,
-                  const float* gamma, const float* beta, float eps, const float* resid,
-                  float* out32, void* out16, void* split, int split_kind, int batches,
-                  long long rows, int n, opp_stream_t stream) {
+                  const float* gamma, const float* beta, float eps, const void* resid,
+                  void* out16, float* out32, int batches, long long rows, int n, int split,
+                  opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(n == 128 || n == 256, "LayerNorm epilogue needs N in {128,256}, got %d", n);
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, w_batched, batches, rows, n);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, w_batched, batches, rows, n, split);
   if (rc) return rc;
   OPP_REQUIRE(gamma && beta, "null LayerNorm parameters");
-  OPP_REQUIRE(split == nullptr || split_kind == 1 || split_kind == 2, "bad split_kind");
-  EpiLN::Params ep{gamma, beta, eps, resid, out32, (__half*)out16, (long long)n, (__half*)split,
-                   split_kind};
+  OPP_REQUIRE(out16 || out32, "no output requested");
+  EpiLN::Params ep{gamma, beta, eps, (const __half*)resid, (__half*)out16,
+                   (long long)n * (split ? 2 : 1), split ? n : 0, out32};
   return launch<A_ROWS, EpiLN>(maps, s, ep, (cudaStream_t)stream);
 }
 
 int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void* resid,
                     void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
-                    int ksize, int stride, int act, float slope, float* tok32, void* tok16,
-                    const float* pe, opp_stream_t stream) {
+                    int ksize, int stride, int act, float slope, void* tok, const float* pe,
+                    int split, opp_stream_t stream) {
   OPP_REQUIRE(in && w && bias, "null operand");
   OPP_REQUIRE(ksize == 1 || ksize == 3, "kernel size %d unsupported (1 or 3)", ksize);
   OPP_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
@@ -218,7 +229,8 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
               "channel counts must be padded to multiples of 16 (got %d -> %d)", c_in_pad,
               c_out_pad);
   OPP_REQUIRE(stride == 1 || (in_h % 2 == 0 && in_w % 2 == 0), "stride 2 needs even H, W");
-  OPP_REQUIRE(out || tok32, "no output requested");
+  OPP_REQUIRE(out || tok, "no output requested");
+  const int planes = split ? 2 : 1;
   const int pad = ksize / 2;
   const int out_h = (in_h + 2 * pad - ksize) / stride + 1;
   const int out_w = (in_w + 2 * pad - ksize) / stride + 1;
@@ -243,7 +255,8 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   s.conv_stride = stride;
   s.out_w = out_w;
   s.out_h = out_h;
-  const long long C = c_in_pad;
+  s.split = split ? 1 : 0;
+  const long long C = (long long)planes * c_in_pad;  // pixel stride in elements
   const __half* base = (const __half*)in;
   int rc;
   if (stride == 1) {
@@ -266,19 +279,21 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
         if (rc) return rc;
       }
   }
-  const long long kt = (long long)ksize * ksize * c_in_pad;
+  const long long kplane = (long long)ksize * ksize * c_in_pad;
+  s.b_lo = (int)kplane;
+  const long long kt = kplane * planes;
   rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n);
   if (rc) return rc;
-  EpiConv::Params ep{(__half*)out, (long long)c_out_pad, bias, (const __half*)resid, act, slope,
-                     tok32,        (__half*)tok16,       pe};
+  EpiConv::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias,
+                     (const __half*)resid, act, slope, (__half*)tok, pe};
   return launch<A_CONV, EpiConv>(maps, s, ep, (cudaStream_t)stream);
 }
 
 int opp_sim_lse(const void* a, const void* b, float* part_m, float* part_s, int batches, int rows,
-                int cols, int k, float scale, opp_stream_t stream) {
+                int cols, int k, float scale, int split, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, 1);
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
   if (rc) return rc;
   EpiLse::Params ep{part_m, part_s, scale};
   return launch<A_ROWS, EpiLse>(maps, s, ep, (cudaStream_t)stream);
@@ -286,10 +301,10 @@ int opp_sim_lse(const void* a, const void* b, float* part_m, float* part_s, int 
 
 int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float* lse_other,
                  int own_is_pt, float* conf, float* part_val, int* part_idx, int batches,
-                 int rows, int cols, int k, float scale, opp_stream_t stream) {
+                 int rows, int cols, int k, float scale, int split, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, 1);
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
   if (rc) return rc;
   EpiConf::Params ep{lse_own, lse_other, scale, own_is_pt, conf, part_val, part_idx};
   return launch<A_ROWS, EpiConf>(maps, s, ep, (cudaStream_t)stream);

@@ -3,8 +3,16 @@
 // D[M,N] = A[M,K] * W[N,K]^T on tcgen05 (fp16 operands, fp32 accumulators in TMEM), operands
 // staged by TMA into 128B-swizzled shared memory through an mbarrier ring, persistent over
 // output tiles with a double-buffered TMEM accumulator so the epilogue of tile i overlaps the
-// MMAs of tile i+1.  The A operand is either
-//   A_ROWS : token rows  [batch][rows][K]   (up to two arrays concatenated along K), or
+// MMAs of tile i+1.
+//
+// Precision: the reference computes in fp32 and the parity bar is 1e-3 on outputs whose logits
+// reach ~1e2, so single fp16 operands (2^-11) are not enough.  In `split` mode every operand is a
+// pair of fp16 planes  x = hi + lo  (see opp_common.cuh) and each K-step issues three MMAs into
+// the same accumulator:  hi*hi + hi*lo + lo*hi  (the dropped lo*lo term is ~2^-22), i.e. an
+// fp32-grade GEMM at 3 tensor-core passes and 2x operand bytes.  split = 0 is plain fp16.
+//
+// The A operand is either
+//   A_ROWS : token rows  [batch][rows][planes*K]  (up to two arrays concatenated along K), or
 //   A_CONV : an NHWC feature map read as an implicit-GEMM im2col: for every filter tap the TMA
 //            box is the output tile shifted by the tap offset; out-of-bounds coordinates are
 //            zero-filled by the TMA unit, which implements the convolution padding for free.
@@ -44,14 +52,17 @@ struct GemmShape {
   int n_tiles;
   int n_total;      // valid output columns
   int block_n;      // UMMA N (multiple of 16, <= 256)
-  int k_chunks;     // number of 64-wide K chunks per tile
+  int k_chunks;     // number of 64-wide K chunks per tile (per plane)
   int stages;
   int b_batched;    // W operand has a leading batch dim
+  int split;        // operands are (hi|lo) plane pairs; 3 MMAs per K-step
+  int b_lo;         // element offset of W's lo plane inside a row (= K total)
   // A_ROWS
   int k_chunks_a0;  // chunks read through maps.a[0]; the rest through maps.a[1]
+  int a0_lo, a1_lo; // element offsets of the lo planes of the two A arrays (= their K)
   // A_CONV
   int conv_cchunks; // K chunks per filter tap
-  int conv_c;       // padded input channels (multiple of 16)
+  int conv_c;       // padded input channels (multiple of 16); also the lo-plane offset
   int conv_kw;      // filter width/height (1 or 3)
   int conv_pad;
   int conv_stride;  // 1 or 2
@@ -75,15 +86,17 @@ struct EpiCtx {
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, 128); }
 
 // =============================================================================================
-// Epilogues
+// Epilogues.  Outputs that feed later GEMMs are written as (hi|lo) plane pairs when
+// `out_lo` != 0: row layout [hi(n_total) | lo(n_total)], out_lo = n_total.
 // =============================================================================================
 
-// Plain fp16 store with an optional activation on the leading `act_cols` columns.
+// Plain store with an optional activation on the leading `act_cols` columns.
 //   act 1 = ReLU  (transformer.py:41-45 mlp ReLU), act 2 = elu(x)+1 (linear_attention.py:10-11)
 struct EpiStoreF16 {
   struct Params {
     __half* out;
-    long long ld;
+    long long ld;   // row stride in elements
+    int out_lo;     // 0 or n_total
     int act;
     int act_cols;
   };
@@ -100,10 +113,10 @@ struct EpiStoreF16 {
         }
       }
       if (c.valid) {
-        __half* dst = p.out + c.grow * p.ld + g0;
+        __half* row = p.out + c.grow * p.ld;
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (col + g * 8 < c.ncols) store_half8(dst + g * 8, v + g * 8);
+          if (col + g * 8 < c.ncols) store_split8(row, g0 + g * 8, v + g * 8, p.out_lo);
       }
     }
   }
@@ -112,11 +125,12 @@ struct EpiStoreF16 {
 // Query side of linear attention (linear_attention.py:45,58-59): Q = elu(q)+1,
 // Z = 1/(Q . Ksum + eps), output Q * Z * v_length per head of 32 channels.  The matching KV
 // state is pre-divided by v_length (linear_attention.py:55-56), so (Q*Z*v_length) @ (KV/v_length)
-// reproduces the reference product without leaving fp16 range.
+// reproduces the reference product.
 struct EpiQ {
   struct Params {
     __half* out;
     long long ld;
+    int out_lo;
     const float* ksum;  // [batches][n_total]
     float v_len;
     float eps;
@@ -139,29 +153,26 @@ struct EpiQ {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= z;
       if (c.valid) {
-        __half* dst = p.out + c.grow * p.ld + c.n0 + col;
+        __half* row = p.out + c.grow * p.ld;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) store_half8(dst + g * 8, v + g * 8);
+        for (int g = 0; g < 4; ++g) store_split8(row, c.n0 + col + g * 8, v + g * 8, p.out_lo);
       }
     }
   }
 };
 
-// LayerNorm over the full output row (the tile spans all N columns), optional residual add,
-// fp32 master + fp16 shadow outputs (transformer.py:86-94: norm1 after merge; norm2 then x+msg).
-// `split` additionally writes the 2-term fp16 split of the fp32 result, laid out as three
-// K-blocks so that [hi|hi|lo] . [hi|lo|hi] = hi*hi + hi*lo + lo*hi (coarse similarity operands).
+// LayerNorm over the full output row (the tile spans all N columns), optional residual add
+// (transformer.py:86-94: norm1 after merge; norm2 then x + msg).
 struct EpiLN {
   struct Params {
     const float* gamma;
     const float* beta;
     float eps;
-    const float* resid;  // fp32 [rows][ld] or null
-    float* out32;        // or null
-    __half* out16;       // or null
+    const __half* resid;  // same layout as out16 (ld, out_lo) or null
+    __half* out16;        // or null
     long long ld;
-    __half* split;       // or null; row stride 3*n_total
-    int split_kind;      // 1: [hi|hi|lo]   2: [hi|lo|hi]
+    int out_lo;
+    float* out32;         // fp32 [rows][n_total] or null
   };
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     float* g_s = c.smem;
@@ -198,42 +209,26 @@ struct EpiLN {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g_s[col + j] + b_s[col + j];
       if (!c.valid) continue;
-      const long long off = c.grow * p.ld + col;
       if (p.resid) {
-        const float4* r4 = reinterpret_cast<const float4*>(p.resid + off);
+        const __half* rrow = p.resid + c.grow * p.ld;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 r = r4[g];
-          v[4 * g + 0] += r.x;
-          v[4 * g + 1] += r.y;
-          v[4 * g + 2] += r.z;
-          v[4 * g + 3] += r.w;
+        for (int g = 0; g < 4; ++g) {
+          float r[8];
+          load_split8(rrow, col + g * 8, r, p.out_lo);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[g * 8 + j] += r[j];
         }
       }
       if (p.out32) {
-        float4* o4 = reinterpret_cast<float4*>(p.out32 + off);
+        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + col);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           o4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
       }
       if (p.out16) {
+        __half* row = p.out16 + c.grow * p.ld;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) store_half8(p.out16 + off + g * 8, v + g * 8);
-      }
-      if (p.split) {
-        float lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) lo[j] = v[j] - __half2float(__float2half_rn(v[j]));
-        const int n = s.n_total;
-        __half* base = p.split + c.grow * (3LL * n) + col;
-        __half* d_hi2 = base + (p.split_kind == 1 ? n : 2 * n);
-        __half* d_lo = base + (p.split_kind == 1 ? 2 * n : n);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          store_half8(base + g * 8, v + g * 8);
-          store_half8(d_hi2 + g * 8, v + g * 8);
-          store_half8(d_lo + g * 8, lo + g * 8);
-        }
+        for (int g = 0; g < 4; ++g) store_split8(row, col + g * 8, v + g * 8, p.out_lo);
       }
     }
   }
@@ -244,14 +239,14 @@ struct EpiLN {
 // (position_encoding.py:37-42 + OnePosePlusModel.py:137-142: NHWC *is* 'n (h w) c').
 struct EpiConv {
   struct Params {
-    __half* out;          // NHWC fp16, channel stride ld (or null)
+    __half* out;          // NHWC, pixel stride ld (or null)
     long long ld;
+    int out_lo;
     const float* bias;    // [n_total]
-    const __half* resid;  // NHWC fp16 with the same ld, or null
+    const __half* resid;  // same layout as out, or null
     int act;              // 0 none, 1 relu, 2 leaky relu
     float slope;
-    float* tok32;         // [B*H*W][n_total] or null
-    __half* tok16;
+    __half* tok;          // [B*H*W] rows with the same (ld, out_lo) layout, or null
     const float* pe;      // [H*W][n_total]
   };
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
@@ -263,7 +258,6 @@ struct EpiConv {
       tmem_ld32(c.tmem + col, v);
       if (!c.valid) continue;
       const int g0 = c.n0 + col;
-      const long long off = c.grow * p.ld + g0;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (col + g * 8 >= c.ncols) break;
@@ -272,7 +266,7 @@ struct EpiConv {
         for (int j = 0; j < 8; ++j) vv[j] += c.smem[col + g * 8 + j];
         if (p.resid) {
           float r[8];
-          load_half8(p.resid + off + g * 8, r);
+          load_split8(p.resid + c.grow * p.ld, g0 + g * 8, r, p.out_lo);
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] += r[j];
         }
@@ -283,17 +277,13 @@ struct EpiConv {
 #pragma unroll
           for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * p.slope;
         }
-        if (p.out) store_half8(p.out + off + g * 8, vv);
-        if (p.tok32) {
-          const long long toff = c.grow * s.n_total + g0 + g * 8;
+        if (p.out) store_split8(p.out + c.grow * p.ld, g0 + g * 8, vv, p.out_lo);
+        if (p.tok) {
           const float* pe = p.pe + (long long)c.row * s.n_total + g0 + g * 8;
           float t[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) t[j] = vv[j] + pe[j];
-          float4* o4 = reinterpret_cast<float4*>(p.tok32 + toff);
-          o4[0] = make_float4(t[0], t[1], t[2], t[3]);
-          o4[1] = make_float4(t[4], t[5], t[6], t[7]);
-          store_half8(p.tok16 + toff, t);
+          store_split8(p.tok + c.grow * p.ld, g0 + g * 8, t, p.out_lo);
         }
       }
     }
@@ -401,10 +391,13 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int b_bytes = s.block_n * kBlockK * 2;
+  const int planes = s.split ? 2 : 1;
+  const int b_bytes = s.block_n * kBlockK * 2;   // one plane of the W tile
+  const int a_stage = kABytes * planes;
+  const int b_stage = b_bytes * planes;
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + s.stages * kABytes;
-  float* epi_smem = reinterpret_cast<float*>(smem_b + s.stages * b_bytes);
+  uint8_t* smem_b = smem + s.stages * a_stage;
+  float* epi_smem = reinterpret_cast<float*>(smem_b + s.stages * b_stage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_smem) +
                                                kEpiSmemBytes);
   uint64_t* full = bars;
@@ -462,15 +455,18 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
         }
         for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], kABytes + b_bytes);
-          uint8_t* sa = smem_a + stage * kABytes;
-          uint8_t* sb = smem_b + stage * b_bytes;
+          mbar_expect_tx(&full[stage], a_stage + b_stage);
+          uint8_t* sa = smem_a + stage * a_stage;
+          uint8_t* sb = smem_b + stage * b_stage;
           int kb;
           if (A_MODE == A_ROWS) {
             const bool first = chunk < s.k_chunks_a0;
-            const int kc = first ? chunk : chunk - s.k_chunks_a0;
-            tma_load_3d(first ? &maps.a[0] : &maps.a[1], &full[stage], sa, kc * kBlockK,
-                        m_tile * kBlockM, b);
+            const int kc = (first ? chunk : chunk - s.k_chunks_a0) * kBlockK;
+            const CUtensorMap* am = first ? &maps.a[0] : &maps.a[1];
+            tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
+            if (s.split)
+              tma_load_3d(am, &full[stage], sa + kABytes, kc + (first ? s.a0_lo : s.a1_lo),
+                          m_tile * kBlockM, b);
             kb = chunk * kBlockK;
           } else {
             const int tap = chunk / s.conv_cchunks;
@@ -485,9 +481,15 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
               mi = py * 2 + px;
             }
             tma_load_4d(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
+            if (s.split)
+              tma_load_4d(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
+                          ox0 + dx, oy0 + dy, b);
             kb = tap * s.conv_c + cc * kBlockK;
           }
-          tma_load_3d(&maps.b, &full[stage], sb, kb, n_tile * s.block_n, s.b_batched ? b : 0);
+          const int bb = s.b_batched ? b : 0;
+          tma_load_3d(&maps.b, &full[stage], sb, kb, n_tile * s.block_n, bb);
+          if (s.split)
+            tma_load_3d(&maps.b, &full[stage], sb + b_bytes, s.b_lo + kb, n_tile * s.block_n, bb);
           if (++stage == s.stages) {
             stage = 0;
             phase ^= 1;
@@ -517,11 +519,18 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
             const int rem = (s.conv_c - cc * kBlockK) >> 4;
             ksteps = rem < 4 ? rem : 4;
           }
-          const uint64_t a_desc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * kABytes));
-          const uint64_t b_desc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * b_bytes));
-          for (int k = 0; k < ksteps; ++k) {
-            // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-            tc_mma_f16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (chunk | k) != 0);
+          const uint32_t sa = smem_u32(smem_a + stage * a_stage);
+          const uint32_t sb = smem_u32(smem_b + stage * b_stage);
+          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+          const uint64_t b_hi = make_kmajor_sw128_desc(sb);
+          // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+          for (int k = 0; k < ksteps; ++k)
+            tc_mma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (chunk | k) != 0);
+          if (s.split) {
+            const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes);
+            const uint64_t b_lo = make_kmajor_sw128_desc(sb + b_bytes);
+            for (int k = 0; k < ksteps; ++k) tc_mma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
+            for (int k = 0; k < ksteps; ++k) tc_mma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
           }
           tc_commit(&empty[stage]);
           if (++stage == s.stages) {
@@ -581,12 +590,15 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
 }
 
 // dynamic shared memory a launch needs (ring + epilogue scratch + barriers + alignment slack)
-inline int gemm_smem_bytes(int stages, int block_n) {
-  return stages * (kABytes + block_n * kBlockK * 2) + kEpiSmemBytes + (2 * kMaxStages + 4) * 8 +
-         16 + 1024;
+inline int gemm_stage_bytes(int block_n, int split) {
+  return (kABytes + block_n * kBlockK * 2) * (split ? 2 : 1);
 }
-inline int gemm_pick_stages(int block_n, int k_chunks) {
-  int st = (227 * 1024 - kEpiSmemBytes - 2048) / (kABytes + block_n * kBlockK * 2);
+inline int gemm_smem_bytes(int stages, int block_n, int split) {
+  return stages * gemm_stage_bytes(block_n, split) + kEpiSmemBytes + (2 * kMaxStages + 4) * 8 + 16 +
+         1024;
+}
+inline int gemm_pick_stages(int block_n, int k_chunks, int split) {
+  int st = (227 * 1024 - kEpiSmemBytes - 2048) / gemm_stage_bytes(block_n, split);
   if (st > kMaxStages) st = kMaxStages;
   if (st > k_chunks * 2 && k_chunks * 2 >= 2) st = k_chunks * 2;
   return st < 2 ? 2 : st;

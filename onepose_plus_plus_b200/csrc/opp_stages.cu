@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict_
                                                         const float* __restrict__ w_t,
                                                         const float* __restrict__ bias,
                                                         __half* __restrict__ out, int H, int W,
-                                                        int C) {
+                                                        int C, int lo_off) {
   extern __shared__ float sm[];
   float* w_s = sm;                 // [49][C]
   float* b_s = w_s + 49 * C;       // [C]
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict_
 #pragma unroll
     for (int kx = 0; kx < 7; ++kx) x[ky * 7 + kx] = p_s[(2 * ly + ky) * P + 2 * lx + kx];
   if (oy >= OH || ox >= OW) return;
-  __half* dst = out + (((long long)b * OH + oy) * OW + ox) * C;
+  __half* dst = out + (((long long)b * OH + oy) * OW + ox) * (lo_off ? 2 * C : C);
   for (int c0 = 0; c0 < C; c0 += 8) {
     float acc[8];
 #pragma unroll
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict_
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    store_half8(dst + c0, acc);
+    store_split8(dst, c0, acc, lo_off);
   }
 }
 
@@ -80,8 +80,9 @@ __global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) upsample2x_add_kernel(const __half* __restrict__ a,
                                                              const __half* __restrict__ bsrc,
                                                              __half* __restrict__ out, int B,
-                                                             int h, int w, int C) {
+                                                             int h, int w, int C, int lo_off) {
   const int cg = C / 8;
+  const int ld = lo_off ? 2 * C : C;
   const long long total = (long long)B * (2 * h) * (2 * w) * cg;
   const float sy = (float)(h - 1) / (float)(2 * h - 1);
   const float sx = (float)(w - 1) / (float)(2 * w - 1);
@@ -98,18 +99,18 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const __half* __res
     const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
     const float ly = fy - (float)y0, lx = fx - (float)x0;
     const float hy = 1.f - ly, hx = 1.f - lx;
-    const __half* base = bsrc + (long long)b * h * w * C + c8 * 8;
+    const __half* base = bsrc + (long long)b * h * w * ld;
     float v00[8], v01[8], v10[8], v11[8], va[8], r[8];
-    load_half8(base + ((long long)y0 * w + x0) * C, v00);
-    load_half8(base + ((long long)y0 * w + x1) * C, v01);
-    load_half8(base + ((long long)y1 * w + x0) * C, v10);
-    load_half8(base + ((long long)y1 * w + x1) * C, v11);
-    const long long off = (((long long)b * 2 * h + y) * (2 * w) + x) * C + c8 * 8;
-    load_half8(a + off, va);
+    load_split8(base + ((long long)y0 * w + x0) * ld, c8 * 8, v00, lo_off);
+    load_split8(base + ((long long)y0 * w + x1) * ld, c8 * 8, v01, lo_off);
+    load_split8(base + ((long long)y1 * w + x0) * ld, c8 * 8, v10, lo_off);
+    load_split8(base + ((long long)y1 * w + x1) * ld, c8 * 8, v11, lo_off);
+    const long long off = (((long long)b * 2 * h + y) * (2 * w) + x) * ld;
+    load_split8(a + off, c8 * 8, va, lo_off);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       r[j] = va[j] + (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]));
-    store_half8(out + off, r);
+    store_split8(out + off, c8 * 8, r, lo_off);
   }
 }
 
@@ -220,8 +221,7 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
                   const float* __restrict__ b1, const float* __restrict__ w2_t,
                   const float* __restrict__ b2, const float* __restrict__ w3_t,
                   const float* __restrict__ b3, const float* __restrict__ w4_t,
-                  const float* __restrict__ b4, float* __restrict__ tok32,
-                  __half* __restrict__ tok16, int n) {
+                  const float* __restrict__ b4, __half* __restrict__ tok, int n, int lo_off) {
   __shared__ float buf_a[kKeP * 129];   // holds [P][3], [P][64+1] ... reused
   __shared__ float buf_b[kKeP * 257];
   const int b = blockIdx.y;
@@ -273,12 +273,8 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
   for (int i = threadIdx.x; i < kKeP * 256; i += 256) {
     const int p = i / 256, c = i % 256;
     const int gp = p0 + p;
-    if (gp < n) {
-      const float v = buf_b[p * 257 + c];
-      const long long o = ((long long)b * n + gp) * 256 + c;
-      tok32[o] = v;
-      tok16[o] = __float2half_rn(v);
-    }
+    if (gp < n)
+      store_split1(tok + ((long long)b * n + gp) * (lo_off ? 512 : 256), c, buf_b[p * 257 + c], lo_off);
   }
 }
 
@@ -286,39 +282,43 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
 // Linear-attention source state   (loftr_module/linear_attention.py:55-57)
 // part[b][chunk][h][d][v] = sum_{s in chunk} K'[s,h,d] V[s,h,v];  row d = 32 holds sum_s K'[s,h,:]
 // =============================================================================================
-constexpr int kKvChunk = 256;
+constexpr int kKvChunk = 128;
 
 __global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restrict__ kv16,
-                                                         float* __restrict__ part, int S, int d) {
-  __shared__ __half k_s[kKvChunk][32];
-  __shared__ __half v_s[kKvChunk][32];
+                                                         float* __restrict__ part, int S, int d,
+                                                         int lo_off) {
+  __shared__ float k_s[kKvChunk][32];
+  __shared__ float v_s[kKvChunk][32];
   const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int chunks = gridDim.x, H = gridDim.y;
   const int s0 = chunk * kKvChunk;
   const int cnt = min(kKvChunk, S - s0);
-  const __half* src = kv16 + ((long long)b * S + s0) * (2 * d);
-  // 256 tokens x (32 K' + 32 V) halves; 4 threads per token row move 8 halves each per operand
+  const int ld = lo_off ? 4 * d : 2 * d;
+  const __half* src = kv16 + ((long long)b * S + s0) * ld;
+  // tokens x (32 K' + 32 V); 4 threads per token row move 8 values each per operand
   for (int i = threadIdx.x; i < kKvChunk * 4; i += 256) {
     const int t = i >> 2, part4 = i & 3;
-    uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+    float kq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (t < cnt) {
-      kq = *reinterpret_cast<const uint4*>(src + (long long)t * 2 * d + h * 32 + part4 * 8);
-      vq = *reinterpret_cast<const uint4*>(src + (long long)t * 2 * d + d + h * 32 + part4 * 8);
+      load_split8(src + (long long)t * ld, h * 32 + part4 * 8, kq, lo_off);
+      load_split8(src + (long long)t * ld, d + h * 32 + part4 * 8, vq, lo_off);
     }
-    *reinterpret_cast<uint4*>(&k_s[t][part4 * 8]) = kq;
-    *reinterpret_cast<uint4*>(&v_s[t][part4 * 8]) = vq;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      k_s[t][part4 * 8 + j] = kq[j];
+      v_s[t][part4 * 8 + j] = vq[j];
+    }
   }
   __syncthreads();
   const int dd = threadIdx.x >> 3, v0 = (threadIdx.x & 7) * 4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, ks = 0.f;
   for (int t = 0; t < kKvChunk; ++t) {
-    const float k = __half2float(k_s[t][dd]);
-    const __half2* vp = reinterpret_cast<const __half2*>(&v_s[t][v0]);
-    const float2 va = __half22float2(vp[0]), vb = __half22float2(vp[1]);
+    const float k = k_s[t][dd];
+    const float4 va = *reinterpret_cast<const float4*>(&v_s[t][v0]);
     acc[0] = fmaf(k, va.x, acc[0]);
     acc[1] = fmaf(k, va.y, acc[1]);
-    acc[2] = fmaf(k, vb.x, acc[2]);
-    acc[3] = fmaf(k, vb.y, acc[3]);
+    acc[2] = fmaf(k, va.z, acc[2]);
+    acc[3] = fmaf(k, va.w, acc[3]);
     ks += k;
   }
   float* dst = part + ((((long long)b * chunks + chunk) * H + h) * 33) * 32;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
                                                           const float* __restrict__ merge_w,
                                                           __half* __restrict__ mt,
                                                           float* __restrict__ ksum, int chunks,
-                                                          int d, float inv_vlen) {
+                                                          int d, float inv_vlen, int lo_off) {
   __shared__ float kv_s[33][33];
   const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
   for (int i = threadIdx.x; i < 33 * 32; i += 256) {
@@ -354,9 +354,9 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
       for (int v = 0; v < 32; ++v) s = fmaf(w[v], kv_s[dd][v], s);
       o[dd] = s * inv_vlen;
     }
-    __half* dst = mt + ((long long)b * d + c) * d + h * 32;
+    __half* dst = mt + ((long long)b * d + c) * (lo_off ? 2 * d : d);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) store_half8(dst + g * 8, o + g * 8);
+    for (int g = 0; g < 4; ++g) store_split8(dst, h * 32 + g * 8, o + g * 8, lo_off);
   }
 }
 
@@ -515,21 +515,22 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const __half* __restrict__ fine, const float* __restrict__ desc3d,
     const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
     const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
-    int wf, int wc, int stride, int n) {
+    int wf, int wc, int stride, int n, int lo_off) {
   const int m = blockIdx.x, c = threadIdx.x;
   const long long b = b_ids[m], i = i_ids[m], j = j_ids[m];
   const int jy = (int)(j / wc), jx = (int)(j - (long long)jy * wc);
   const long long row0 = (long long)m * 26;
+  const int ld = lo_off ? 256 : 128;
   const float d = desc3d[(b * 128 + c) * n + i];
-  x32[row0 * 128 + c] = d;
-  x16[row0 * 128 + c] = __float2half_rn(d);
-  const __half* fb = fine + b * hf * wf * 128;
+  if (x32) x32[row0 * 128 + c] = d;
+  store_split1(x16 + row0 * ld, c, d, lo_off);
+  const __half* fb = fine + b * hf * wf * ld;
   for (int ww = 0; ww < 25; ++ww) {
     const int y = jy * stride + ww / 5 - 2, x = jx * stride + ww % 5 - 2;
-    __half hv = __float2half_rn(0.f);
-    if (y >= 0 && y < hf && x >= 0 && x < wf) hv = fb[((long long)y * wf + x) * 128 + c];
-    x32[(row0 + 1 + ww) * 128 + c] = __half2float(hv);
-    x16[(row0 + 1 + ww) * 128 + c] = hv;
+    float v = 0.f;
+    if (y >= 0 && y < hf && x >= 0 && x < wf) v = load_split1(fb + ((long long)y * wf + x) * ld, c, lo_off);
+    if (x32) x32[(row0 + 1 + ww) * 128 + c] = v;
+    store_split1(x16 + (row0 + 1 + ww) * ld, c, v, lo_off);
   }
 }
 
@@ -539,18 +540,18 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
 // =============================================================================================
 __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __restrict__ qkv,
                                                              __half* __restrict__ msg, int cross,
-                                                             float eps) {
-  __shared__ __half q_s[26][128];
-  __shared__ __half k_s[26][128];
-  __shared__ __half v_s[26][128];
-  __shared__ float kv2[8][16][16];   // state of the 25 window tokens
-  __shared__ float ks2[128];
+                                                             float eps, int lo_off_in,
+                                                             int lo_off_out) {
+  __shared__ float q_s[26][128];
+  __shared__ float k_s[26][128];
+  __shared__ float v_s[26][128];
   const int m = blockIdx.x, c = threadIdx.x;
-  const __half* src = qkv + (long long)m * 26 * 384;
+  const int ldi = lo_off_in ? 768 : 384;
+  const __half* src = qkv + (long long)m * 26 * ldi;
   for (int t = 0; t < 26; ++t) {
-    q_s[t][c] = src[t * 384 + c];
-    k_s[t][c] = src[t * 384 + 128 + c];
-    v_s[t][c] = src[t * 384 + 256 + c];
+    q_s[t][c] = load_split1(src + t * ldi, c, lo_off_in);
+    k_s[t][c] = load_split1(src + t * ldi, 128 + c, lo_off_in);
+    v_s[t][c] = load_split1(src + t * ldi, 256 + c, lo_off_in);
   }
   __syncthreads();
   const int h = c >> 4, v = c & 15;
@@ -560,16 +561,22 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
   for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
   float ksum_c = 0.f;  // thread c also owns ks2[c]
   for (int t = 1; t < 26; ++t) {
-    const float vv = __half2float(v_s[t][c]);
+    const float vv = v_s[t][c];
 #pragma unroll
-    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(__half2float(k_s[t][h * 16 + dd]), vv, col[dd]);
-    ksum_c += __half2float(k_s[t][c]);
+    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(k_s[t][h * 16 + dd], vv, col[dd]);
+    ksum_c += k_s[t][c];
   }
+  // rows 1..25 of k_s / v_s are dead once every thread has its partial state: reuse them for the
+  // window state kv2[h][dd][v] and ks2[c]
+  __syncthreads();
+  float (*kv2)[16][16] = reinterpret_cast<float (*)[16][16]>(&v_s[1][0]);
+  float* ks2 = &k_s[1][0];
 #pragma unroll
   for (int dd = 0; dd < 16; ++dd) kv2[h][dd][v] = col[dd];
   ks2[c] = ksum_c;
   __syncthreads();
-  __half* dst = msg + (long long)m * 26 * 128;
+  const int ldo = lo_off_out ? 256 : 128;
+  __half* dst = msg + (long long)m * 26 * ldo;
   for (int t = 0; t < 26; ++t) {
     // which source state does token t read?  self: own sequence; cross: the other one
     const bool use_window = cross ? (t == 0) : (t > 0);
@@ -577,7 +584,7 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
     if (use_window) {
 #pragma unroll
       for (int dd = 0; dd < 16; ++dd) {
-        const float q = __half2float(q_s[t][h * 16 + dd]);
+        const float q = q_s[t][h * 16 + dd];
         num = fmaf(q, kv2[h][dd][v], num);
         den = fmaf(q, ks2[h * 16 + dd], den);
       }
@@ -585,12 +592,11 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
       // source is the single 3D token (row 0): KV = k0^T v0, Ksum = k0
       float qk = 0.f;
 #pragma unroll
-      for (int dd = 0; dd < 16; ++dd)
-        qk = fmaf(__half2float(q_s[t][h * 16 + dd]), __half2float(k_s[0][h * 16 + dd]), qk);
-      num = qk * __half2float(v_s[0][c]);
+      for (int dd = 0; dd < 16; ++dd) qk = fmaf(q_s[t][h * 16 + dd], k_s[0][h * 16 + dd], qk);
+      num = qk * v_s[0][c];
       den = qk;
     }
-    dst[t * 128 + c] = __float2half_rn(num / (den + eps));
+    store_split1(dst + t * ldo, c, num / (den + eps), lo_off_out);
   }
 }
 
@@ -667,7 +673,7 @@ int opp_version(void) { return 100; }
 int opp_num_sms(void) { return opp::num_sms(); }
 
 int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
-                  int h, int w, int c_out, opp_stream_t stream) {
+                  int h, int w, int c_out, int split, opp_stream_t stream) {
   OPP_REQUIRE(image && w_t && bias && out, "null pointer");
   OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
   const int smem = (49 * c_out + c_out + 37 * 37) * 4;
@@ -679,18 +685,18 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
   }
   dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
   conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
-                                                              c_out);
+                                                              c_out, split ? c_out : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
-                       opp_stream_t stream) {
+                       int split, opp_stream_t stream) {
   OPP_REQUIRE(a && b && out, "null pointer");
   OPP_REQUIRE(c % 8 == 0 && h > 1 && w > 1, "bad upsample shape");
   const long long total = (long long)batch * 4 * h * w * (c / 8);
   upsample2x_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c);
+      (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -704,33 +710,38 @@ int opp_kpt_stats(const float* kpts, float* stats, int batch, int n, opp_stream_
 
 int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, const float* w1_t,
                    const float* b1, const float* w2_t, const float* b2, const float* w3_t,
-                   const float* b3, const float* w4_t, const float* b4, float* tok32, void* tok16,
-                   int batch, int n, opp_stream_t stream) {
-  OPP_REQUIRE(kpts && stats && desc && tok32 && tok16, "null pointer");
+                   const float* b3, const float* w4_t, const float* b4, void* tok, int batch, int n,
+                   int split, opp_stream_t stream) {
+  OPP_REQUIRE(kpts && stats && desc && tok, "null pointer");
   dim3 grid((n + kKeP - 1) / kKeP, batch);
   kpt_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kpts, stats, desc, w1_t, b1, w2_t, b2,
-                                                            w3_t, b3, w4_t, b4, tok32,
-                                                            (__half*)tok16, n);
+                                                            w3_t, b3, w4_t, b4, (__half*)tok, n,
+                                                            split ? 256 : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
-int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, opp_stream_t stream) {
+int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
+
+int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
+                   opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");
   OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
   dim3 grid((s + kKvChunk - 1) / kKvChunk, d / 32, batch);
-  kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d);
+  kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d,
+                                                            split ? 2 * d : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ksum, int batch,
-                    int chunks, int d, float v_len, opp_stream_t stream) {
+                    int chunks, int d, float v_len, int split, opp_stream_t stream) {
   OPP_REQUIRE(part && merge_w && mt && ksum, "null pointer");
   OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
   dim3 grid(d / 32, batch);
   kv_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(part, merge_w, (__half*)mt, ksum,
-                                                             chunks, d, 1.f / v_len);
+                                                             chunks, d, 1.f / v_len,
+                                                             split ? d : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -775,22 +786,23 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
 
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
-                    int hf, int wf, int wc, int stride, int n, opp_stream_t stream) {
+                    int hf, int wf, int wc, int stride, int n, int split, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
-  OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x32 && x16, "null pointer");
+  OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x16, "null pointer");
   fine_gather_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)fine, desc3d, b_ids,
                                                           i_ids, j_ids, x32, (__half*)x16, hf, wf,
-                                                          wc, stride, n);
+                                                          wc, stride, n, split ? 128 : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
-int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps,
+int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, int split,
                        opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(qkv && msg, "null pointer");
   fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
-                                                             cross, eps);
+                                                             cross, eps, split ? 384 : 0,
+                                                             split ? 128 : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

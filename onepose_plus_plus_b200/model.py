@@ -1,0 +1,615 @@
+"""Drop-in for the reference ``OnePosePlus_model`` (src/models/OnePosePlus/OnePosePlusModel.py:25-201).
+
+Same constructor (``config, profiler=None, debug=False``), same config keys, same 195 state-dict
+keys (so ``load_state_dict(strict=True)`` of a reference checkpoint works), same in-place
+``forward(data)`` contract — but ``forward`` runs the whole coarse-to-fine matcher through the
+sm_100a kernels of ``libopp_b200.so``.  The ``nn.Module`` tree below only *holds* parameters with
+the reference's names and initialisers; there is no PyTorch math on the hot path and no fallback:
+CPU tensors, training mode, or a missing extension raise.
+
+Round-1 scope: inference (``eval()``, no autograd), linear attention, no
+``query_image_mask`` (cold in every shipped config).
+"""
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+__all__ = ["OnePosePlus_model", "build_backbone"]
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter containers — names / shapes / initialisers follow the reference
+# ---------------------------------------------------------------------------------------------
+def _conv(cin, cout, k, stride=1):
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+
+
+class BasicBlock(nn.Module):
+    """backbone/resnet.py:20-45"""
+
+    def __init__(self, in_planes, planes, stride=1):
+        super().__init__()
+        self.conv1 = _conv(in_planes, planes, 3, stride)
+        self.conv2 = _conv(planes, planes, 3)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = None if stride == 1 else nn.Sequential(
+            nn.Conv2d(in_planes, planes, kernel_size=1, stride=stride, padding=0, bias=False),
+            nn.BatchNorm2d(planes))
+
+
+class ResNetFPN_8_2(nn.Module):
+    """backbone/resnet.py:85-164 (parameters only; compute is in OnePosePlus_model._backbone)"""
+
+    def __init__(self, config):
+        super().__init__()
+        if config["block_type"] != "BasicBlock":
+            raise NotImplementedError("only BasicBlock backbones are built (resnet.py:80-83)")
+        d0 = config["initial_dim"]
+        b = config["block_dims"]
+        self.block_dims = b
+        self.output_layers = config["output_layers"]
+        self.conv1 = nn.Conv2d(1, d0, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(d0)
+        self.layer1 = nn.Sequential(BasicBlock(d0, b[0], 1), BasicBlock(b[0], b[0], 1))
+        self.layer2 = nn.Sequential(BasicBlock(b[0], b[1], 2), BasicBlock(b[1], b[1], 1))
+        self.layer3 = nn.Sequential(BasicBlock(b[1], b[2], 2), BasicBlock(b[2], b[2], 1))
+        self.layer3_outconv = _conv(b[2], b[2], 1)
+        self.layer2_outconv = _conv(b[1], b[2], 1)
+        self.layer2_outconv2 = nn.Sequential(_conv(b[2], b[2], 3), nn.BatchNorm2d(b[2]),
+                                             nn.LeakyReLU(), _conv(b[2], b[1], 3))
+        self.layer1_outconv = _conv(b[0], b[1], 1)
+        self.layer1_outconv2 = nn.Sequential(_conv(b[1], b[1], 3), nn.BatchNorm2d(b[1]),
+                                             nn.LeakyReLU(), _conv(b[1], b[0], 3))
+        for m in self.modules():  # resnet.py:126-131
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+
+
+def build_backbone(config):
+    """backbone/__init__.py:7-15"""
+    if config["type"] == "ResNetFPN":
+        if list(config["resolution"]) == [8, 2]:
+            return ResNetFPN_8_2(config["resnetfpn"])
+        raise NotImplementedError
+    raise ValueError("reaching this line! LOFTR_BACKBONE.TYEP and RESOLUTION are not correct")
+
+
+class PositionEncodingSine(nn.Module):
+    """utils/position_encoding.py:8-42 — keeps the reference's floor-division quirk."""
+
+    def __init__(self, d_model, max_shape=(256, 256)):
+        super().__init__()
+        max_shape = tuple(max_shape)
+        pe = torch.zeros((d_model, *max_shape))
+        y_position = torch.ones(max_shape).cumsum(0).float().unsqueeze(0)
+        x_position = torch.ones(max_shape).cumsum(1).float().unsqueeze(0)
+        div_term = torch.exp(torch.arange(0, d_model // 2, 2).float()
+                             * (-math.log(10000.0) / d_model // 2))[:, None, None]
+        pe[0::4] = torch.sin(x_position * div_term)
+        pe[1::4] = torch.cos(x_position * div_term)
+        pe[2::4] = torch.sin(y_position * div_term)
+        pe[3::4] = torch.cos(y_position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0), persistent=False)
+
+
+class KeypointEncoding_linear(nn.Module):
+    """utils/position_encoding.py:46-79 (parameters only)"""
+
+    def __init__(self, inp_dim, feature_dim, layers, norm_method="batchnorm"):
+        super().__init__()
+        if norm_method != "instancenorm":
+            raise NotImplementedError("kernel implements norm_method 'instancenorm' (shipped configs)")
+        channels = [inp_dim] + list(layers) + [feature_dim]
+        mods = []
+        for i in range(1, len(channels)):
+            mods.append(nn.Linear(channels[i - 1], channels[i], bias=True))
+            if i < len(channels) - 1:
+                mods.append(nn.InstanceNorm1d(channels[i]))
+                mods.append(nn.ReLU())
+        self.encoder = nn.Sequential(*mods)
+        nn.init.constant_(self.encoder[-1].bias, 0.0)
+
+
+class LoFTREncoderLayer(nn.Module):
+    """loftr_module/transformer.py:7-63 (parameters only)"""
+
+    def __init__(self, d_model, nhead, attention="linear", norm_method="layernorm", rezero=None):
+        super().__init__()
+        if attention != "linear":
+            raise NotImplementedError("only attention='linear' is built (the shipped configs)")
+        if norm_method != "layernorm":
+            raise NotImplementedError("only norm_method='layernorm' is built")
+        if rezero is not None:
+            raise NotImplementedError("rezero is not built (null in the shipped configs)")
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(nn.Linear(d_model * 2, d_model * 2, bias=False), nn.ReLU(True),
+                                 nn.Linear(d_model * 2, d_model, bias=False))
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class LocalFeatureTransformer(nn.Module):
+    """loftr_module/transformer.py:97-131 (parameters only)"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.d_model = config["d_model"]
+        self.nhead = config["nhead"]
+        self.layer_names = list(config["layer_names"]) * config["layer_iter_n"]
+        if config["redraw_interval"] is not None:
+            assert config["redraw_interval"] % 2 == 0
+        if config["type"] != "LoFTR":
+            raise ValueError()
+        if config["final_proj"]:
+            raise NotImplementedError("final_proj is False in every shipped config")
+        layers = []
+        for name in self.layer_names:
+            if name not in ("self", "cross"):
+                raise NotImplementedError
+            layers.append(LoFTREncoderLayer(config["d_model"], config["nhead"], config["attention"],
+                                            config["norm_method"], config["rezero"]))
+        self.layers = nn.ModuleList(layers)
+        for p in self.parameters():  # transformer.py:128-131
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+class CoarseMatching(nn.Module):
+    """utils/coarse_matching.py:45-75 (configuration only)"""
+
+    def __init__(self, config, profiler=None):
+        super().__init__()
+        self.config = config
+        if config["feat_norm_method"] != "sqrt_feat_dim":
+            raise ValueError("only feat_norm_method 'sqrt_feat_dim' is built")
+        if config["type"] != "dual-softmax":
+            raise NotImplementedError()
+        self.temperature = config["dual_softmax"]["temperature"]
+        self.thr = config["thr"]
+        self.border_rm = config["border_rm"]
+
+
+class FinePreprocess(nn.Module):
+    """loftr_module/fine_preprocess.py:8-30 (configuration only)"""
+
+    def __init__(self, config, cf_res=None, feat_ids=None, feat_dims=None):
+        super().__init__()
+        self.config = config
+        self.W = config["window_size"]
+
+
+class FineMatching(nn.Module):
+    """utils/fine_matching.py:10-27 (configuration only)"""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self._type = config["s2d"]["type"]
+        if self._type != "heatmap":
+            raise NotImplementedError()
+
+
+def _pad16(c):
+    return (c + 15) // 16 * 16
+
+
+# ---------------------------------------------------------------------------------------------
+# the model
+# ---------------------------------------------------------------------------------------------
+class OnePosePlus_model(nn.Module):
+    def __init__(self, config, profiler=None, debug=False, precision=None):
+        """`precision` (extension; default from $OPP_B200_PRECISION or "fp16x3"):
+        "fp16x3" = 2-term fp16 split operands, three tcgen05 MMAs per K-step (fp32-grade, the
+        parity mode); "fp16" = single fp16 operands (fast, ~1e-2 deviations on high-gain inputs)."""
+        super().__init__()
+        self.config = config
+        self.profiler = profiler
+        self.debug = debug
+        precision = precision or os.environ.get("OPP_B200_PRECISION", "fp16x3")
+        if precision not in ("fp16x3", "fp16"):
+            raise ValueError(f"unknown precision {precision!r}")
+        self.precision = precision
+        self.backbone = build_backbone(config["loftr_backbone"])
+        if config["positional_encoding"]["enable"]:
+            self.dense_pos_encoding = PositionEncodingSine(
+                config["loftr_coarse"]["d_model"],
+                max_shape=config["positional_encoding"]["pos_emb_shape"])
+        else:
+            self.dense_pos_encoding = None
+        if config["keypoints_encoding"]["enable"]:
+            if config["keypoints_encoding"]["type"] != "mlp_linear":
+                raise NotImplementedError
+            self.kpt_3d_pos_encoding = KeypointEncoding_linear(
+                inp_dim=3, feature_dim=config["keypoints_encoding"]["descriptor_dim"],
+                layers=config["keypoints_encoding"]["keypoints_encoder"],
+                norm_method=config["keypoints_encoding"]["norm_method"])
+        else:
+            raise NotImplementedError("keypoints_encoding.enable=False is not built")
+        self.loftr_coarse = LocalFeatureTransformer(config["loftr_coarse"])
+        self.coarse_matching = CoarseMatching(config["coarse_matching"], profiler=profiler)
+        self.fine_preprocess = FinePreprocess(config["loftr_fine"],
+                                              cf_res=config["loftr_backbone"]["resolution"])
+        self.loftr_fine = LocalFeatureTransformer(config["loftr_fine"])
+        self.fine_matching = FineMatching(config["fine_matching"])
+        if config["loftr_coarse"]["d_model"] != 256 or config["loftr_coarse"]["nhead"] != 8:
+            raise NotImplementedError("coarse kernels are built for d_model 256, 8 heads")
+        if config["loftr_fine"]["d_model"] != 128 or config["loftr_fine"]["nhead"] != 8:
+            raise NotImplementedError("fine kernels are built for d_model 128, 8 heads")
+        if config["loftr_fine"]["window_size"] != 5:
+            raise NotImplementedError("fine kernels are built for window_size 5")
+        b = config["loftr_backbone"]["resnetfpn"]
+        if list(b["block_dims"]) != [128, 196, 256] or b["initial_dim"] != 128 \
+                or list(b["output_layers"]) != [3, 1]:
+            raise NotImplementedError("backbone kernels are built for dims 128/[128,196,256], outputs [3,1]")
+
+        self.loftr_backbone_pretrained = config["loftr_backbone"]["pretrained"]
+        if self.loftr_backbone_pretrained is not None:
+            # OnePosePlusModel.py:79-94: initialise the backbone from a LoFTR checkpoint
+            ckpt = torch.load(self.loftr_backbone_pretrained, "cpu")["state_dict"]
+            for k in list(ckpt.keys()):
+                if "backbone" in k:
+                    ckpt[k[k.find("backbone") + len("backbone") + 1:]] = ckpt[k]
+                ckpt.pop(k)
+            self.backbone.load_state_dict(ckpt)
+            if config["loftr_backbone"]["pretrained_fix"]:
+                for p in self.backbone.parameters():
+                    p.requires_grad = False
+        self._plan = None
+        self._plan_sig = None
+        self._ws = {}
+
+    @property
+    def split(self):
+        return self.precision == "fp16x3"
+
+    # pickling (Ray ships the module object): drop device-side caches
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_plan"], st["_plan_sig"], st["_ws"] = None, None, {}
+        return st
+
+    # ------------------------------------------------------------------ weight preparation
+    def _signature(self):
+        return (self.precision,) + tuple((t.data_ptr(), t._version)
+                                         for t in self.state_dict(keep_vars=True).values())
+
+    @torch.no_grad()
+    def _prepare(self, device):
+        """Fold eval-mode BatchNorm into the convolutions (w' = w*g/sqrt(var+eps),
+        b' = beta - mean*g/sqrt(var+eps)), pad 196-channel tensors to 208, reorder weights to the
+        kernels' layouts and convert GEMM operands to fp16 planes (hi | lo)."""
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) if v.is_floating_point() else v
+              for k, v in self.state_dict().items()}
+        split = self.split
+        P = {}
+
+        def fold(wkey, bnkey):
+            w = sd[wkey + ".weight"]
+            if bnkey is None:
+                return w, torch.zeros(w.shape[0], device=device)
+            g = sd[bnkey + ".weight"] / torch.sqrt(sd[bnkey + ".running_var"] + 1e-5)
+            return w * g[:, None, None, None], sd[bnkey + ".bias"] - sd[bnkey + ".running_mean"] * g
+
+        def conv(name, wkey, bnkey):
+            w, b = fold("backbone." + wkey, None if bnkey is None else "backbone." + bnkey)
+            co, ci, k, _ = w.shape
+            wp = torch.zeros(_pad16(co), k, k, _pad16(ci), device=device)
+            wp[:co, :, :, :ci] = w.permute(0, 2, 3, 1)
+            bp = torch.zeros(_pad16(co), device=device)
+            bp[:co] = b
+            P[name] = (ops.to_planes(wp.reshape(_pad16(co), -1), split), bp.contiguous())
+
+        w, b = fold("backbone.conv1", "backbone.bn1")
+        P["conv1"] = (w.view(w.shape[0], 49).t().contiguous(), b.contiguous())
+        for li in (1, 2, 3):
+            for bi in (0, 1):
+                p = f"layer{li}.{bi}"
+                conv(p + ".conv1", p + ".conv1", p + ".bn1")
+                conv(p + ".conv2", p + ".conv2", p + ".bn2")
+                if li > 1 and bi == 0:
+                    conv(p + ".down", p + ".downsample.0", p + ".downsample.1")
+        conv("layer3_outconv", "layer3_outconv", None)
+        conv("layer2_outconv", "layer2_outconv", None)
+        conv("layer2_outconv2.0", "layer2_outconv2.0", "layer2_outconv2.1")
+        conv("layer2_outconv2.3", "layer2_outconv2.3", None)
+        conv("layer1_outconv", "layer1_outconv", None)
+        conv("layer1_outconv2.0", "layer1_outconv2.0", "layer1_outconv2.1")
+        conv("layer1_outconv2.3", "layer1_outconv2.3", None)
+
+        P["kpt_mlp"] = [(sd[f"kpt_3d_pos_encoding.encoder.{i}.weight"].t().contiguous(),
+                         sd[f"kpt_3d_pos_encoding.encoder.{i}.bias"].contiguous()) for i in (0, 3, 6, 9)]
+
+        def layer(prefix):
+            g = lambda k: sd[prefix + k]  # noqa: E731
+            tp = lambda t: ops.to_planes(t, split)  # noqa: E731
+            return {
+                "wq": tp(g("q_proj.weight")),
+                "wkv": tp(torch.cat([g("k_proj.weight"), g("v_proj.weight")], 0)),
+                "wqkv": tp(torch.cat([g("q_proj.weight"), g("k_proj.weight"), g("v_proj.weight")], 0)),
+                "merge32": g("merge.weight").contiguous(),
+                "merge16": tp(g("merge.weight")),
+                "mlp0": tp(g("mlp.0.weight")),
+                "mlp2": tp(g("mlp.2.weight")),
+                "n1": (g("norm1.weight").contiguous(), g("norm1.bias").contiguous()),
+                "n2": (g("norm2.weight").contiguous(), g("norm2.bias").contiguous()),
+            }
+
+        P["coarse"] = [layer(f"loftr_coarse.layers.{i}.") for i in range(len(self.loftr_coarse.layers))]
+        P["fine"] = [layer(f"loftr_fine.layers.{i}.") for i in range(len(self.loftr_fine.layers))]
+        P["pe"] = {}
+        return P
+
+    def _pe_tokens(self, hc, wc, device):
+        key = (hc, wc)
+        if key not in self._plan["pe"]:
+            if self.dense_pos_encoding is None:
+                pe = torch.zeros(hc * wc, 256, device=device)
+            else:
+                pe = self.dense_pos_encoding.pe[0, :, :hc, :wc].to(device)
+                pe = pe.permute(1, 2, 0).reshape(hc * wc, -1).contiguous()
+            self._plan["pe"][key] = pe
+        return self._plan["pe"][key]
+
+    def _buf(self, name, shape, dtype, device):
+        """Workspace tensors are allocated once per (name, shape) and reused across calls."""
+        key = (name, tuple(shape), dtype)
+        t = self._ws.get(key)
+        if t is None or t.device != device:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self._ws[key] = t
+        return t
+
+    # ------------------------------------------------------------------ stages
+    def _backbone(self, img):
+        """ResNetFPN_8_2.forward (backbone/resnet.py:141-164) -> coarse tokens (+pe), fine map."""
+        P = self._plan
+        dev = img.device
+        B, _, H, W = img.shape
+        f16 = torch.float16
+        split = self.split
+        pl = 2 if split else 1
+
+        def cv(name, x, out_name, ksize, stride, act=0, resid=None, **kw):
+            w, b = P[name]
+            Bn, h, wd, _ = x.shape
+            oh, ow = (h - 1) // stride + 1, (wd - 1) // stride + 1
+            out = self._buf(out_name, (Bn, oh, ow, pl * w.shape[0]), f16, dev)
+            return ops.conv2d_nhwc(x, w, b, out, ksize, stride, split, act, resid, **kw)
+
+        x0 = ops.conv1_7x7(img, *P["conv1"], self._buf("x0", (B, H // 2, W // 2, pl * 128), f16, dev),
+                           split)
+
+        def block(prefix, x, tag, stride):
+            t = cv(prefix + ".conv1", x, tag + "_t", 3, stride, act=1)
+            sc = x if stride == 1 else cv(prefix + ".down", x, tag + "_ds", 1, stride)
+            return cv(prefix + ".conv2", t, tag + "_o", 3, 1, act=1, resid=sc)
+
+        x1 = block("layer1.1", block("layer1.0", x0, "l1a", 1), "l1b", 1)
+        x2 = block("layer2.1", block("layer2.0", x1, "l2a", 2), "l2b", 1)
+        x3 = block("layer3.1", block("layer3.0", x2, "l3a", 2), "l3b", 1)
+        hc, wc = x3.shape[1:3]
+        S = hc * wc
+        tok = self._buf("q2_0", (B, S, pl * 256), f16, dev)
+        x3_out = cv("layer3_outconv", x3, "x3_out", 1, 1, tok=tok, pe=self._pe_tokens(hc, wc, dev))
+        x2_lat = cv("layer2_outconv", x2, "x2_lat", 1, 1)
+        ops.upsample2x_add(x2_lat, x3_out, x2_lat, split)
+        t = cv("layer2_outconv2.0", x2_lat, "x2_h", 3, 1, act=2)
+        x2_out = cv("layer2_outconv2.3", t, "x2_out", 3, 1)
+        x1_lat = cv("layer1_outconv", x1, "x1_lat", 1, 1)
+        ops.upsample2x_add(x1_lat, x2_out, x1_lat, split)
+        t = cv("layer1_outconv2.0", x1_lat, "x1_h", 3, 1, act=2)
+        x1_out = cv("layer1_outconv2.3", t, "x1_out", 3, 1)
+        return tok, x1_out, (hc, wc)
+
+    def _encoder_layer(self, L, tag, x, src, B, lx, ls, out):
+        """LoFTREncoderLayer.forward (transformer.py:65-94) with linear attention
+        (linear_attention.py:29-61) for d_model 256.  x, src, out: fp16 planes [B, len, pl*256]."""
+        dev = x.device
+        f16 = torch.float16
+        split = self.split
+        pl = 2 if split else 1
+        kv16 = self._buf(tag + "kv16", (B * ls, pl * 512), f16, dev)
+        ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split)
+        part = self._buf(tag + "part", (B, ops.kv_chunks(ls), 8, 33, 32), torch.float32, dev)
+        mt = self._buf(tag + "mt", (B, 256, pl * 256), f16, dev)
+        ksum = self._buf(tag + "ksum", (B, 256), torch.float32, dev)
+        ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split)
+        qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
+        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split)
+        msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
+        ops.linear_ln(qz, None, mt, True, *L["n1"], B, lx, split, out16=msg)
+        h = self._buf(tag + "h", (B * lx, pl * 512), f16, dev)
+        ops.linear_act(x, msg, L["mlp0"], h, B * lx, 1, 512, split)
+        ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, B * lx, split, resid=x, out16=out)
+
+    def _coarse_transformer(self, q2, d3, B, S, N):
+        """LocalFeatureTransformer.forward (transformer.py:133-171): self layers update each
+        sequence from itself; cross layers update BOTH from the pre-update tensors."""
+        dev = q2.device
+        f16 = torch.float16
+        pl = 2 if self.split else 1
+        names = self.loftr_coarse.layer_names
+        cur2, cur3 = q2, d3
+        for i, name in enumerate(names):
+            L = self._plan["coarse"][i]
+            nxt = (i + 1) % 2
+            o2 = self._buf(f"q2_{nxt}", (B, S, pl * 256), f16, dev)
+            o3 = self._buf(f"d3_{nxt}", (B, N, pl * 256), f16, dev)
+            self_layer = name == "self"
+            self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
+                                S if self_layer else N, o2)
+            self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
+                                N if self_layer else S, o3)
+            cur2, cur3 = o2, o3
+        return cur2, cur3
+
+    def _coarse_matching(self, q2, d3, data, B, N, hc, wc):
+        """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch."""
+        dev = q2.device
+        S = hc * wc
+        f32, i32 = torch.float32, torch.int32
+        split = self.split
+        cm = self.coarse_matching
+        scale = 1.0 / (256.0 * (cm.temperature + 1e-4))  # (a/16).(b/16)/(T+1e-4)
+        ts, tl = ops.sim_tiles(S), ops.sim_tiles(N)
+        pm_pt = self._buf("pm_pt", (B * N, ts), f32, dev)
+        ps_pt = self._buf("ps_pt", (B * N, ts), f32, dev)
+        pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
+        ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
+        lse_pt = self._buf("lse_pt", (B, N), f32, dev)
+        lse_px = self._buf("lse_px", (B, S), f32, dev)
+        ops.sim_lse(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, split)
+        ops.sim_lse(q2, d3, B, S, N, 256, scale, pm_px, ps_px, lse_px, split)
+        conf = torch.empty((B, N, S), dtype=f32, device=dev)  # owned by the caller's dict
+        pi_pt = self._buf("pi_pt", (B * N, ts), i32, dev)
+        pi_px = self._buf("pi_px", (B * S, tl), i32, dev)
+        pt_val = self._buf("pt_val", (B, N), f32, dev)
+        pt_idx = self._buf("pt_idx", (B, N), i32, dev)
+        px_val = self._buf("px_val", (B, S), f32, dev)
+        px_idx = self._buf("px_idx", (B, S), i32, dev)
+        ops.sim_conf(d3, q2, lse_pt, lse_px, True, conf, B, N, S, 256, scale, pm_pt, pi_pt,
+                     pt_val, pt_idx, split)
+        ops.sim_conf(q2, d3, lse_px, lse_pt, False, None, B, S, N, 256, scale, pm_px, pi_px,
+                     px_val, px_idx, split)
+        cap = B * min(N, S)
+        scratch = self._buf("match_scratch", ((B * N + 1023) // 1024 + 2,), i32, dev)
+        count = self._buf("match_count", (1,), i32, dev)
+        b_ids = torch.empty(cap, dtype=torch.int64, device=dev)
+        i_ids = torch.empty(cap, dtype=torch.int64, device=dev)
+        j_ids = torch.empty(cap, dtype=torch.int64, device=dev)
+        mconf = torch.empty(cap, dtype=f32, device=dev)
+        mk3 = torch.empty((cap, 3), dtype=f32, device=dev)
+        mkc = torch.empty((cap, 2), dtype=f32, device=dev)
+        img_scale = data.get("query_image_scale")
+        if img_scale is not None:
+            img_scale = img_scale.to(device=dev, dtype=f32).contiguous()
+        cell = float(data["q_hw_i"][0] / hc)
+        ops.match_select(pt_val, pt_idx, px_idx, data["keypoints3d"], img_scale, B, N, hc, wc,
+                         cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf, mk3, mkc,
+                         count)
+        M = int(count.item())  # the one host sync of the forward (the reference syncs in torch.where)
+        data.update({
+            "conf_matrix": conf,
+            "b_ids": b_ids[:M], "i_ids": i_ids[:M], "j_ids": j_ids[:M],
+            "gt_mask": torch.zeros(M, dtype=torch.bool, device=dev),
+            "m_bids": b_ids[:M], "mkpts_3d_db": mk3[:M], "mkpts_query_c": mkc[:M], "mconf": mconf[:M],
+        })
+        return M, img_scale
+
+    def _fine(self, data, fine_map, M, img_scale, wc):
+        """FinePreprocess (fine_preprocess.py:32-55) -> loftr_fine -> FineMatching
+        (fine_matching.py:28-110)."""
+        dev = fine_map.device
+        f16, f32 = torch.float16, torch.float32
+        split = self.split
+        pl = 2 if split else 1
+        data["W"] = self.fine_preprocess.W
+        if M == 0:
+            data.update({"expec_f": torch.empty(0, 3, device=dev),
+                         "mkpts_query_f": data["mkpts_query_c"]})
+            return
+        B, hf, wf, _ = fine_map.shape
+        stride = data["q_hw_f"][0] // data["q_hw_c"][0]
+        rows = 26 * M
+        x = [torch.empty((rows, pl * 128), dtype=f16, device=dev) for _ in range(2)]
+        x32 = torch.empty((rows, 128), dtype=f32, device=dev)
+        desc = data["descriptors3d_db"]
+        fine_layers = self.loftr_fine.layer_names if self.config["loftr_fine"]["enable"] else []
+        ops.fine_gather(fine_map, desc, data["b_ids"], data["i_ids"], data["j_ids"],
+                        None if fine_layers else x32, x[0], M, hf, wf, wc, stride, desc.shape[2], split)
+        cur = 0
+        if fine_layers:
+            qkv = torch.empty((rows, pl * 384), dtype=f16, device=dev)
+            att = torch.empty((rows, pl * 128), dtype=f16, device=dev)
+            msg = torch.empty((rows, pl * 128), dtype=f16, device=dev)
+            h = torch.empty((rows, pl * 256), dtype=f16, device=dev)
+            for i, name in enumerate(fine_layers):
+                L = self._plan["fine"][i]
+                last = i == len(fine_layers) - 1
+                ops.linear_act(x[cur], None, L["wqkv"], qkv, rows, 2, 256, split)
+                ops.fine_attention(qkv, att, M, name == "cross", split)
+                ops.linear_ln(att, None, L["merge16"], False, *L["n1"], 1, rows, split, out16=msg)
+                ops.linear_act(x[cur], msg, L["mlp0"], h, rows, 1, 256, split)
+                ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, rows, split, resid=x[cur],
+                              out16=None if last else x[1 - cur], out32=x32 if last else None)
+                cur = 1 - cur
+        expec_f = torch.empty((M, 3), dtype=f32, device=dev)
+        mkpts_f = torch.empty((M, 2), dtype=f32, device=dev)
+        fine_scale = float(data["q_hw_i"][0] / data["q_hw_f"][0])
+        ops.fine_match(x32, data["mkpts_query_c"], data["b_ids"], img_scale, expec_f, mkpts_f, M,
+                       fine_scale)
+        data.update({"expec_f": expec_f, "mkpts_query_f": mkpts_f})
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, data):
+        """Same contract as the reference (OnePosePlusModel.py:96-201): reads query_image,
+        keypoints3d, descriptors3d_db, descriptors3d_coarse_db (optional), query_image_scale
+        (optional); writes bs, q_hw_i, q_hw_c, q_hw_f, conf_matrix, b_ids, i_ids, j_ids, gt_mask,
+        m_bids, mkpts_3d_db, mkpts_query_c, mconf, W, expec_f, mkpts_query_f; returns None."""
+        if self.training:
+            raise NotImplementedError(
+                "onepose_plus_plus_b200 round 1 builds the inference path only: call .eval() "
+                "(training/autograd is listed under 'next' in DESIGN.md)")
+        if "query_image_mask" in data:
+            raise NotImplementedError("query_image_mask (cold path, img_pad=False in every shipped "
+                                      "config) is not built")
+        img = data["query_image"]
+        if not img.is_cuda:
+            raise RuntimeError("OnePosePlus_model (B200) has no CPU path: move the model and data to "
+                               "a CUDA device")
+        with torch.no_grad():
+            dev = img.device
+            sig = self._signature()
+            if self._plan is None or self._plan_sig != sig:
+                self._plan = self._prepare(dev)
+                self._plan_sig = sig
+            img = img.contiguous().float()
+            B, _, H, W = img.shape
+            if H % 8 or W % 8:
+                raise ValueError("query_image height/width must be multiples of 8")
+            data.update({"bs": B, "q_hw_i": img.shape[2:]})
+            q2, fine_map, (hc, wc) = self._backbone(img)
+            data.update({"q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3])})
+            kpts = data["keypoints3d"].contiguous().float()
+            dsel = data["descriptors3d_coarse_db"] if "descriptors3d_coarse_db" in data \
+                else data["descriptors3d_db"]
+            dsel = dsel.contiguous().float()
+            N = kpts.shape[1]
+            if dsel.shape[1] != 256:
+                raise ValueError("coarse descriptors must be 256-d")
+            pl = 2 if self.split else 1
+            d3 = self._buf("d3_0", (B, N, pl * 256), torch.float16, dev)
+            ops.kpt_encode(kpts, dsel, self._plan["kpt_mlp"],
+                           self._buf("kpt_stats", (B, 4), torch.float32, dev), d3, self.split)
+            q2, d3 = self._coarse_transformer(q2, d3, B, hc * wc, N)
+            local = dict(data)
+            local["keypoints3d"] = kpts
+            M, img_scale = self._coarse_matching(q2, d3, local, B, N, hc, wc)
+            for k in ("conf_matrix", "b_ids", "i_ids", "j_ids", "gt_mask", "m_bids", "mkpts_3d_db",
+                      "mkpts_query_c", "mconf"):
+                data[k] = local[k]
+            if not self.config["fine_matching"]["enable"]:
+                data.update({"mkpts_query_f": data["mkpts_query_c"]})
+                return
+            fine_desc = data["descriptors3d_db"]
+            if fine_desc.shape[1] != 128:
+                raise ValueError("fine descriptors (descriptors3d_db) must be 128-d")
+            local = dict(data)
+            local["descriptors3d_db"] = fine_desc.contiguous().float()
+            self._fine(local, fine_map, M, img_scale, wc)
+            for k in ("W", "expec_f", "mkpts_query_f"):
+                data[k] = local[k]

@@ -1,0 +1,161 @@
+"""Thin tensor-level wrappers over the C ABI (include/opp_b200.h).  Each wrapper checks dtype /
+contiguity, passes raw device pointers and the current CUDA stream, and raises on error.  There
+is deliberately no alternative code path: without libopp_b200.so these functions raise."""
+import torch
+
+from . import _lib
+
+ptr, call, stream = _lib.ptr, _lib.call, _lib.stream
+
+
+def to_planes(x, split):
+    """fp32 tensor [..., C] -> fp16 storage [..., planes*C]: (hi | lo) planes when split."""
+    hi = x.half()
+    if not split:
+        return hi.contiguous()
+    lo = (x - hi.float()).half()
+    return torch.cat([hi, lo], -1).contiguous()
+
+
+def from_planes(t, split):
+    """Inverse of to_planes (returns fp32)."""
+    if not split:
+        return t.float()
+    c = t.shape[-1] // 2
+    return t[..., :c].float() + t[..., c:].float()
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def conv1_7x7(image, w_t, bias, out, split):
+    B, _, H, W = image.shape
+    _chk(image, torch.float32, "image")
+    call("opp_conv1_7x7", ptr(image), ptr(w_t), ptr(bias), ptr(out), B, H, W, w_t.shape[1],
+         int(split), stream())
+    return out
+
+
+def conv2d_nhwc(x, w, bias, out, ksize, stride, split, act=0, resid=None, slope=0.01, tok=None,
+                pe=None):
+    """x NHWC fp16 [B,H,W,planes*Cin_pad]; w fp16 [Cout_pad, planes*k*k*Cin_pad];
+    act 0 none / 1 relu / 2 leaky."""
+    _chk(x, torch.float16, "x")
+    _chk(w, torch.float16, "w")
+    _chk(resid, torch.float16, "resid")
+    B, H, W, C = x.shape
+    planes = 2 if split else 1
+    call("opp_conv2d_nhwc", ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), B, H, W, C // planes,
+         w.shape[0], ksize, stride, act, float(slope), ptr(tok), ptr(pe), int(split), stream())
+    return out
+
+
+def upsample2x_add(a, b, out, split):
+    B, h, w, C = b.shape
+    _chk(a, torch.float16, "a")
+    _chk(b, torch.float16, "b")
+    call("opp_upsample2x_add", ptr(a), ptr(b), ptr(out), B, h, w, C // (2 if split else 1),
+         int(split), stream())
+    return out
+
+
+def kpt_encode(kpts, desc, mlp, stats, tok, split):
+    B, N, _ = kpts.shape
+    _chk(kpts, torch.float32, "keypoints3d")
+    _chk(desc, torch.float32, "descriptors3d")
+    call("opp_kpt_stats", ptr(kpts), ptr(stats), B, N, stream())
+    (w1, b1), (w2, b2), (w3, b3), (w4, b4) = mlp
+    call("opp_kpt_encode", ptr(kpts), ptr(stats), ptr(desc), ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+         ptr(w3), ptr(b3), ptr(w4), ptr(b4), ptr(tok), B, N, int(split), stream())
+
+
+def linear_act(a0, a1, w, out, rows, act, act_cols, split):
+    """a_i fp16 [rows, planes*k_i]; w fp16 [n, planes*(k0+k1)]; out fp16 [rows, planes*n]."""
+    _chk(a0, torch.float16, "a0")
+    _chk(a1, torch.float16, "a1")
+    _chk(w, torch.float16, "w")
+    planes = 2 if split else 1
+    k0 = a0.shape[-1] // planes
+    k1 = a1.shape[-1] // planes if a1 is not None else 0
+    call("opp_linear_act_f16", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
+         act_cols, int(split), stream())
+    return out
+
+
+def linear_q(x16, wq, ksum, out, batches, rows, v_len, split, eps=1e-6):
+    call("opp_linear_q_f16", ptr(x16), ptr(wq), ptr(ksum), ptr(out), batches, rows, wq.shape[0],
+         float(v_len), float(eps), int(split), stream())
+    return out
+
+
+def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=None, out16=None,
+              out32=None, eps=1e-5):
+    _chk(a0, torch.float16, "a0")
+    _chk(w, torch.float16, "w")
+    _chk(resid, torch.float16, "resid")
+    planes = 2 if split else 1
+    k0 = a0.shape[-1] // planes
+    k1 = a1.shape[-1] // planes if a1 is not None else 0
+    n = w.shape[-2]
+    call("opp_linear_ln", ptr(a0), k0, ptr(a1), k1, ptr(w), int(w_batched), ptr(gamma), ptr(beta),
+         float(eps), ptr(resid), ptr(out16), ptr(out32), batches, rows, n, int(split), stream())
+
+
+def kv_chunks(s):
+    return _lib.load().opp_kv_chunks(s)
+
+
+def kv_state(kv16, part, merge_w, mt, ksum, batches, s, d, v_len, split):
+    call("opp_kv_partial", ptr(kv16), ptr(part), batches, s, d, int(split), stream())
+    call("opp_kv_finalize", ptr(part), ptr(merge_w), ptr(mt), ptr(ksum), batches, kv_chunks(s), d,
+         float(v_len), int(split), stream())
+
+
+def sim_tiles(cols):
+    return _lib.load().opp_sim_tiles(cols)
+
+
+def sim_lse(a, b, batches, rows, cols, k, scale, part_m, part_s, lse, split):
+    tiles = sim_tiles(cols)
+    call("opp_sim_lse", ptr(a), ptr(b), ptr(part_m), ptr(part_s), batches, rows, cols, k,
+         float(scale), int(split), stream())
+    call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse), batches * rows, tiles, stream())
+
+
+def sim_conf(a, b, lse_own, lse_other, own_is_pt, conf, batches, rows, cols, k, scale, part_val,
+             part_idx, best_val, best_idx, split):
+    tiles = sim_tiles(cols)
+    call("opp_sim_conf", ptr(a), ptr(b), ptr(lse_own), ptr(lse_other), int(own_is_pt), ptr(conf),
+         ptr(part_val), ptr(part_idx), batches, rows, cols, k, float(scale), int(split), stream())
+    call("opp_best_finalize", ptr(part_val), ptr(part_idx), ptr(best_val), ptr(best_idx),
+         batches * rows, tiles, stream())
+
+
+def match_select(pt_val, pt_idx, px_idx, kpts, img_scale, batch, l, hc, wc, thr, border, cell,
+                 scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count):
+    call("opp_match_select", ptr(pt_val), ptr(pt_idx), ptr(px_idx), ptr(kpts), ptr(img_scale),
+         batch, l, hc, wc, float(thr), int(border), float(cell), ptr(scratch), ptr(b_ids),
+         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), stream())
+
+
+def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stride, n, split):
+    _chk(desc3d, torch.float32, "descriptors3d_db")
+    call("opp_fine_gather", ptr(fine), ptr(desc3d), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x32),
+         ptr(x16), m, hf, wf, wc, stride, n, int(split), stream())
+
+
+def fine_attention(qkv, msg, m, cross, split, eps=1e-6):
+    call("opp_fine_attention", ptr(qkv), ptr(msg), m, int(cross), float(eps), int(split), stream())
+
+
+def fine_match(x32, mkpts_c, b_ids, img_scale, expec_f, mkpts_f, m, fine_scale):
+    call("opp_fine_match", ptr(x32), ptr(mkpts_c), ptr(b_ids), ptr(img_scale), ptr(expec_f),
+         ptr(mkpts_f), m, float(fine_scale), stream())

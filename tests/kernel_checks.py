@@ -12,7 +12,7 @@ import torch
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from onepose_plus_plus_b200 import _lib  # noqa: E402
+from onepose_plus_plus_b200 import _lib, ops  # noqa: E402
 
 DEV = "cuda"
 
@@ -38,261 +38,297 @@ def _elu1(x):
 
 
 # ------------------------------------------------------------------------------------------ GEMMs
+# tolerances: split=1 (hi|lo planes, 3 MMAs) must be fp32-grade; split=0 is plain fp16 operands
+def _tol(split, loose, tight):
+    return tight if split else loose
+
+
+def _planes(x, split):
+    return ops.to_planes(x, split)
+
+
+def _unplanes(t, split):
+    return ops.from_planes(t, split)
+
+
+def _q(x, split):
+    """what the kernel sees: the value represented by the stored planes"""
+    return _unplanes(_planes(x, split), split)
+
+
 def check_linear_act():
-    for (rows, k0, k1, n, act, act_cols) in [(1000, 256, 0, 512, 2, 256), (777, 128, 128, 256, 1, 256),
-                                             (300, 128, 0, 384, 2, 256), (128 * 150 + 5, 256, 256, 512, 1, 512)]:
-        a0 = _rand(rows, k0, seed=1).half()
-        a1 = _rand(rows, k1, seed=2).half() if k1 else None
-        w = _rand(n, k0 + k1, scale=0.05, seed=3).half()
-        out = torch.full((rows, n), float("nan"), device=DEV, dtype=torch.half)
-        _lib.call("opp_linear_act_f16", _lib.ptr(a0), k0, _lib.ptr(a1), k1, _lib.ptr(w),
-                  _lib.ptr(out), rows, n, act, act_cols, _lib.stream())
-        torch.cuda.synchronize()
-        a = a0.float() if a1 is None else torch.cat([a0, a1], 1).float()
-        ref = a @ w.float().t()
-        fn = torch.relu if act == 1 else _elu1
-        ref[:, :act_cols] = fn(ref[:, :act_cols])
-        _close(f"linear_act rows={rows} k={k0}+{k1} n={n}", out, ref, 2e-3, 2e-3)
+    for split in (0, 1):
+        for (rows, k0, k1, n, act, act_cols) in [(1000, 256, 0, 512, 2, 256), (777, 128, 128, 256, 1, 256),
+                                                 (300, 128, 0, 384, 2, 256), (128 * 150 + 5, 256, 256, 512, 1, 512)]:
+            a0f = _rand(rows, k0, seed=1)
+            a1f = _rand(rows, k1, seed=2) if k1 else None
+            wf = _rand(n, k0 + k1, scale=0.05, seed=3)
+            a0 = _planes(a0f, split)
+            a1 = _planes(a1f, split) if k1 else None
+            w = _planes(wf, split)
+            pl = 2 if split else 1
+            out = torch.full((rows, pl * n), float("nan"), device=DEV, dtype=torch.half)
+            _lib.call("opp_linear_act_f16", _lib.ptr(a0), k0, _lib.ptr(a1), k1, _lib.ptr(w),
+                      _lib.ptr(out), rows, n, act, act_cols, split, _lib.stream())
+            torch.cuda.synchronize()
+            a = _q(a0f, split) if a1 is None else torch.cat([_q(a0f, split), _q(a1f, split)], 1)
+            ref = (a.double() @ _q(wf, split).double().t()).float()
+            fn = torch.relu if act == 1 else _elu1
+            ref[:, :act_cols] = fn(ref[:, :act_cols])
+            _close(f"linear_act split={split} rows={rows} k={k0}+{k1} n={n}", _unplanes(out, split), ref,
+                   *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
 
 
 def check_linear_ln():
-    for (B, rows, k0, k1, n, batched, resid, split) in [(2, 1000, 256, 0, 256, True, False, 0),
-                                                        (1, 2600, 128, 0, 128, False, False, 0),
-                                                        (3, 500, 512, 0, 256, False, True, 1),
-                                                        (1, 26 * 70, 256, 0, 128, False, True, 2)]:
-        a0 = _rand(B * rows, k0, seed=1).half()
-        w = _rand(B if batched else 1, n, k0, scale=0.05, seed=3).half()
-        gamma = 1 + 0.1 * _rand(n, seed=4)
-        beta = 0.1 * _rand(n, seed=5)
-        res = _rand(B * rows, n, seed=6) if resid else None
-        out32 = torch.full((B * rows, n), float("nan"), device=DEV)
-        out16 = torch.full((B * rows, n), float("nan"), device=DEV, dtype=torch.half)
-        sp = torch.full((B * rows, 3 * n), float("nan"), device=DEV, dtype=torch.half) if split else None
-        _lib.call("opp_linear_ln", _lib.ptr(a0), k0, None, k1, _lib.ptr(w), int(batched),
-                  _lib.ptr(gamma), _lib.ptr(beta), 1e-5, _lib.ptr(res), _lib.ptr(out32),
-                  _lib.ptr(out16), _lib.ptr(sp), split, B, rows, n, _lib.stream())
-        torch.cuda.synchronize()
-        a = a0.float().view(B, rows, k0)
-        wf = w.float()
-        y = torch.einsum("brk,bnk->brn", a, wf.expand(B, n, k0)).reshape(B * rows, n)
-        ref = F.layer_norm(y, (n,), gamma, beta, 1e-5)
-        if resid:
-            ref = ref + res
-        _close(f"linear_ln out32 B={B} rows={rows} k={k0} n={n}", out32, ref, 1e-3, 2e-3)
-        _close("linear_ln out16", out16, ref, 2e-3, 3e-3)
-        if split:
-            hi = sp[:, :n].float()
-            hi2 = sp[:, n:2 * n] if split == 1 else sp[:, 2 * n:]
-            lo = sp[:, 2 * n:] if split == 1 else sp[:, n:2 * n]
-            assert torch.equal(hi2.float(), hi)
-            _close("linear_ln split hi+lo == out32", hi + lo.float(), out32, 0, 2e-6 * 8)
+    for split in (0, 1):
+        for (B, rows, k0, n, batched, resid, want32) in [(2, 1000, 256, 256, True, False, False),
+                                                         (1, 2600, 128, 128, False, False, True),
+                                                         (3, 500, 512, 256, False, True, False),
+                                                         (1, 26 * 70, 256, 128, False, True, True)]:
+            a0f = _rand(B * rows, k0, seed=1)
+            wf = _rand(B if batched else 1, n, k0, scale=0.05, seed=3)
+            gamma = 1 + 0.1 * _rand(n, seed=4)
+            beta = 0.1 * _rand(n, seed=5)
+            resf = _rand(B * rows, n, seed=6) if resid else None
+            pl = 2 if split else 1
+            out16 = torch.full((B * rows, pl * n), float("nan"), device=DEV, dtype=torch.half)
+            out32 = torch.full((B * rows, n), float("nan"), device=DEV) if want32 else None
+            a0, w = _planes(a0f, split), _planes(wf, split)
+            res = _planes(resf, split) if resid else None
+            _lib.call("opp_linear_ln", _lib.ptr(a0), k0, None, 0, _lib.ptr(w), int(batched),
+                      _lib.ptr(gamma), _lib.ptr(beta), 1e-5, _lib.ptr(res), _lib.ptr(out16),
+                      _lib.ptr(out32), B, rows, n, split, _lib.stream())
+            torch.cuda.synchronize()
+            a = _q(a0f, split).view(B, rows, k0).double()
+            y = torch.einsum("brk,bnk->brn", a, _q(wf, split).double().expand(B, n, k0)).reshape(B * rows, n)
+            ref = F.layer_norm(y, (n,), gamma.double(), beta.double(), 1e-5)
+            if resid:
+                ref = ref + _q(resf, split).double()
+            ref = ref.float()
+            name = f"linear_ln split={split} B={B} rows={rows} k={k0} n={n}"
+            _close(name + " out16", _unplanes(out16, split), ref, *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
+            if want32:
+                _close(name + " out32", out32, ref, *_tol(split, (1e-3, 2e-3), (2e-5, 2e-5)))
 
 
 def check_linear_q():
-    B, rows, d = 2, 1111, 256
-    x = _rand(B * rows, d, seed=1).half()
-    wq = _rand(d, d, scale=0.06, seed=2).half()
-    ksum = _rand(B, d, seed=3).abs() * 100 + 50
-    out = torch.full((B * rows, d), float("nan"), device=DEV, dtype=torch.half)
-    _lib.call("opp_linear_q_f16", _lib.ptr(x), _lib.ptr(wq), _lib.ptr(ksum), _lib.ptr(out), B, rows,
-              d, 4096.0, 1e-6, _lib.stream())
-    torch.cuda.synchronize()
-    q = _elu1(x.float() @ wq.float().t()).view(B, rows, 8, 32)
-    z = 1.0 / (torch.einsum("blhd,bhd->blh", q, ksum.view(B, 8, 32)) + 1e-6)
-    ref = (q * z[..., None] * 4096.0).reshape(B * rows, d)
-    _close("linear_q", out, ref, 2e-3, 1e-4)
+    for split in (0, 1):
+        B, rows, d = 2, 1111, 256
+        xf = _rand(B * rows, d, seed=1)
+        wf = _rand(d, d, scale=0.06, seed=2)
+        ksum = _rand(B, d, seed=3).abs() * 100 + 50
+        pl = 2 if split else 1
+        out = torch.full((B * rows, pl * d), float("nan"), device=DEV, dtype=torch.half)
+        x, wq = _planes(xf, split), _planes(wf, split)
+        _lib.call("opp_linear_q_f16", _lib.ptr(x), _lib.ptr(wq), _lib.ptr(ksum), _lib.ptr(out), B, rows,
+                  d, 4096.0, 1e-6, split, _lib.stream())
+        torch.cuda.synchronize()
+        q = _elu1((_q(xf, split).double() @ _q(wf, split).double().t())).view(B, rows, 8, 32)
+        z = 1.0 / (torch.einsum("blhd,bhd->blh", q, ksum.double().view(B, 8, 32)) + 1e-6)
+        ref = (q * z[..., None] * 4096.0).reshape(B * rows, d).float()
+        _close(f"linear_q split={split}", _unplanes(out, split), ref, *_tol(split, (2e-3, 1e-4), (2e-5, 1e-6)))
 
 
-def _conv_case(B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, resid, tokens):
-    x = torch.zeros(B, H, W, cin_pad, device=DEV)
-    x[..., :cin] = _rand(B, H, W, cin, seed=1)
-    x16 = x.half()
-    w = torch.zeros(cout_pad, k, k, cin_pad, device=DEV)
-    w[:cout, :, :, :cin] = _rand(cout, k, k, cin, scale=1.0 / math.sqrt(k * k * cin), seed=2)
-    w16 = w.half()
+def _conv_case(split, B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, resid, tokens):
+    xf = torch.zeros(B, H, W, cin_pad, device=DEV)
+    xf[..., :cin] = _rand(B, H, W, cin, seed=1)
+    wf = torch.zeros(cout_pad, k, k, cin_pad, device=DEV)
+    wf[:cout, :, :, :cin] = _rand(cout, k, k, cin, scale=1.0 / math.sqrt(k * k * cin), seed=2)
     bias = torch.zeros(cout_pad, device=DEV)
     bias[:cout] = _rand(cout, seed=3) * 0.1
     pad = k // 2
     oh, ow = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    res = None
+    pl = 2 if split else 1
+    x16 = _planes(xf, split)
+    w16 = _planes(wf.reshape(cout_pad, -1), split)
+    res = resf = None
     if resid:
-        res = torch.zeros(B, oh, ow, cout_pad, device=DEV)
-        res[..., :cout] = _rand(B, oh, ow, cout, seed=4)
-        res = res.half()
-    out = torch.full((B, oh, ow, cout_pad), float("nan"), device=DEV, dtype=torch.half)
-    tok32 = tok16 = pe = None
+        resf = torch.zeros(B, oh, ow, cout_pad, device=DEV)
+        resf[..., :cout] = _rand(B, oh, ow, cout, seed=4)
+        res = _planes(resf, split)
+    out = torch.full((B, oh, ow, pl * cout_pad), float("nan"), device=DEV, dtype=torch.half)
+    tok = pe = None
     if tokens:
-        tok32 = torch.full((B, oh * ow, cout_pad), float("nan"), device=DEV)
-        tok16 = torch.full((B, oh * ow, cout_pad), float("nan"), device=DEV, dtype=torch.half)
+        tok = torch.full((B, oh * ow, pl * cout_pad), float("nan"), device=DEV, dtype=torch.half)
         pe = _rand(oh * ow, cout_pad, seed=5)
     _lib.call("opp_conv2d_nhwc", _lib.ptr(x16), _lib.ptr(w16), _lib.ptr(bias), _lib.ptr(res),
-              _lib.ptr(out), B, H, W, cin_pad, cout_pad, k, stride, act, 0.01, _lib.ptr(tok32),
-              _lib.ptr(tok16), _lib.ptr(pe), _lib.stream())
+              _lib.ptr(out), B, H, W, cin_pad, cout_pad, k, stride, act, 0.01, _lib.ptr(tok),
+              _lib.ptr(pe), split, _lib.stream())
     torch.cuda.synchronize()
-    ref = F.conv2d(x16.float().permute(0, 3, 1, 2), w16.float().permute(0, 3, 1, 2), bias,
-                   stride=stride, padding=pad).permute(0, 2, 3, 1)
+    ref = F.conv2d(_q(xf, split).double().permute(0, 3, 1, 2), _q(wf, split).double().permute(0, 3, 1, 2),
+                   bias.double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
     if resid:
-        ref = ref + res.float()
+        ref = ref + _q(resf, split).double()
     if act == 1:
         ref = torch.relu(ref)
     elif act == 2:
         ref = F.leaky_relu(ref, 0.01)
-    name = f"conv k={k} s={stride} {cin}->{cout} {H}x{W} act={act} resid={resid}"
-    _close(name, out, ref, 2e-3, 3e-3)
+    ref = ref.float()
+    name = f"conv split={split} k={k} s={stride} {cin}->{cout} {H}x{W} act={act} resid={resid}"
+    got = _unplanes(out, split)
+    _close(name, got, ref, *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
     if cout_pad > cout:
-        assert out[..., cout:].abs().max().item() == 0.0, "padding channels must stay zero"
+        assert got[..., cout:].abs().max().item() == 0.0, "padding channels must stay zero"
     if tokens:
-        _close(name + " tok32", tok32, ref.reshape(B, oh * ow, cout_pad) + pe, 1e-3, 1e-3)
-        _close(name + " tok16", tok16, ref.reshape(B, oh * ow, cout_pad) + pe, 2e-3, 3e-3)
+        _close(name + " tok", _unplanes(tok, split), ref.reshape(B, oh * ow, cout_pad) + pe,
+               *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
 
 
 def check_conv():
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    _conv_case(2, 64, 64, 128, 128, 128, 128, 3, 1, 1, True, False)
-    _conv_case(1, 64, 96, 128, 128, 196, 208, 3, 2, 1, False, False)
-    _conv_case(2, 32, 48, 196, 208, 196, 208, 3, 1, 2, False, False)
-    _conv_case(1, 64, 64, 128, 128, 196, 208, 1, 2, 0, False, False)
-    _conv_case(2, 30, 40, 256, 256, 256, 256, 1, 1, 0, False, True)
-    _conv_case(1, 60, 80, 196, 208, 256, 256, 3, 2, 1, False, False)
-    _conv_case(1, 24, 40, 256, 256, 196, 208, 3, 1, 0, False, False)
+    for split in (0, 1):
+        _conv_case(split, 2, 64, 64, 128, 128, 128, 128, 3, 1, 1, True, False)
+        _conv_case(split, 1, 64, 96, 128, 128, 196, 208, 3, 2, 1, False, False)
+        _conv_case(split, 2, 32, 48, 196, 208, 196, 208, 3, 1, 2, False, False)
+        _conv_case(split, 1, 64, 64, 128, 128, 196, 208, 1, 2, 0, False, False)
+        _conv_case(split, 2, 30, 40, 256, 256, 256, 256, 1, 1, 0, False, True)
+        _conv_case(split, 1, 60, 80, 196, 208, 256, 256, 3, 2, 1, False, False)
+        _conv_case(split, 1, 24, 40, 256, 256, 196, 208, 3, 1, 0, False, False)
 
 
 def check_sim():
-    for (B, L, S, K) in [(2, 700, 520, 768), (1, 300, 100, 768), (1, 5000, 4096, 768)]:
-        a = _rand(B, L, K, scale=0.5, seed=1).half()
-        b = _rand(B, S, K, scale=0.5, seed=2).half()
-        scale = 1.0 / (256 * 0.0801)
-        sim = torch.einsum("blk,bsk->bls", a.float(), b.float()) * scale
-        lse_pt_ref = torch.logsumexp(sim, 2)   # over query cells, per 3D point
-        lse_px_ref = torch.logsumexp(sim, 1)   # over 3D points, per query cell
-        lib = _lib.load()
-        ts, tl = lib.opp_sim_tiles(S), lib.opp_sim_tiles(L)
+    for split in (0, 1):
+        for (B, L, S, K) in [(2, 700, 520, 256), (1, 300, 100, 256), (1, 5000, 4096, 256)]:
+            af = _rand(B, L, K, scale=0.9, seed=1)
+            bf = _rand(B, S, K, scale=0.9, seed=2)
+            a, b = _planes(af, split), _planes(bf, split)
+            scale = 1.0 / (256 * 0.0801)
+            sim = (torch.einsum("blk,bsk->bls", _q(af, split).double(), _q(bf, split).double()) * scale)
+            lse_pt_ref = torch.logsumexp(sim, 2).float()   # over query cells, per 3D point
+            lse_px_ref = torch.logsumexp(sim, 1).float()   # over 3D points, per query cell
+            lib = _lib.load()
+            ts, tl = lib.opp_sim_tiles(S), lib.opp_sim_tiles(L)
 
-        def lse(x, y, rows, cols, tiles):
-            pm = torch.empty(B * rows, tiles, device=DEV)
-            ps = torch.empty(B * rows, tiles, device=DEV)
-            out = torch.empty(B, rows, device=DEV)
-            _lib.call("opp_sim_lse", _lib.ptr(x), _lib.ptr(y), _lib.ptr(pm), _lib.ptr(ps), B, rows,
-                      cols, K, scale, _lib.stream())
-            _lib.call("opp_lse_finalize", _lib.ptr(pm), _lib.ptr(ps), _lib.ptr(out), B * rows, tiles,
-                      _lib.stream())
-            return out
+            def lse(x, y, rows, cols, tiles):
+                pm = torch.empty(B * rows, tiles, device=DEV)
+                ps = torch.empty(B * rows, tiles, device=DEV)
+                out = torch.empty(B, rows, device=DEV)
+                _lib.call("opp_sim_lse", _lib.ptr(x), _lib.ptr(y), _lib.ptr(pm), _lib.ptr(ps), B, rows,
+                          cols, K, scale, split, _lib.stream())
+                _lib.call("opp_lse_finalize", _lib.ptr(pm), _lib.ptr(ps), _lib.ptr(out), B * rows, tiles,
+                          _lib.stream())
+                return out
 
-        lse_pt = lse(a, b, L, S, ts)
-        lse_px = lse(b, a, S, L, tl)
-        torch.cuda.synchronize()
-        _close(f"sim lse_pt B={B} L={L} S={S}", lse_pt, lse_pt_ref, 1e-5, 1e-4)
-        _close("sim lse_px", lse_px, lse_px_ref, 1e-5, 1e-4)
+            lse_pt = lse(a, b, L, S, ts)
+            lse_px = lse(b, a, S, L, tl)
+            torch.cuda.synchronize()
+            _close(f"sim split={split} lse_pt B={B} L={L} S={S}", lse_pt, lse_pt_ref, 1e-5, 1e-4)
+            _close("sim lse_px", lse_px, lse_px_ref, 1e-5, 1e-4)
 
-        conf = torch.full((B, L, S), float("nan"), device=DEV)
+            conf = torch.full((B, L, S), float("nan"), device=DEV)
 
-        def best(x, y, own, other, own_is_pt, rows, cols, tiles, conf_out):
-            pv = torch.empty(B * rows, tiles, device=DEV)
-            pi = torch.empty(B * rows, tiles, device=DEV, dtype=torch.int32)
-            bv = torch.empty(B, rows, device=DEV)
-            bi = torch.empty(B, rows, device=DEV, dtype=torch.int32)
-            _lib.call("opp_sim_conf", _lib.ptr(x), _lib.ptr(y), _lib.ptr(own), _lib.ptr(other),
-                      own_is_pt, _lib.ptr(conf_out), _lib.ptr(pv), _lib.ptr(pi), B, rows, cols, K,
-                      scale, _lib.stream())
-            _lib.call("opp_best_finalize", _lib.ptr(pv), _lib.ptr(pi), _lib.ptr(bv), _lib.ptr(bi),
-                      B * rows, tiles, _lib.stream())
-            return bv, bi
+            def best(x, y, own, other, own_is_pt, rows, cols, tiles, conf_out):
+                pv = torch.empty(B * rows, tiles, device=DEV)
+                pi = torch.empty(B * rows, tiles, device=DEV, dtype=torch.int32)
+                bv = torch.empty(B, rows, device=DEV)
+                bi = torch.empty(B, rows, device=DEV, dtype=torch.int32)
+                _lib.call("opp_sim_conf", _lib.ptr(x), _lib.ptr(y), _lib.ptr(own), _lib.ptr(other),
+                          own_is_pt, _lib.ptr(conf_out), _lib.ptr(pv), _lib.ptr(pi), B, rows, cols, K,
+                          scale, split, _lib.stream())
+                _lib.call("opp_best_finalize", _lib.ptr(pv), _lib.ptr(pi), _lib.ptr(bv), _lib.ptr(bi),
+                          B * rows, tiles, _lib.stream())
+                return bv, bi
 
-        pt_val, pt_idx = best(a, b, lse_pt, lse_px, 1, L, S, ts, conf)
-        px_val, px_idx = best(b, a, lse_px, lse_pt, 0, S, L, tl, None)
-        torch.cuda.synchronize()
-        conf_ref = torch.softmax(sim, 1) * torch.softmax(sim, 2)
-        _close("sim conf", conf, conf_ref, 2e-4, 1e-7)
-        # maxima must agree with the conf matrix the kernel itself wrote (index-exact)
-        v, i = conf.max(2)
-        assert torch.equal(pt_idx.long(), i), "row argmax mismatch"
-        assert torch.equal(pt_val, v), "row max mismatch"
-        v, i = conf.max(1)
-        _close("sim col max", px_val, v, 1e-5, 1e-9)
-        agree = (px_idx.long() == i).float().mean().item()
-        print(f"  col argmax agreement {agree:.6f}")
-        assert agree > 0.999
+            pt_val, pt_idx = best(a, b, lse_pt, lse_px, 1, L, S, ts, conf)
+            px_val, px_idx = best(b, a, lse_px, lse_pt, 0, S, L, tl, None)
+            torch.cuda.synchronize()
+            conf_ref = (torch.softmax(sim, 1) * torch.softmax(sim, 2)).float()
+            _close("sim conf", conf, conf_ref, 5e-4, 1e-7)
+            # maxima must agree with the conf matrix the kernel itself wrote (index-exact)
+            v, i = conf.max(2)
+            assert torch.equal(pt_idx.long(), i), "row argmax mismatch"
+            assert torch.equal(pt_val, v), "row max mismatch"
+            v, i = conf.max(1)
+            _close("sim col max", px_val, v, 1e-5, 1e-9)
+            agree = (px_idx.long() == i).float().mean().item()
+            print(f"  col argmax agreement {agree:.6f}")
+            assert agree > 0.999
 
 
 # ------------------------------------------------------------------------------------------ SIMT
 def check_conv1():
-    B, H, W, C = 2, 96, 128, 128
-    img = torch.rand(B, 1, H, W, device=DEV)
-    w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
-    bias = _rand(C, seed=3) * 0.1
-    out = torch.full((B, H // 2, W // 2, C), float("nan"), device=DEV, dtype=torch.half)
-    w_t = w.view(C, 49).t().contiguous()
-    _lib.call("opp_conv1_7x7", _lib.ptr(img), _lib.ptr(w_t), _lib.ptr(bias), _lib.ptr(out), B, H, W,
-              C, _lib.stream())
-    torch.cuda.synchronize()
-    ref = torch.relu(F.conv2d(img, w, bias, stride=2, padding=3)).permute(0, 2, 3, 1)
-    _close("conv1_7x7", out, ref, 1e-3, 1e-3)
+    for split in (0, 1):
+        B, H, W, C = 2, 96, 128, 128
+        img = torch.rand(B, 1, H, W, device=DEV)
+        w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
+        bias = _rand(C, seed=3) * 0.1
+        pl = 2 if split else 1
+        out = torch.full((B, H // 2, W // 2, pl * C), float("nan"), device=DEV, dtype=torch.half)
+        w_t = w.view(C, 49).t().contiguous()
+        _lib.call("opp_conv1_7x7", _lib.ptr(img), _lib.ptr(w_t), _lib.ptr(bias), _lib.ptr(out), B, H, W,
+                  C, split, _lib.stream())
+        torch.cuda.synchronize()
+        ref = torch.relu(F.conv2d(img.double(), w.double(), bias.double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
+        _close(f"conv1_7x7 split={split}", _unplanes(out, split), ref, *_tol(split, (1e-3, 1e-3), (2e-6, 2e-6)))
 
 
 def check_upsample():
-    B, h, w, C = 2, 30, 40, 208
-    a = _rand(B, 2 * h, 2 * w, C, seed=1).half()
-    b = _rand(B, h, w, C, seed=2).half()
-    out = torch.empty_like(a)
-    _lib.call("opp_upsample2x_add", _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), B, h, w, C,
-              _lib.stream())
-    torch.cuda.synchronize()
-    up = F.interpolate(b.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="bilinear",
-                       align_corners=True).permute(0, 2, 3, 1)
-    _close("upsample2x_add", out, a.float() + up, 1e-3, 2e-3)
+    for split in (0, 1):
+        B, h, w, C = 2, 30, 40, 208
+        af, bf = _rand(B, 2 * h, 2 * w, C, seed=1), _rand(B, h, w, C, seed=2)
+        a, b = _planes(af, split), _planes(bf, split)
+        out = torch.empty_like(a)
+        _lib.call("opp_upsample2x_add", _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), B, h, w, C, split,
+                  _lib.stream())
+        torch.cuda.synchronize()
+        up = F.interpolate(_q(bf, split).permute(0, 3, 1, 2), scale_factor=2.0, mode="bilinear",
+                           align_corners=True).permute(0, 2, 3, 1)
+        _close(f"upsample2x_add split={split}", _unplanes(out, split), _q(af, split) + up,
+               *_tol(split, (1e-3, 2e-3), (2e-6, 2e-6)))
 
 
 def check_kpt_encode():
-    B, N = 2, 1003
-    kpts = torch.rand(B, N, 3, device=DEV) - 0.5
-    desc = _rand(B, 256, N, seed=1)
-    dims = [3, 32, 64, 128, 256]
-    ws = [_rand(dims[i + 1], dims[i], scale=1 / math.sqrt(dims[i]), seed=10 + i) for i in range(4)]
-    bs = [_rand(dims[i + 1], seed=20 + i) * 0.1 for i in range(4)]
-    stats = torch.empty(B, 4, device=DEV)
-    tok32 = torch.empty(B, N, 256, device=DEV)
-    tok16 = torch.empty(B, N, 256, device=DEV, dtype=torch.half)
-    _lib.call("opp_kpt_stats", _lib.ptr(kpts), _lib.ptr(stats), B, N, _lib.stream())
-    wts = [w.t().contiguous() for w in ws]
-    _lib.call("opp_kpt_encode", _lib.ptr(kpts), _lib.ptr(stats), _lib.ptr(desc), _lib.ptr(wts[0]),
-              _lib.ptr(bs[0]), _lib.ptr(wts[1]), _lib.ptr(bs[1]), _lib.ptr(wts[2]), _lib.ptr(bs[2]),
-              _lib.ptr(wts[3]), _lib.ptr(bs[3]), _lib.ptr(tok32), _lib.ptr(tok16), B, N,
-              _lib.stream())
-    torch.cuda.synchronize()
-    ext = (kpts[0].max(0).values - kpts[0].min(0).values).max() * 0.6
-    x = (kpts - kpts.mean(1, keepdim=True)) / ext
-    for i in range(4):
-        x = x @ ws[i].t() + bs[i]
-        if i < 3:
-            m = x.mean(-1, keepdim=True)
-            v = x.var(-1, unbiased=False, keepdim=True)
-            x = torch.relu((x - m) / torch.sqrt(v + 1e-5))
-    ref = desc.transpose(1, 2) + x
-    _close("kpt_encode tok32", tok32, ref, 1e-4, 1e-4)
-    _close("kpt_encode tok16", tok16, ref, 2e-3, 2e-3)
+    for split in (0, 1):
+        B, N = 2, 1003
+        kpts = torch.rand(B, N, 3, device=DEV) - 0.5
+        desc = _rand(B, 256, N, seed=1)
+        dims = [3, 32, 64, 128, 256]
+        ws = [_rand(dims[i + 1], dims[i], scale=1 / math.sqrt(dims[i]), seed=10 + i) for i in range(4)]
+        bs = [_rand(dims[i + 1], seed=20 + i) * 0.1 for i in range(4)]
+        stats = torch.empty(B, 4, device=DEV)
+        pl = 2 if split else 1
+        tok = torch.empty(B, N, pl * 256, device=DEV, dtype=torch.half)
+        _lib.call("opp_kpt_stats", _lib.ptr(kpts), _lib.ptr(stats), B, N, _lib.stream())
+        wts = [w.t().contiguous() for w in ws]
+        _lib.call("opp_kpt_encode", _lib.ptr(kpts), _lib.ptr(stats), _lib.ptr(desc), _lib.ptr(wts[0]),
+                  _lib.ptr(bs[0]), _lib.ptr(wts[1]), _lib.ptr(bs[1]), _lib.ptr(wts[2]), _lib.ptr(bs[2]),
+                  _lib.ptr(wts[3]), _lib.ptr(bs[3]), _lib.ptr(tok), B, N, split, _lib.stream())
+        torch.cuda.synchronize()
+        ext = (kpts[0].max(0).values - kpts[0].min(0).values).max() * 0.6
+        x = (kpts - kpts.mean(1, keepdim=True)) / ext
+        for i in range(4):
+            x = x @ ws[i].t() + bs[i]
+            if i < 3:
+                m = x.mean(-1, keepdim=True)
+                v = x.var(-1, unbiased=False, keepdim=True)
+                x = torch.relu((x - m) / torch.sqrt(v + 1e-5))
+        ref = desc.transpose(1, 2) + x
+        _close(f"kpt_encode split={split}", _unplanes(tok, split), ref, *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
 
 
 def check_kv_state():
-    B, S, d = 2, 1000, 256
-    kv = torch.cat([_rand(B, S, d, seed=1).abs() + 0.1, _rand(B, S, d, seed=2)], 2).half()
-    mw = _rand(d, d, scale=0.06, seed=3)
-    chunks = (S + 255) // 256
-    part = torch.empty(B, chunks, 8, 33, 32, device=DEV)
-    mt = torch.empty(B, d, d, device=DEV, dtype=torch.half)
-    ksum = torch.empty(B, d, device=DEV)
-    _lib.call("opp_kv_partial", _lib.ptr(kv), _lib.ptr(part), B, S, d, _lib.stream())
-    _lib.call("opp_kv_finalize", _lib.ptr(part), _lib.ptr(mw), _lib.ptr(mt), _lib.ptr(ksum), B,
-              chunks, d, float(S), _lib.stream())
-    torch.cuda.synchronize()
-    K = kv[..., :d].float().view(B, S, 8, 32)
-    V = kv[..., d:].float().view(B, S, 8, 32)
-    KV = torch.einsum("bshd,bshv->bhdv", K, V) / S
-    ref_ksum = K.sum(1).reshape(B, d)
-    # mt[b][c][h*32+dd] = sum_v mw[c][h*32+v] KV[b][h][dd][v]
-    ref_mt = torch.einsum("chv,bhdv->bchd", mw.view(d, 8, 32), KV).reshape(B, d, d)
-    _close("kv ksum", ksum, ref_ksum, 1e-5, 1e-3)
-    _close("kv mt", mt, ref_mt, 2e-3, 1e-4)
+    for split in (0, 1):
+        B, S, d = 2, 1000, 256
+        kvf = torch.cat([_rand(B, S, d, seed=1).abs() + 0.1, _rand(B, S, d, seed=2)], 2)
+        kv = _planes(kvf, split)
+        mw = _rand(d, d, scale=0.06, seed=3)
+        chunks = _lib.load().opp_kv_chunks(S)
+        pl = 2 if split else 1
+        part = torch.empty(B, chunks, 8, 33, 32, device=DEV)
+        mt = torch.empty(B, d, pl * d, device=DEV, dtype=torch.half)
+        ksum = torch.empty(B, d, device=DEV)
+        _lib.call("opp_kv_partial", _lib.ptr(kv), _lib.ptr(part), B, S, d, split, _lib.stream())
+        _lib.call("opp_kv_finalize", _lib.ptr(part), _lib.ptr(mw), _lib.ptr(mt), _lib.ptr(ksum), B,
+                  chunks, d, float(S), split, _lib.stream())
+        torch.cuda.synchronize()
+        kvq = _q(kvf, split).double()
+        K = kvq[..., :d].view(B, S, 8, 32)
+        V = kvq[..., d:].view(B, S, 8, 32)
+        KV = torch.einsum("bshd,bshv->bhdv", K, V) / S
+        ref_ksum = K.sum(1).reshape(B, d).float()
+        # mt[b][c][h*32+dd] = sum_v mw[c][h*32+v] KV[b][h][dd][v]
+        ref_mt = torch.einsum("chv,bhdv->bchd", mw.double().view(d, 8, 32), KV).reshape(B, d, d).float()
+        _close(f"kv ksum split={split}", ksum, ref_ksum, 1e-5, 1e-3)
+        _close("kv mt", _unplanes(mt, split), ref_mt, *_tol(split, (2e-3, 1e-4), (2e-5, 1e-6)))
 
 
 def check_match_select():
@@ -344,51 +380,58 @@ def check_match_select():
 
 
 def check_fine():
-    B, hf, wf, N, wc = 2, 64, 80, 500, 20
-    M = 333
-    fine = _rand(B, hf, wf, 128, seed=1).half()
-    desc = _rand(B, 128, N, seed=2)
-    g = torch.Generator().manual_seed(1)
-    b_ids = torch.randint(0, B, (M,), generator=g).sort().values.to(DEV)
-    i_ids = torch.randint(0, N, (M,), generator=g).to(DEV)
-    j_ids = torch.randint(0, (hf // 4) * wc, (M,), generator=g).to(DEV)
-    x32 = torch.empty(M * 26, 128, device=DEV)
-    x16 = torch.empty(M * 26, 128, device=DEV, dtype=torch.half)
-    _lib.call("opp_fine_gather", _lib.ptr(fine), _lib.ptr(desc), _lib.ptr(b_ids), _lib.ptr(i_ids),
-              _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, _lib.stream())
-    torch.cuda.synchronize()
-    unf = F.unfold(fine.float().permute(0, 3, 1, 2), kernel_size=5, stride=4, padding=2)
-    unf = unf.view(B, 128, 25, -1).permute(0, 3, 2, 1)  # n l ww c
-    ref = torch.cat([desc.permute(0, 2, 1)[b_ids, i_ids][:, None], unf[b_ids, j_ids]], 1)
-    assert torch.equal(x32.view(M, 26, 128), ref), "fine_gather mismatch"
-    assert torch.equal(x16.float(), x32.half().float())
-    print("  fine_gather exact")
-
-    # attention
-    qkv = torch.cat([_rand(M * 26, 256, seed=3).abs() + 0.05, _rand(M * 26, 128, seed=4)], 1).half()
-    for cross in (0, 1):
-        msg = torch.empty(M * 26, 128, device=DEV, dtype=torch.half)
-        _lib.call("opp_fine_attention", _lib.ptr(qkv), _lib.ptr(msg), M, cross, 1e-6, _lib.stream())
+    for split in (0, 1):
+        B, hf, wf, N, wc = 2, 64, 80, 500, 20
+        M = 333
+        pl = 2 if split else 1
+        finef = _rand(B, hf, wf, 128, seed=1)
+        fine = _planes(finef, split)
+        desc = _rand(B, 128, N, seed=2)
+        g = torch.Generator().manual_seed(1)
+        b_ids = torch.randint(0, B, (M,), generator=g).sort().values.to(DEV)
+        i_ids = torch.randint(0, N, (M,), generator=g).to(DEV)
+        j_ids = torch.randint(0, (hf // 4) * wc, (M,), generator=g).to(DEV)
+        x32 = torch.empty(M * 26, 128, device=DEV)
+        x16 = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
+        _lib.call("opp_fine_gather", _lib.ptr(fine), _lib.ptr(desc), _lib.ptr(b_ids), _lib.ptr(i_ids),
+                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, _lib.stream())
         torch.cuda.synchronize()
-        t = qkv.float().view(M, 26, 3, 8, 16)
-        Q, K, V = t[:, :, 0], t[:, :, 1], t[:, :, 2]
+        unf = F.unfold(_q(finef, split).permute(0, 3, 1, 2), kernel_size=5, stride=4, padding=2)
+        unf = unf.view(B, 128, 25, -1).permute(0, 3, 2, 1)  # n l ww c
+        ref = torch.cat([desc.permute(0, 2, 1)[b_ids, i_ids][:, None], unf[b_ids, j_ids]], 1)
+        assert torch.equal(x32.view(M, 26, 128), ref), "fine_gather mismatch"
+        _close(f"fine_gather planes split={split}", _unplanes(x16, split), x32, *_tol(split, (1e-3, 1e-3), (1e-6, 1e-6)))
 
-        def attn(q, k, v):
-            vl = v.size(1)
-            kvm = torch.einsum("nshd,nshv->nhdv", k, v / vl)
-            z = 1 / (torch.einsum("nlhd,nhd->nlh", q, k.sum(1)) + 1e-6)
-            return torch.einsum("nlhd,nhdv,nlh->nlhv", q, kvm, z) * vl
+        # attention
+        qkvf = torch.cat([_rand(M * 26, 256, seed=3).abs() + 0.05, _rand(M * 26, 128, seed=4)], 1)
+        qkv = _planes(qkvf, split)
+        for cross in (0, 1):
+            msg = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
+            _lib.call("opp_fine_attention", _lib.ptr(qkv), _lib.ptr(msg), M, cross, 1e-6, split, _lib.stream())
+            torch.cuda.synchronize()
+            t = _q(qkvf, split).double().view(M, 26, 3, 8, 16)
+            Q, K, V = t[:, :, 0], t[:, :, 1], t[:, :, 2]
 
-        if cross == 0:
-            m3 = attn(Q[:, :1], K[:, :1], V[:, :1])
-            m2 = attn(Q[:, 1:], K[:, 1:], V[:, 1:])
-        else:
-            m3 = attn(Q[:, :1], K[:, 1:], V[:, 1:])
-            m2 = attn(Q[:, 1:], K[:, :1], V[:, :1])
-        ref = torch.cat([m3, m2], 1).reshape(M * 26, 128)
-        _close(f"fine_attention cross={cross}", msg, ref, 2e-3, 1e-3)
+            def attn(q, k, v):
+                vl = v.size(1)
+                kvm = torch.einsum("nshd,nshv->nhdv", k, v / vl)
+                z = 1 / (torch.einsum("nlhd,nhd->nlh", q, k.sum(1)) + 1e-6)
+                return torch.einsum("nlhd,nhdv,nlh->nlhv", q, kvm, z) * vl
+
+            if cross == 0:
+                m3 = attn(Q[:, :1], K[:, :1], V[:, :1])
+                m2 = attn(Q[:, 1:], K[:, 1:], V[:, 1:])
+            else:
+                m3 = attn(Q[:, :1], K[:, 1:], V[:, 1:])
+                m2 = attn(Q[:, 1:], K[:, :1], V[:, :1])
+            ref = torch.cat([m3, m2], 1).reshape(M * 26, 128).float()
+            _close(f"fine_attention split={split} cross={cross}", _unplanes(msg, split), ref,
+                   *_tol(split, (2e-3, 1e-3), (2e-5, 2e-6)))
 
     # matching
+    B, M = 2, 333
+    g = torch.Generator().manual_seed(1)
+    b_ids = torch.randint(0, B, (M,), generator=g).sort().values.to(DEV)
     xf = _rand(M * 26, 128, seed=5)
     mkc = torch.rand(M, 2, device=DEV) * 300
     scale = torch.rand(B, 2, device=DEV) + 0.5

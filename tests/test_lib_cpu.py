@@ -1,0 +1,98 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol declared in
+include/opp_b200.h, the drop-in module has the reference's state-dict layout, and the product
+fails loudly (no fallback) without a GPU."""
+import ctypes
+import os
+import pickle
+import re
+
+import pytest
+import torch
+
+from oracle import oracle, workload
+from onepose_plus_plus_b200 import OnePosePlus_model, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "opp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(opp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/opp_b200.h but not exported"
+    bound = set(_lib.SIGNATURES) | set(_lib.PLAIN)
+    assert bound == set(syms), f"ctypes binding and header disagree: {bound ^ set(syms)}"
+
+
+def test_version_and_tiles_without_gpu():
+    lib = _lib.load()
+    assert lib.opp_version() >= 100
+    assert lib.opp_sim_tiles(4096) == 16 and lib.opp_sim_tiles(5000) == 20 and lib.opp_sim_tiles(100) == 1
+    assert lib.opp_kv_chunks(4096) * 128 >= 4096
+
+
+def test_state_dict_is_the_reference_layout():
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG)
+    sd = workload.synthetic_state_dict(0)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    m.load_state_dict(sd, strict=True)
+    assert sum(p.numel() for p in m.parameters()) == 10_226_480
+    assert "dense_pos_encoding.pe" not in m.state_dict()  # non-persistent, position_encoding.py:35
+    m2 = pickle.loads(pickle.dumps(m))  # Ray ships the module object
+    assert torch.equal(m2.state_dict()["backbone.conv1.weight"], sd["backbone.conv1.weight"])
+
+
+def test_position_encoding_matches_oracle():
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG)
+    pe = oracle.position_encoding_sine(256, 24, 40)
+    assert torch.allclose(m.dense_pos_encoding.pe[0, :, :24, :40], pe, atol=1e-6)
+
+
+def test_no_cpu_fallback_and_config_errors():
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
+    data = workload.random_workload(64, 64, 50)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(data)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(data)
+    import copy
+    bad = copy.deepcopy(oracle.DEFAULT_CONFIG)
+    bad["loftr_backbone"]["type"] = "VGG"
+    with pytest.raises(ValueError):
+        OnePosePlus_model(bad)
+    bad = copy.deepcopy(oracle.DEFAULT_CONFIG)
+    bad["coarse_matching"]["type"] = "sinkhorn"
+    with pytest.raises(NotImplementedError):
+        OnePosePlus_model(bad)
+    bad = copy.deepcopy(oracle.DEFAULT_CONFIG)
+    bad["keypoints_encoding"]["type"] = "other"
+    with pytest.raises(NotImplementedError):
+        OnePosePlus_model(bad)
+
+
+def test_bn_folding_and_planes_roundtrip():
+    from onepose_plus_plus_b200 import ops
+    x = torch.randn(7, 64) * 3
+    for split in (0, 1):
+        back = ops.from_planes(ops.to_planes(x, split), split)
+        tol = 2e-6 if split else 2e-3
+        assert torch.allclose(back, x, rtol=tol, atol=tol)
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG)
+    m.load_state_dict(workload.synthetic_state_dict(0))
+    P = m._prepare(torch.device("cpu"))
+    sd = m.state_dict()
+    w, b = P["layer2.0.conv1"]
+    assert w.shape == (208, 2 * 9 * 128) and b.shape == (208,)
+    g = sd["backbone.layer2.0.bn1.weight"] / torch.sqrt(sd["backbone.layer2.0.bn1.running_var"] + 1e-5)
+    ref = (sd["backbone.layer2.0.conv1.weight"] * g[:, None, None, None]).permute(0, 2, 3, 1).reshape(196, -1)
+    got = ops.from_planes(w, 1)[:196]
+    assert torch.allclose(got, ref, atol=1e-6)
+    assert got.shape[1] == 9 * 128 and ops.from_planes(w, 1)[196:].abs().max() == 0

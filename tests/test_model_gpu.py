@@ -1,0 +1,109 @@
+"""pytest -m gpu: end-to-end parity of the CUDA OnePosePlus_model (called through its public
+forward(data) API -> C ABI) against (i) the golden fixtures produced by the unmodified reference
+and (ii) the CPU oracle on seeded planted workloads, plus size-independent properties at the
+BASELINE sizes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, workload
+from tests import golden_io, parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd():
+    return workload.synthetic_state_dict(0)
+
+
+@pytest.mark.parametrize("case", golden_io.cases())
+def test_golden_parity(case):
+    data, z = golden_io.load(case)
+    got = parity.run_cuda(data)
+    rep = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
+    print(case, rep)
+    conf = got["conf_matrix"].cpu()
+    assert np.allclose(conf.max(2).values.numpy(), z["conf_rowmax"], atol=1e-3)
+    assert np.allclose(conf.max(1).values.numpy(), z["conf_colmax"], atol=1e-3)
+    assert np.allclose(conf.flatten()[torch.from_numpy(z["conf_sample_idx"])].numpy(), z["conf_sample"], atol=1e-3)
+    assert got["m_bids"].cpu().tolist() == z["m_bids"].tolist()
+    assert tuple(got["q_hw_c"]) == tuple(s // 8 for s in data["query_image"].shape[2:])
+    assert got["W"] == 5 and got["bs"] == data["query_image"].shape[0]
+
+
+@pytest.mark.parametrize("shape", [(512, 512, 5000, 3000, 1, True),    # BASELINE configs[0]/[1]
+                                   (480, 640, 2500, 1500, 1, False),   # config 5 image shape (S = 4800)
+                                   (256, 320, 1500, 700, 3, True)])
+def test_planted_parity_vs_oracle(shape):
+    h, w, n, npl, B, with_scale = shape
+    sd = _sd()
+    data, meta = workload.planted_workload(sd, h, w, n, npl, batch=B, with_scale=with_scale)
+    ref = {k: v.clone() for k, v in data.items()}
+    oracle.forward(sd, ref)
+    got = parity.run_cuda(data)
+    rep = parity.compare(got, ref)
+    print(shape, rep)
+    assert rep["M"] >= 50 * B
+    assert (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+
+
+def test_no_match_path():
+    # BASELINE configs[0] taken literally (random descriptors): M = 0, empty outputs, no error
+    data = workload.random_workload(192, 192, 2000)
+    got = parity.run_cuda(data)
+    assert got["b_ids"].numel() == 0 and got["mconf"].numel() == 0
+    assert got["expec_f"].shape == (0, 3) and got["mkpts_query_f"].shape == (0, 2)
+    assert got["mkpts_3d_db"].shape == (0, 3) and got["conf_matrix"].shape == (1, 2000, 576)
+    ref = {k: v.clone() for k, v in data.items()}
+    oracle.forward(_sd(), ref)
+    assert (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+
+
+def test_properties_at_baseline_size():
+    """512x512, 5000 points, batch 4: determinism, ordering, mutual uniqueness, batch independence."""
+    sd = _sd()
+    data, _ = workload.planted_workload(sd, 512, 512, 5000, 3000, batch=4)
+    a = parity.run_cuda(data)
+    b = parity.run_cuda(data)
+    for k in ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f", "conf_matrix"):
+        assert torch.equal(a[k], b[k]), f"{k} is not run-to-run deterministic"
+    bi = list(zip(a["b_ids"].tolist(), a["i_ids"].tolist()))
+    assert bi == sorted(bi) and len(set(bi)) == len(bi)
+    bj = list(zip(a["b_ids"].tolist(), a["j_ids"].tolist()))
+    assert len(set(bj)) == len(bj), "a query cell may be matched at most once (mutual NN)"
+    assert (a["mconf"] > 0.1).all()
+    jy, jx = a["j_ids"] // 64, a["j_ids"] % 64
+    assert (jy >= 2).all() and (jx >= 2).all(), "top/left border cells are masked"
+    conf = a["conf_matrix"]
+    assert conf.min().item() >= 0 and conf.max().item() <= 1.0 + 1e-5
+    # image 0 alone gives the same matches as image 0 inside the batch
+    single = {k: v[:1].clone() for k, v in data.items()}
+    s = parity.run_cuda(single)
+    m0 = a["b_ids"] == 0
+    assert torch.equal(s["i_ids"], a["i_ids"][m0]) and torch.equal(s["j_ids"], a["j_ids"][m0])
+    assert torch.allclose(s["mconf"], a["mconf"][m0], atol=1e-5)
+    assert torch.allclose(s["mkpts_query_f"], a["mkpts_query_f"][m0], atol=1e-3)
+
+
+def test_weights_reload_invalidates_plan():
+    m = parity.cuda_model(seed=0)
+    data, z = golden_io.load("planted_128x160_n400")
+    d0 = {k: v.cuda() for k, v in data.items()}
+    m(d0)
+    sd1 = workload.synthetic_state_dict(1)
+    m.load_state_dict(sd1, strict=True)
+    d1 = {k: v.cuda() for k, v in data.items()}
+    m(d1)
+    assert not torch.equal(d0["conf_matrix"], d1["conf_matrix"])
+    m.load_state_dict(workload.synthetic_state_dict(0), strict=True)
+    d2 = {k: v.cuda() for k, v in data.items()}
+    m(d2)
+    assert torch.equal(d0["conf_matrix"], d2["conf_matrix"])
+
+
+def test_fast_fp16_mode_runs_and_is_close():
+    data, z = golden_io.load("planted_96x128_n300_b2")
+    got = parity.run_cuda(data, precision="fp16")
+    conf = got["conf_matrix"].cpu()
+    assert np.allclose(conf.max(2).values.numpy(), z["conf_rowmax"], atol=8e-2)
+    assert abs(got["b_ids"].numel() - len(z["b_ids"])) <= 5
