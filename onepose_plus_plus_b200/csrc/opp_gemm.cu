@@ -4,6 +4,7 @@
 // maps for the call, and launches one persistent kernel.  No allocation, no synchronisation.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -101,6 +102,20 @@ template <int A_MODE, class Epi>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream) {
   s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split);
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("OPP_DEBUG_SKIP");
+      dbg = e ? atoi(e) : 0;
+    }
+    s.debug_skip = dbg;
+    static int cap = -1;
+    if (cap < 0) {
+      const char* e = getenv("OPP_STAGES");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap > 1 && s.stages > cap) s.stages = cap;
+  }
   const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split);
   auto kern = gemm_kernel<A_MODE, Epi>;
   static bool attr_set = false;  // one per template instantiation
@@ -109,12 +124,36 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const long long total = (long long)s.batches * s.m_tiles * s.n_tiles;
+  const long long total = (long long)s.batches * s.msup * s.n_tiles;   // super tiles
   if (total == 0) return OPP_OK;
-  const int grid = (int)(total < num_sms() ? total : num_sms());
-  kern<<<grid, kGemmThreads, smem, stream>>>(maps, s, ep);
-  OPP_CHECK_CUDA(cudaGetLastError());
+  const int max_clusters = num_sms() / s.cluster;
+  const int n_clusters = (int)(total < max_clusters ? total : max_clusters);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_clusters * s.cluster);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = s.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  OPP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, s, ep));
   return OPP_OK;
+}
+
+// cluster size for a GEMM: W-tile slices must be whole 8-row swizzle groups; $OPP_CLUSTER overrides
+static int pick_cluster(int block_n, int m_tiles) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("OPP_CLUSTER");
+    forced = e ? atoi(e) : 0;
+  }
+  int c = forced > 0 ? forced : 2;
+  while (c > 1 && (block_n % (8 * c) != 0 || m_tiles < c)) c >>= 1;
+  return c < 1 ? 1 : c;
 }
 
 static int pick_block_n(int n) {
@@ -162,8 +201,11 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   }
   maps.a[2] = maps.a[0];
   maps.a[3] = maps.a[0];
+  s.cluster = pick_cluster(s.block_n, s.m_tiles);
+  s.msup = (s.m_tiles + s.cluster - 1) / s.cluster;
   const long long kt = (long long)planes * (k0 + k1);
-  return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt, s.block_n);
+  return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt,
+                  s.block_n / s.cluster);
 }
 
 }  // namespace opp
@@ -182,6 +224,7 @@ int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const voi
   int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, split);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
+  OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
   EpiStoreF16::Params ep{(__half*)out, (long long)n * (split ? 2 : 1), split ? n : 0, act,
                          act_cols};
   return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
@@ -282,7 +325,9 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   const long long kplane = (long long)ksize * ksize * c_in_pad;
   s.b_lo = (int)kplane;
   const long long kt = kplane * planes;
-  rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n);
+  s.cluster = pick_cluster(s.block_n, s.m_tiles);
+  s.msup = (s.m_tiles + s.cluster - 1) / s.cluster;
+  rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n / s.cluster);
   if (rc) return rc;
   EpiConv::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias,
                      (const __half*)resid, act, slope, (__half*)tok, pe};

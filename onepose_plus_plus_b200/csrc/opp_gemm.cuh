@@ -35,7 +35,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;               // 64 fp16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 8;
-constexpr int kEpiSmemBytes = 8192;
+constexpr int kEpiParamBytes = 4096;            // bias / gamma,beta / lse vectors
+constexpr int kEpiSmemBytes = kEpiParamBytes + 4 * 4608;   // + one transpose buffer per epilogue warp
 constexpr int kGemmThreads = 192;
 
 enum AMode : int { A_ROWS = 0, A_CONV = 1 };
@@ -55,6 +56,10 @@ struct GemmShape {
   int k_chunks;     // number of 64-wide K chunks per tile (per plane)
   int stages;
   int b_batched;    // W operand has a leading batch dim
+  int cluster;      // CTAs per cluster (1, 2, 4): they work on adjacent M tiles of the same
+                    // (batch, n_tile) in lockstep and share the W tile through TMA multicast
+  int msup;         // ceil(m_tiles / cluster)
+  int debug_skip;   // TIMING EXPERIMENTS ONLY ($OPP_DEBUG_SKIP): 1 = skip W loads, 2 = skip A loads
   int split;        // operands are (hi|lo) plane pairs; 3 MMAs per K-step
   int b_lo;         // element offset of W's lo plane inside a row (= K total)
   // A_ROWS
@@ -74,16 +79,159 @@ struct GemmShape {
 struct EpiCtx {
   uint32_t tmem;   // accumulator address of this thread's lane quarter, column 0 of the tile
   int b, m_tile, n_tile;
+  int q;           // TMEM lane quarter of this warp: rows 32q .. 32q+31 of the tile
+  int a_mode;
   int row;         // row within the batch (pixel index within the image for A_CONV)
   long long grow;  // b*rows + row
   bool valid;      // row is inside the tensor
   int n0;          // first global column of the tile
   int ncols;       // valid columns in this tile (multiple of 8)
   int etid;        // 0..127 within the epilogue group
-  float* smem;     // kEpiSmemBytes of scratch shared by the epilogue group
+  float* smem;     // kEpiParamBytes of scratch shared by the epilogue group
+  uint8_t* wstage; // kWarpStageBytes private to this warp (transpose buffer for coalesced I/O)
 };
 
 __device__ __forceinline__ void epi_sync() { named_bar_sync(1, 128); }
+
+// (global row, validity) of row `rr` (0..31) of this warp's quarter of the tile
+__device__ __forceinline__ bool epi_row_info(const GemmShape& s, const EpiCtx& c, int rr,
+                                             long long& grow, int& row) {
+  const int rit = c.q * 32 + rr;
+  bool ok;
+  if (c.a_mode == A_ROWS) {
+    row = c.m_tile * kBlockM + rit;
+    ok = row < s.rows;
+  } else {
+    const int ty = c.m_tile / s.tiles_x;
+    const int tx = c.m_tile - ty * s.tiles_x;
+    const int ly = rit / s.tile_w;
+    const int oy = ty * s.tile_h + ly;
+    const int ox = tx * s.tile_w + (rit - ly * s.tile_w);
+    ok = oy < s.out_h && ox < s.out_w;
+    row = oy * s.out_w + ox;
+  }
+  grow = (long long)c.b * s.rows + row;
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-staged, coalesced epilogue I/O.  Accumulator rows live one-per-thread, but global memory
+// wants whole 64/128-byte segments: every 32x32 chunk goes through a per-warp shared-memory
+// transpose buffer (row stride padded by 16 B so both access directions are conflict-light).
+// ---------------------------------------------------------------------------------------------
+constexpr int kStageRowH = 80;    // 32 fp16 (64 B) + 16 B pad
+constexpr int kStageRowF = 144;   // 32 fp32 (128 B) + 16 B pad
+constexpr int kWarpStageBytes = 32 * kStageRowF;   // 4608 B >= 32*80
+
+// fp16 planes: v = this lane's 32 values for global columns [gcol, gcol+32); nvalid = valid
+// columns of the chunk (multiple of 8).  Writes hi (and lo when lo_off != 0).
+__device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCtx& c, __half* out,
+                                                 long long ld, int lo_off, int gcol,
+                                                 const float* v, int nvalid) {
+  const int lane = threadIdx.x & 31;
+  uint8_t* st = c.wstage;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane == 1 && lo_off == 0) break;
+    uint4* mine = reinterpret_cast<uint4*>(st + lane * kStageRowH);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      uint4 u;
+      if (plane == 0) {
+        u.x = pack_half2(v[8 * g + 0], v[8 * g + 1]);
+        u.y = pack_half2(v[8 * g + 2], v[8 * g + 3]);
+        u.z = pack_half2(v[8 * g + 4], v[8 * g + 5]);
+        u.w = pack_half2(v[8 * g + 6], v[8 * g + 7]);
+      } else {
+        float l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          l[j] = v[8 * g + j] - __half2float(__float2half_rn(v[8 * g + j]));
+        u.x = pack_half2(l[0], l[1]);
+        u.y = pack_half2(l[2], l[3]);
+        u.z = pack_half2(l[4], l[5]);
+        u.w = pack_half2(l[6], l[7]);
+      }
+      mine[g] = u;
+    }
+    __syncwarp();
+    const int seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      long long grow;
+      int row;
+      const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 8 < nvalid;
+      if (ok)
+        *reinterpret_cast<uint4*>(out + grow * ld + plane * lo_off + gcol + seg * 8) =
+            *reinterpret_cast<const uint4*>(st + rr * kStageRowH + seg * 16);
+    }
+    __syncwarp();
+  }
+}
+
+// r[32] += (hi + lo) of this lane's row, global columns [gcol, gcol+32), read coalesced
+__device__ __forceinline__ void staged_load_add_h32(const GemmShape& s, const EpiCtx& c,
+                                                    const __half* src, long long ld, int lo_off,
+                                                    int gcol, float* r, int nvalid) {
+  const int lane = threadIdx.x & 31;
+  uint8_t* st = c.wstage;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane == 1 && lo_off == 0) break;
+    const int seg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      long long grow;
+      int row;
+      const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 8 < nvalid;
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (ok)
+        u = *reinterpret_cast<const uint4*>(src + grow * ld + plane * lo_off + gcol + seg * 8);
+      *reinterpret_cast<uint4*>(st + rr * kStageRowH + seg * 16) = u;
+    }
+    __syncwarp();
+    const uint4* mine = reinterpret_cast<const uint4*>(st + lane * kStageRowH);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = mine[g];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        r[8 * g + 2 * j] += f.x;
+        r[8 * g + 2 * j + 1] += f.y;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 rows: out[grow*ld + gcol + j] = v[j]; requires 16-byte aligned row segments
+__device__ __forceinline__ void staged_store_f32(const GemmShape& s, const EpiCtx& c, float* out,
+                                                 long long ld, int gcol, const float* v,
+                                                 int nvalid) {
+  const int lane = threadIdx.x & 31;
+  uint8_t* st = c.wstage;
+  float4* mine = reinterpret_cast<float4*>(st + lane * kStageRowF);
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    mine[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  __syncwarp();
+  const int seg = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = (lane >> 3) + 4 * i;
+    long long grow;
+    int row;
+    const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 4 < nvalid;
+    if (ok)
+      *reinterpret_cast<float4*>(out + grow * ld + gcol + seg * 4) =
+          *reinterpret_cast<const float4*>(st + rr * kStageRowF + seg * 16);
+  }
+  __syncwarp();
+}
 
 // =============================================================================================
 // Epilogues.  Outputs that feed later GEMMs are written as (hi|lo) plane pairs when
@@ -98,27 +246,21 @@ struct EpiStoreF16 {
     long long ld;   // row stride in elements
     int out_lo;     // 0 or n_total
     int act;
-    int act_cols;
+    int act_cols;   // multiple of 32
   };
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
       const int g0 = c.n0 + col;
+      const int act = g0 < p.act_cols ? p.act : 0;
+      if (act == 1) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (g0 + j < p.act_cols) {
-          if (p.act == 1) v[j] = fmaxf(v[j], 0.f);
-          else if (p.act == 2) v[j] = elu_plus_one(v[j]);
-        }
-      }
-      if (c.valid) {
-        __half* row = p.out + c.grow * p.ld;
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (act == 2) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (col + g * 8 < c.ncols) store_split8(row, g0 + g * 8, v + g * 8, p.out_lo);
+        for (int j = 0; j < 32; ++j) v[j] = elu_plus_one(v[j]);
       }
-    }
+      staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, c.ncols - col);
+    });
   }
 };
 
@@ -140,9 +282,7 @@ struct EpiQ {
     for (int i = c.etid; i < c.ncols; i += 128)
       c.smem[i] = p.ksum[(long long)c.b * s.n_total + c.n0 + i];
     epi_sync();
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
       float dot = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -152,12 +292,8 @@ struct EpiQ {
       const float z = p.v_len / (dot + p.eps);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= z;
-      if (c.valid) {
-        __half* row = p.out + c.grow * p.ld;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) store_split8(row, c.n0 + col + g * 8, v + g * 8, p.out_lo);
-      }
-    }
+      staged_store_h32(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, 32);
+    });
   }
 };
 
@@ -174,6 +310,8 @@ struct EpiLN {
     int out_lo;
     float* out32;         // fp32 [rows][n_total] or null
   };
+  // Row-per-thread loads/stores measured faster here than the warp-staged path (the three TMEM
+  // passes already saturate the instruction budget of the four epilogue warps).
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     float* g_s = c.smem;
     float* b_s = c.smem + 256;
@@ -253,40 +391,30 @@ struct EpiConv {
     epi_sync();
     for (int i = c.etid; i < c.ncols; i += 128) c.smem[i] = p.bias[c.n0 + i];
     epi_sync();
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
-      if (!c.valid) continue;
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
       const int g0 = c.n0 + col;
+      const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (col + g * 8 >= c.ncols) break;
-        float* vv = v + g * 8;
+      for (int j = 0; j < 32; ++j) v[j] += c.smem[(col + j) & 255];
+      if (p.resid) staged_load_add_h32(s, c, p.resid, p.ld, p.out_lo, g0, v, nvalid);
+      if (p.act == 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) vv[j] += c.smem[col + g * 8 + j];
-        if (p.resid) {
-          float r[8];
-          load_split8(p.resid + c.grow * p.ld, g0 + g * 8, r, p.out_lo);
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == 2) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] += r[j];
-        }
-        if (p.act == 1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = fmaxf(vv[j], 0.f);
-        } else if (p.act == 2) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) vv[j] = vv[j] > 0.f ? vv[j] : vv[j] * p.slope;
-        }
-        if (p.out) store_split8(p.out + c.grow * p.ld, g0 + g * 8, vv, p.out_lo);
-        if (p.tok) {
-          const float* pe = p.pe + (long long)c.row * s.n_total + g0 + g * 8;
-          float t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) t[j] = vv[j] + pe[j];
-          store_split8(p.tok + c.grow * p.ld, g0 + g * 8, t, p.out_lo);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
       }
-    }
+      if (p.out) staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, nvalid);
+      if (p.tok) {
+        if (c.valid) {
+          const float* pe = p.pe + (long long)c.row * s.n_total + g0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) v[j] += pe[j];
+        }
+        staged_store_h32(s, c, p.tok, p.ld, p.out_lo, g0, v, nvalid);
+      }
+    });
   }
 };
 
@@ -300,21 +428,17 @@ struct EpiLse {
   };
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     float m = -INFINITY;
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col + j < c.ncols) m = fmaxf(m, v[j] * p.scale);
-    }
+    });
     float sum = 0.f;
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col + j < c.ncols) sum += expf(v[j] * p.scale - m);
-    }
+    });
     if (c.valid) {
       p.part_m[c.grow * s.n_tiles + c.n_tile] = m;
       p.part_s[c.grow * s.n_tiles + c.n_tile] = sum;
@@ -345,9 +469,8 @@ struct EpiConf {
     const float lown = c.valid ? p.lse_own[c.grow] : 0.f;
     float best = -1.f;
     int best_idx = c.n0;
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    const bool vec_ok = (s.n_total & 3) == 0;
+    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x2 = 2.f * (v[j] * p.scale);
@@ -359,9 +482,9 @@ struct EpiConf {
           best_idx = c.n0 + col + j;
         }
       }
-      if (c.valid && p.conf) {
+      if (p.conf && c.valid) {
         float* dst = p.conf + c.grow * (long long)s.n_total + c.n0 + col;
-        if ((s.n_total & 3) == 0) {
+        if (vec_ok) {
           float4* o4 = reinterpret_cast<float4*>(dst);
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -373,7 +496,7 @@ struct EpiConf {
             if (col + j < c.ncols) dst[j] = v[j];
         }
       }
-    }
+    });
     if (c.valid) {
       p.part_val[c.grow * s.n_tiles + c.n_tile] = best;
       p.part_idx[c.grow * s.n_tiles + c.n_tile] = best_idx;
@@ -410,7 +533,14 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   const int lane = threadIdx.x & 31;
   const int acc_stride = s.block_n <= 128 ? 128 : 256;
   const uint32_t tmem_cols = 2 * acc_stride;
-  const int tiles_per_batch = s.m_tiles * s.n_tiles;
+  // tile schedule: "super tiles" of `cluster` adjacent M tiles; every CTA of a cluster walks the
+  // same sequence, so the multicast W loads and the cross-CTA stage releases stay in lockstep.
+  const int csize = s.cluster;
+  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int cluster_id = blockIdx.x / csize;
+  const int n_clusters = gridDim.x / csize;
+  const int tiles_per_batch = s.msup * s.n_tiles;
   const int total_tiles = s.batches * tiles_per_batch;
 
   if (warp == 0 && lane == 0) {
@@ -420,7 +550,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   if (warp == 2 && lane == 0) {
     for (int i = 0; i < s.stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], csize);   // one tcgen05.commit arrival from every CTA of the cluster
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -433,113 +563,156 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     tmem_relinquish();
   }
   tc_fence_before();
-  __syncthreads();
+  if (csize > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps run their loops warp-uniformly (all 32 lanes evaluate the same
+  // addresses, coordinates and descriptors, so they live in uniform registers) and only the
+  // asynchronous-issue instructions sit under elect_one().  A single divergent lane doing the
+  // whole loop made instruction issue, not the tensor pipe, the limiter (~110 clk per MMA).
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int b = t / tiles_per_batch;
-        const int r = t - b * tiles_per_batch;
-        const int m_tile = r / s.n_tiles;
-        const int n_tile = r - m_tile * s.n_tiles;
-        int ox0 = 0, oy0 = 0;
-        if (A_MODE == A_CONV) {
-          const int ty = m_tile / s.tiles_x;
-          oy0 = ty * s.tile_h;
-          ox0 = (m_tile - ty * s.tiles_x) * s.tile_w;
-        }
-        for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], a_stage + b_stage);
-          uint8_t* sa = smem_a + stage * a_stage;
-          uint8_t* sb = smem_b + stage * b_stage;
-          int kb;
-          if (A_MODE == A_ROWS) {
-            const bool first = chunk < s.k_chunks_a0;
-            const int kc = (first ? chunk : chunk - s.k_chunks_a0) * kBlockK;
-            const CUtensorMap* am = first ? &maps.a[0] : &maps.a[1];
-            tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
-            if (s.split)
-              tma_load_3d(am, &full[stage], sa + kABytes, kc + (first ? s.a0_lo : s.a1_lo),
-                          m_tile * kBlockM, b);
-            kb = chunk * kBlockK;
-          } else {
-            const int tap = chunk / s.conv_cchunks;
-            const int cc = chunk - tap * s.conv_cchunks;
-            const int ky = tap / s.conv_kw;
-            const int kx = tap - ky * s.conv_kw;
-            int dy = ky - s.conv_pad, dx = kx - s.conv_pad, mi = 0;
-            if (s.conv_stride == 2) {
-              const int py = dy & 1, px = dx & 1;
-              dy = (dy - py) >> 1;
-              dx = (dx - px) >> 1;
-              mi = py * 2 + px;
+    int stage = 0;
+    uint32_t phase = 0;
+    const bool skip_b = (s.debug_skip & 1) != 0, skip_a = (s.debug_skip & 2) != 0;
+    const uint32_t tx_bytes = (skip_a ? 0 : a_stage) + (skip_b ? 0 : b_stage);
+    for (int t = cluster_id; t < total_tiles; t += n_clusters) {
+      const int b = t / tiles_per_batch;
+      const int r = t - b * tiles_per_batch;
+      const int msi = r / s.n_tiles;
+      const int n_tile = r - msi * s.n_tiles;
+      const int m_tile = msi * csize + crank;
+      int ox0 = 0, oy0 = 0;
+      if (A_MODE == A_CONV) {
+        const int ty = m_tile / s.tiles_x;
+        oy0 = ty * s.tile_h;
+        ox0 = (m_tile - ty * s.tiles_x) * s.tile_w;
+      }
+      const int bb = s.b_batched ? b : 0;
+      const int nrow0 = n_tile * s.block_n;
+      // incremental (tap, channel-chunk) counters instead of per-chunk divisions
+      int cc = 0, ky = 0, kx = 0, kb_tap = 0;
+      for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sa = smem_a + stage * a_stage;
+        uint8_t* sb = smem_b + stage * b_stage;
+        int kb;
+        if (A_MODE == A_ROWS) {
+          const bool first = chunk < s.k_chunks_a0;
+          const int kc = (first ? chunk : chunk - s.k_chunks_a0) * kBlockK;
+          const CUtensorMap* am = first ? &maps.a[0] : &maps.a[1];
+          const int lo = first ? s.a0_lo : s.a1_lo;
+          kb = chunk * kBlockK;
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], tx_bytes);
+            if (!skip_a) {
+              tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
+              if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
             }
-            tma_load_4d(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
+          }
+        } else {
+          int dy = ky - s.conv_pad, dx = kx - s.conv_pad, mi = 0;
+          if (s.conv_stride == 2) {
+            const int py = dy & 1, px = dx & 1;
+            dy = (dy - py) >> 1;
+            dx = (dx - px) >> 1;
+            mi = py * 2 + px;
+          }
+          kb = kb_tap + cc * kBlockK;
+          if (elect_one()) {
+            mbar_expect_tx(&full[stage], tx_bytes);
+            if (!skip_a) {
+              tma_load_4d(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
+              if (s.split)
+                tma_load_4d(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
+                            ox0 + dx, oy0 + dy, b);
+            }
+          }
+          if (++cc == s.conv_cchunks) {
+            cc = 0;
+            kb_tap += s.conv_c;
+            if (++kx == s.conv_kw) {
+              kx = 0;
+              ++ky;
+            }
+          }
+        }
+        if (!skip_b && elect_one()) {
+          if (csize == 1) {
+            tma_load_3d(&maps.b, &full[stage], sb, kb, nrow0, bb);
+            if (s.split) tma_load_3d(&maps.b, &full[stage], sb + b_bytes, s.b_lo + kb, nrow0, bb);
+          } else {
+            // this CTA fetches rows [crank*slice, +slice) of the W tile and multicasts them into
+            // every CTA of the cluster (each CTA's full barrier expects the whole tile)
+            const int slice = s.block_n / csize;
+            const int soff = crank * slice * (kBlockK * 2);
+            const int nrow = nrow0 + crank * slice;
+            tma_load_3d_mc(&maps.b, &full[stage], sb + soff, kb, nrow, bb, cmask);
             if (s.split)
-              tma_load_4d(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
-                          ox0 + dx, oy0 + dy, b);
-            kb = tap * s.conv_c + cc * kBlockK;
+              tma_load_3d_mc(&maps.b, &full[stage], sb + b_bytes + soff, s.b_lo + kb, nrow, bb, cmask);
           }
-          const int bb = s.b_batched ? b : 0;
-          tma_load_3d(&maps.b, &full[stage], sb, kb, n_tile * s.block_n, bb);
-          if (s.split)
-            tma_load_3d(&maps.b, &full[stage], sb + b_bytes, s.b_lo + kb, n_tile * s.block_n, bb);
-          if (++stage == s.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == s.stages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kBlockM, s.block_n);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tempty[acc], acc_phase ^ 1);
+    const uint32_t idesc = make_idesc_f16(kBlockM, s.block_n);
+    const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * acc_stride;
+      int cc = 0;
+      for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_stride;
-        for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          int ksteps = 4;
-          if (A_MODE == A_CONV) {
-            const int cc = chunk % s.conv_cchunks;
-            const int rem = (s.conv_c - cc * kBlockK) >> 4;
-            ksteps = rem < 4 ? rem : 4;
-          }
-          const uint32_t sa = smem_u32(smem_a + stage * a_stage);
-          const uint32_t sb = smem_u32(smem_b + stage * b_stage);
-          const uint64_t a_hi = make_kmajor_sw128_desc(sa);
-          const uint64_t b_hi = make_kmajor_sw128_desc(sb);
-          // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
-          for (int k = 0; k < ksteps; ++k)
-            tc_mma_f16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc, (chunk | k) != 0);
-          if (s.split) {
-            const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes);
-            const uint64_t b_lo = make_kmajor_sw128_desc(sb + b_bytes);
-            for (int k = 0; k < ksteps; ++k) tc_mma_f16(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc, 1);
-            for (int k = 0; k < ksteps; ++k) tc_mma_f16(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc, 1);
-          }
-          tc_commit(&empty[stage]);
-          if (++stage == s.stages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        int ksteps = 4;
+        if (A_MODE == A_CONV) {
+          const int rem = (s.conv_c - cc * kBlockK) >> 4;
+          ksteps = rem < 4 ? rem : 4;
+          if (++cc == s.conv_cchunks) cc = 0;
         }
-        tc_commit(&tfull[acc]);
+        const uint32_t sa = sa0 + stage * a_stage;
+        const uint32_t sb = sb0 + stage * b_stage;
+        const uint64_t a_hi = make_kmajor_sw128_desc(sa);
+        const uint64_t b_hi = make_kmajor_sw128_desc(sb);
+        const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes);
+        const uint64_t b_lo = make_kmajor_sw128_desc(sb + b_bytes);
+        if (elect_one()) {
+          // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+          tc_mma_f16(d_tmem, a_hi, b_hi, idesc, chunk != 0);
+#pragma unroll
+          for (int k = 1; k < 4; ++k)
+            if (k < ksteps) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc);
+          if (s.split) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ksteps) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (k < ksteps) tc_mma_f16_acc(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc);
+          }
+          if (csize > 1) tc_commit_mc(&empty[stage], cmask); else tc_commit(&empty[stage]);
+        }
+        __syncwarp();
+        if (++stage == s.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) tc_commit(&tfull[acc]);
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
@@ -548,30 +721,22 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     EpiCtx c;
     c.etid = (warp - 2) * 32 + lane;
     c.smem = epi_smem;
+    c.q = q;
+    c.a_mode = A_MODE;
+    c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + (warp - 2) * kWarpStageBytes;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       c.b = t / tiles_per_batch;
       const int r = t - c.b * tiles_per_batch;
-      c.m_tile = r / s.n_tiles;
-      c.n_tile = r - c.m_tile * s.n_tiles;
+      const int msi = r / s.n_tiles;
+      c.n_tile = r - msi * s.n_tiles;
+      c.m_tile = msi * csize + crank;   // may lie past the last M tile: rows are then invalid
       c.n0 = c.n_tile * s.block_n;
       const int rem = s.n_total - c.n0;
       c.ncols = rem < s.block_n ? rem : s.block_n;
-      if (A_MODE == A_ROWS) {
-        c.row = c.m_tile * kBlockM + row_in_tile;
-        c.valid = c.row < s.rows;
-      } else {
-        const int ty = c.m_tile / s.tiles_x;
-        const int tx = c.m_tile - ty * s.tiles_x;
-        const int ly = row_in_tile / s.tile_w;
-        const int oy = ty * s.tile_h + ly;
-        const int ox = tx * s.tile_w + (row_in_tile - ly * s.tile_w);
-        c.valid = oy < s.out_h && ox < s.out_w;
-        c.row = oy * s.out_w + ox;
-      }
-      c.grow = (long long)c.b * s.rows + c.row;
+      c.valid = epi_row_info(s, c, lane, c.grow, c.row);
       c.tmem = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -582,7 +747,8 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   }
 
   tc_fence_before();
-  __syncthreads();
+  // a CTA must outlive every multicast write / remote barrier arrival aimed at it
+  if (csize > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);

@@ -436,9 +436,11 @@ class OnePosePlus_model(nn.Module):
         ops.linear_act(x, msg, L["mlp0"], h, B * lx, 1, 512, split)
         ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, B * lx, split, resid=x, out16=out)
 
-    def _coarse_transformer(self, q2, d3, B, S, N):
+    def _coarse_transformer(self, q2, d3, B, S, N, d3_shared=None):
         """LocalFeatureTransformer.forward (transformer.py:133-171): self layers update each
-        sequence from itself; cross layers update BOTH from the pre-update tensors."""
+        sequence from itself; cross layers update BOTH from the pre-update tensors.
+        `d3_shared` ([1, N, C]): every batch element carries the same bank, so the 3D side of a
+        leading self layer is image-independent — computed once and broadcast."""
         dev = q2.device
         f16 = torch.float16
         pl = 2 if self.split else 1
@@ -452,8 +454,15 @@ class OnePosePlus_model(nn.Module):
             self_layer = name == "self"
             self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
                                 S if self_layer else N, o2)
-            self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
-                                N if self_layer else S, o3)
+            if d3_shared is not None and self_layer and i == 0:
+                o3_1 = self._buf("d3_shared_out", (1, N, pl * 256), f16, dev)
+                self._encoder_layer(L, "c3s_", d3_shared, d3_shared, 1, N, N, o3_1)
+                o3.copy_(o3_1.expand(B, -1, -1))
+            else:
+                if d3_shared is not None and i == 0:
+                    cur3.copy_(d3_shared.expand(B, -1, -1))
+                self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
+                                    N if self_layer else S, o3)
             cur2, cur3 = o2, o3
         return cur2, cur3
 
@@ -584,18 +593,26 @@ class OnePosePlus_model(nn.Module):
             data.update({"bs": B, "q_hw_i": img.shape[2:]})
             q2, fine_map, (hc, wc) = self._backbone(img)
             data.update({"q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3])})
-            kpts = data["keypoints3d"].contiguous().float()
-            dsel = data["descriptors3d_coarse_db"] if "descriptors3d_coarse_db" in data \
+            kraw = data["keypoints3d"]
+            draw = data["descriptors3d_coarse_db"] if "descriptors3d_coarse_db" in data \
                 else data["descriptors3d_db"]
-            dsel = dsel.contiguous().float()
-            N = kpts.shape[1]
-            if dsel.shape[1] != 256:
+            N = kraw.shape[1]
+            if draw.shape[1] != 256:
                 raise ValueError("coarse descriptors must be 256-d")
             pl = 2 if self.split else 1
+            # one bank shared by the whole batch (expanded view, stride 0): encode it once
+            shared = B > 1 and kraw.stride(0) == 0 and draw.stride(0) == 0
+            kpts = kraw.contiguous().float()
             d3 = self._buf("d3_0", (B, N, pl * 256), torch.float16, dev)
-            ops.kpt_encode(kpts, dsel, self._plan["kpt_mlp"],
-                           self._buf("kpt_stats", (B, 4), torch.float32, dev), d3, self.split)
-            q2, d3 = self._coarse_transformer(q2, d3, B, hc * wc, N)
+            d3_shared = None
+            if shared:
+                d3_shared = self._buf("d3_shared_in", (1, N, pl * 256), torch.float16, dev)
+                ops.kpt_encode(kpts[:1].contiguous(), draw[:1].contiguous().float(), self._plan["kpt_mlp"],
+                               self._buf("kpt_stats", (1, 4), torch.float32, dev), d3_shared, self.split)
+            else:
+                ops.kpt_encode(kpts, draw.contiguous().float(), self._plan["kpt_mlp"],
+                               self._buf("kpt_stats", (B, 4), torch.float32, dev), d3, self.split)
+            q2, d3 = self._coarse_transformer(q2, d3, B, hc * wc, N, d3_shared)
             local = dict(data)
             local["keypoints3d"] = kpts
             M, img_scale = self._coarse_matching(q2, d3, local, B, N, hc, wc)

@@ -107,3 +107,19 @@ def test_fast_fp16_mode_runs_and_is_close():
     conf = got["conf_matrix"].cpu()
     assert np.allclose(conf.max(2).values.numpy(), z["conf_rowmax"], atol=8e-2)
     assert abs(got["b_ids"].numel() - len(z["b_ids"])) <= 5
+
+
+def test_shared_bank_views_match_materialised_bank():
+    """A bank passed as stride-0 expanded views (one object, many images) takes the encode-once
+    path; results must equal the per-batch-element path bit for bit."""
+    sd = _sd()
+    data, _ = workload.planted_workload(sd, 256, 320, 1500, 700, batch=3)
+    a = parity.run_cuda(data)
+    shared = dict(data)
+    for k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db"):
+        shared[k] = data[k][:1].cuda().expand(3, -1, -1)
+    shared = {k: (v if v.is_cuda else v.cuda()) for k, v in shared.items()}
+    parity.cuda_model()(shared)
+    torch.cuda.synchronize()
+    for k in ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f", "conf_matrix"):
+        assert torch.equal(a[k], shared[k]), k
