@@ -101,7 +101,7 @@ static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long ro
 template <int A_MODE, class Epi>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream) {
-  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split);
+  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair);
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -116,7 +116,7 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
     }
     if (cap > 1 && s.stages > cap) s.stages = cap;
   }
-  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split);
+  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair);
   auto kern = gemm_kernel<A_MODE, Epi>;
   static bool attr_set = false;  // one per template instantiation
   if (!attr_set) {
@@ -140,8 +140,40 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  OPP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, s, ep));
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, s, ep);
+  if (le != cudaSuccess) {
+    set_last_error("cudaLaunchKernelEx failed: %s (grid %d cluster %d pair %d smem %d stages %d "
+                   "block_n %d m_tiles %d n_tiles %d batches %d)",
+                   cudaGetErrorString(le), n_clusters * s.cluster, s.cluster, s.pair, smem, s.stages,
+                   s.block_n, s.m_tiles, s.n_tiles, s.batches);
+    return OPP_ERR_CUDA;
+  }
   return OPP_OK;
+}
+
+static int pick_cluster(int block_n, int m_tiles);
+
+// $OPP_PAIR=0 disables the cta_group::2 (CTA pair) mode
+static int pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OPP_PAIR");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// decide the CTA grouping of a GEMM: a cta_group::2 pair (256 x N tiles) when there are at least
+// two M tiles, else a multicast cluster / single CTAs
+static void pick_grouping(GemmShape& s) {
+  if (pair_enabled() && s.m_tiles >= 2 && s.block_n % 16 == 0) {
+    s.pair = 1;
+    s.cluster = 2;
+  } else {
+    s.pair = 0;
+    s.cluster = pick_cluster(s.block_n, s.m_tiles);
+  }
+  s.msup = (s.m_tiles + s.cluster - 1) / s.cluster;
 }
 
 // cluster size for a GEMM: W-tile slices must be whole 8-row swizzle groups; $OPP_CLUSTER overrides
@@ -151,9 +183,12 @@ static int pick_cluster(int block_n, int m_tiles) {
     const char* e = getenv("OPP_CLUSTER");
     forced = e ? atoi(e) : 0;
   }
-  int c = forced > 0 ? forced : 2;
-  while (c > 1 && (block_n % (8 * c) != 0 || m_tiles < c)) c >>= 1;
-  return c < 1 ? 1 : c;
+  // The kernel contains cta_group::2 code paths, and such kernels cannot be launched with a
+  // cluster size of 1 (cudaErrorInvalidClusterSize): the minimum is a 2-CTA multicast cluster,
+  // whose second CTA simply finds its M tile out of range when there is only one.
+  int c = forced > 1 ? forced : 2;
+  while (c > 2 && (block_n % (8 * c) != 0 || m_tiles < c)) c >>= 1;
+  return c;
 }
 
 static int pick_block_n(int n) {
@@ -201,8 +236,7 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   }
   maps.a[2] = maps.a[0];
   maps.a[3] = maps.a[0];
-  s.cluster = pick_cluster(s.block_n, s.m_tiles);
-  s.msup = (s.m_tiles + s.cluster - 1) / s.cluster;
+  pick_grouping(s);
   const long long kt = (long long)planes * (k0 + k1);
   return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt,
                   s.block_n / s.cluster);
@@ -325,8 +359,7 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   const long long kplane = (long long)ksize * ksize * c_in_pad;
   s.b_lo = (int)kplane;
   const long long kt = kplane * planes;
-  s.cluster = pick_cluster(s.block_n, s.m_tiles);
-  s.msup = (s.m_tiles + s.cluster - 1) / s.cluster;
+  pick_grouping(s);
   rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n / s.cluster);
   if (rc) return rc;
   EpiConv::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias,

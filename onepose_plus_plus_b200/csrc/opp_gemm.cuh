@@ -59,6 +59,8 @@ struct GemmShape {
   int cluster;      // CTAs per cluster (1, 2, 4): they work on adjacent M tiles of the same
                     // (batch, n_tile) in lockstep and share the W tile through TMA multicast
   int msup;         // ceil(m_tiles / cluster)
+  int pair;         // 1: the two CTAs of the cluster form ONE cta_group::2 MMA: 256 x N tile, each
+                    // CTA holds 128 rows of A, N/2 rows of W and 128 rows of the accumulator
   int debug_skip;   // TIMING EXPERIMENTS ONLY ($OPP_DEBUG_SKIP): 1 = skip W loads, 2 = skip A loads
   int split;        // operands are (hi|lo) plane pairs; 3 MMAs per K-step
   int b_lo;         // element offset of W's lo plane inside a row (= K total)
@@ -257,7 +259,7 @@ struct EpiStoreF16 {
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       } else if (act == 2) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = elu_plus_one(v[j]);
+        for (int j = 0; j < 32; ++j) v[j] = elu_plus_one_fast(v[j]);
       }
       staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, c.ncols - col);
     });
@@ -286,7 +288,7 @@ struct EpiQ {
       float dot = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = elu_plus_one(v[j]);
+        v[j] = elu_plus_one_fast(v[j]);
         dot = fmaf(v[j], c.smem[col + j], dot);
       }
       const float z = p.v_len / (dot + p.eps);
@@ -437,7 +439,7 @@ struct EpiLse {
     tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col + j < c.ncols) sum += expf(v[j] * p.scale - m);
+        if (col + j < c.ncols) sum += __expf(v[j] * p.scale - m);
     });
     if (c.valid) {
       p.part_m[c.grow * s.n_tiles + c.n_tile] = m;
@@ -476,7 +478,7 @@ struct EpiConf {
         const float x2 = 2.f * (v[j] * p.scale);
         const float lo = c.smem[(col + j) & 255];
         const float e = p.own_is_pt ? (x2 - lown) - lo : (x2 - lo) - lown;
-        v[j] = expf(e);
+        v[j] = __expf(e);
         if (col + j < c.ncols && v[j] > best) {
           best = v[j];
           best_idx = c.n0 + col + j;
@@ -515,7 +517,9 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int planes = s.split ? 2 : 1;
-  const int b_bytes = s.block_n * kBlockK * 2;   // one plane of the W tile
+  const bool pair = s.pair != 0;
+  const int b_rows = pair ? s.block_n / 2 : s.block_n;   // W rows resident in THIS CTA
+  const int b_bytes = b_rows * kBlockK * 2;              // one plane of the (local) W tile
   const int a_stage = kABytes * planes;
   const int b_stage = b_bytes * planes;
   uint8_t* smem_a = smem;
@@ -538,6 +542,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   const int csize = s.cluster;
   const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const bool leader = crank == 0;
   const int cluster_id = blockIdx.x / csize;
   const int n_clusters = gridDim.x / csize;
   const int tiles_per_batch = s.msup * s.n_tiles;
@@ -550,17 +555,23 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   if (warp == 2 && lane == 0) {
     for (int i = 0; i < s.stages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], csize);   // one tcgen05.commit arrival from every CTA of the cluster
+      // multicast clusters: one tcgen05.commit arrival from every CTA; pair: the leader's commit
+      mbar_init(&empty[i], pair ? 1 : csize);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], pair ? 256 : 128);   // pair: epilogue threads of both CTAs -> leader
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, tmem_cols);
-    tmem_relinquish();
+    if (pair) {
+      tmem_alloc2(tmem_slot, tmem_cols);
+      tmem_relinquish2();
+    } else {
+      tmem_alloc(tmem_slot, tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -576,7 +587,8 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     int stage = 0;
     uint32_t phase = 0;
     const bool skip_b = (s.debug_skip & 1) != 0, skip_a = (s.debug_skip & 2) != 0;
-    const uint32_t tx_bytes = (skip_a ? 0 : a_stage) + (skip_b ? 0 : b_stage);
+    // pair: both CTAs' loads are credited to the leader's barrier, which expects twice the bytes
+    const uint32_t tx_bytes = ((skip_a ? 0 : a_stage) + (skip_b ? 0 : b_stage)) * (pair ? 2 : 1);
     for (int t = cluster_id; t < total_tiles; t += n_clusters) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
@@ -605,10 +617,16 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
           const int lo = first ? s.a0_lo : s.a1_lo;
           kb = chunk * kBlockK;
           if (elect_one()) {
-            mbar_expect_tx(&full[stage], tx_bytes);
+            if (!pair || leader) mbar_expect_tx(&full[stage], tx_bytes);
             if (!skip_a) {
-              tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
-              if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
+              if (pair) {
+                tma_load_3d_2sm(am, &full[stage], sa, kc, m_tile * kBlockM, b);
+                if (s.split)
+                  tma_load_3d_2sm(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
+              } else {
+                tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
+                if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
+              }
             }
           }
         } else {
@@ -621,12 +639,19 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
           }
           kb = kb_tap + cc * kBlockK;
           if (elect_one()) {
-            mbar_expect_tx(&full[stage], tx_bytes);
+            if (!pair || leader) mbar_expect_tx(&full[stage], tx_bytes);
             if (!skip_a) {
-              tma_load_4d(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
-              if (s.split)
-                tma_load_4d(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
-                            ox0 + dx, oy0 + dy, b);
+              if (pair) {
+                tma_load_4d_2sm(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
+                if (s.split)
+                  tma_load_4d_2sm(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
+                                  ox0 + dx, oy0 + dy, b);
+              } else {
+                tma_load_4d(&maps.a[mi], &full[stage], sa, cc * kBlockK, ox0 + dx, oy0 + dy, b);
+                if (s.split)
+                  tma_load_4d(&maps.a[mi], &full[stage], sa + kABytes, s.conv_c + cc * kBlockK,
+                              ox0 + dx, oy0 + dy, b);
+              }
             }
           }
           if (++cc == s.conv_cchunks) {
@@ -639,7 +664,12 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
           }
         }
         if (!skip_b && elect_one()) {
-          if (csize == 1) {
+          if (pair) {
+            // this CTA keeps W rows [crank*N/2, +N/2) of the tile; the MMA reads both halves
+            const int nrow = nrow0 + crank * b_rows;
+            tma_load_3d_2sm(&maps.b, &full[stage], sb, kb, nrow, bb);
+            if (s.split) tma_load_3d_2sm(&maps.b, &full[stage], sb + b_bytes, s.b_lo + kb, nrow, bb);
+          } else if (csize == 1) {
             tma_load_3d(&maps.b, &full[stage], sb, kb, nrow0, bb);
             if (s.split) tma_load_3d(&maps.b, &full[stage], sb + b_bytes, s.b_lo + kb, nrow0, bb);
           } else {
@@ -662,56 +692,86 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_f16(kBlockM, s.block_n);
-    const uint32_t sa0 = smem_u32(smem_a), sb0 = smem_u32(smem_b);
+    // The tensor-core instruction queue is shallow: whatever this warp executes between the last
+    // MMA of one chunk and the first MMA of the next is tensor-pipe idle time, so the loop keeps
+    // running smem addresses, a fixed descriptor template and a branch-free full-chunk path.
+    const uint32_t idesc = make_idesc_f16(pair ? 2 * kBlockM : kBlockM, s.block_n);
+    const uint64_t desc_tmpl = make_kmajor_sw128_desc(0);
+    const uint32_t sa0 = (smem_u32(smem_a) >> 4) & 0x3FFF, sb0 = (smem_u32(smem_b) >> 4) & 0x3FFF;  // 16 B units
+    const uint32_t a_step = (uint32_t)a_stage >> 4, b_step = (uint32_t)b_stage >> 4;
+    const uint32_t a_lo_off = kABytes >> 4, b_lo_off = (uint32_t)b_bytes >> 4;
+    const bool split = s.split != 0;
     int stage = 0;
     uint32_t phase = 0;
+    uint32_t sa = sa0, sb = sb0;
     int it = 0;
-    for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
+    for (int t = cluster_id; t < total_tiles && (!pair || leader); t += n_clusters, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      mbar_wait_hot(&tempty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * acc_stride;
       int cc = 0;
       for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
         int ksteps = 4;
         if (A_MODE == A_CONV) {
           const int rem = (s.conv_c - cc * kBlockK) >> 4;
           ksteps = rem < 4 ? rem : 4;
           if (++cc == s.conv_cchunks) cc = 0;
         }
-        const uint32_t sa = sa0 + stage * a_stage;
-        const uint32_t sb = sb0 + stage * b_stage;
-        const uint64_t a_hi = make_kmajor_sw128_desc(sa);
-        const uint64_t b_hi = make_kmajor_sw128_desc(sb);
-        const uint64_t a_lo = make_kmajor_sw128_desc(sa + kABytes);
-        const uint64_t b_lo = make_kmajor_sw128_desc(sb + b_bytes);
-        if (elect_one()) {
-          // advance 16 fp16 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4)
+        const uint64_t a_hi = desc_tmpl | sa, b_hi = desc_tmpl | sb;
+        const uint64_t a_lo = desc_tmpl | (sa + a_lo_off), b_lo = desc_tmpl | (sb + b_lo_off);
+        mbar_wait_hot(&full[stage], phase);
+        tc_fence_after();
+        if (pair) {
+          if (elect_one()) {
+            tc_mma2_f16(d_tmem, a_hi, b_hi, idesc, chunk != 0);
+            for (int k = 1; k < ksteps; ++k) tc_mma2_f16_acc(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc);
+            if (split) {
+              for (int k = 0; k < ksteps; ++k) tc_mma2_f16_acc(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc);
+              for (int k = 0; k < ksteps; ++k) tc_mma2_f16_acc(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc);
+            }
+            tc_commit2_mc(&empty[stage], 3);   // frees the stage in both CTAs
+          }
+        } else if (elect_one()) {
+          // K advance: 16 fp16 = 32 B inside the 128 B swizzle row = +2 in 16-byte units
           tc_mma_f16(d_tmem, a_hi, b_hi, idesc, chunk != 0);
-#pragma unroll
-          for (int k = 1; k < 4; ++k)
-            if (k < ksteps) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc);
-          if (s.split) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ksteps) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (k < ksteps) tc_mma_f16_acc(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc);
+          if (ksteps == 4) {
+            tc_mma_f16_acc(d_tmem, a_hi + 2, b_hi + 2, idesc);
+            tc_mma_f16_acc(d_tmem, a_hi + 4, b_hi + 4, idesc);
+            tc_mma_f16_acc(d_tmem, a_hi + 6, b_hi + 6, idesc);
+            if (split) {
+              tc_mma_f16_acc(d_tmem, a_hi, b_lo, idesc);
+              tc_mma_f16_acc(d_tmem, a_hi + 2, b_lo + 2, idesc);
+              tc_mma_f16_acc(d_tmem, a_hi + 4, b_lo + 4, idesc);
+              tc_mma_f16_acc(d_tmem, a_hi + 6, b_lo + 6, idesc);
+              tc_mma_f16_acc(d_tmem, a_lo, b_hi, idesc);
+              tc_mma_f16_acc(d_tmem, a_lo + 2, b_hi + 2, idesc);
+              tc_mma_f16_acc(d_tmem, a_lo + 4, b_hi + 4, idesc);
+              tc_mma_f16_acc(d_tmem, a_lo + 6, b_hi + 6, idesc);
+            }
+          } else {
+            for (int k = 1; k < ksteps; ++k) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_hi + 2 * k, idesc);
+            if (split) {
+              for (int k = 0; k < ksteps; ++k) tc_mma_f16_acc(d_tmem, a_hi + 2 * k, b_lo + 2 * k, idesc);
+              for (int k = 0; k < ksteps; ++k) tc_mma_f16_acc(d_tmem, a_lo + 2 * k, b_hi + 2 * k, idesc);
+            }
           }
           if (csize > 1) tc_commit_mc(&empty[stage], cmask); else tc_commit(&empty[stage]);
         }
         __syncwarp();
+        sa += a_step;
+        sb += b_step;
         if (++stage == s.stages) {
           stage = 0;
           phase ^= 1;
+          sa = sa0;
+          sb = sb0;
         }
       }
-      if (elect_one()) tc_commit(&tfull[acc]);
+      if (elect_one()) {
+        if (pair) tc_commit2_mc(&tfull[acc], 3); else tc_commit(&tfull[acc]);
+      }
       __syncwarp();
     }
   } else {
@@ -742,7 +802,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
       tc_fence_after();
       Epi::run(ep, s, c);
       tc_fence_before();
-      mbar_arrive(&tempty[acc]);
+      if (pair) mbar_arrive_cluster(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
     }
   }
 
@@ -751,20 +811,20 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   if (csize > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (pair) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 // dynamic shared memory a launch needs (ring + epilogue scratch + barriers + alignment slack)
-inline int gemm_stage_bytes(int block_n, int split) {
-  return (kABytes + block_n * kBlockK * 2) * (split ? 2 : 1);
+inline int gemm_stage_bytes(int block_n, int split, int pair) {
+  return (kABytes + (pair ? block_n / 2 : block_n) * kBlockK * 2) * (split ? 2 : 1);
 }
-inline int gemm_smem_bytes(int stages, int block_n, int split) {
-  return stages * gemm_stage_bytes(block_n, split) + kEpiSmemBytes + (2 * kMaxStages + 4) * 8 + 16 +
-         1024;
+inline int gemm_smem_bytes(int stages, int block_n, int split, int pair) {
+  return stages * gemm_stage_bytes(block_n, split, pair) + kEpiSmemBytes + (2 * kMaxStages + 4) * 8 +
+         16 + 1024;
 }
-inline int gemm_pick_stages(int block_n, int k_chunks, int split) {
-  int st = (227 * 1024 - kEpiSmemBytes - 2048) / gemm_stage_bytes(block_n, split);
+inline int gemm_pick_stages(int block_n, int k_chunks, int split, int pair) {
+  int st = (227 * 1024 - kEpiSmemBytes - 2048) / gemm_stage_bytes(block_n, split, pair);
   if (st > kMaxStages) st = kMaxStages;
   if (st > k_chunks * 2 && k_chunks * 2 >= 2) st = k_chunks * 2;
   return st < 2 ? 2 : st;

@@ -282,48 +282,65 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
 // Linear-attention source state   (loftr_module/linear_attention.py:55-57)
 // part[b][chunk][h][d][v] = sum_{s in chunk} K'[s,h,d] V[s,h,v];  row d = 32 holds sum_s K'[s,h,:]
 // =============================================================================================
-constexpr int kKvChunk = 128;
+constexpr int kKvChunk = 128;   // tokens per CTA
+constexpr int kKvSub = 16;      // tokens staged in shared memory at a time
 
+// One CTA = one chunk of tokens and ALL heads (warp h <-> head h), so every token row is read
+// exactly once, fully coalesced (both planes), and converted to fp32 in shared memory.
+// Lane d of warp h owns row d of the 32x32 head state: acc[v] += K'[t,h,d] * V[t,h,v].
 __global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restrict__ kv16,
                                                          float* __restrict__ part, int S, int d,
                                                          int lo_off) {
-  __shared__ float k_s[kKvChunk][32];
-  __shared__ float v_s[kKvChunk][32];
-  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int chunks = gridDim.x, H = gridDim.y;
+  __shared__ float xs[kKvSub][512];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int chunks = gridDim.x;
+  const int H = d >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s0 = chunk * kKvChunk;
   const int cnt = min(kKvChunk, S - s0);
   const int ld = lo_off ? 4 * d : 2 * d;
+  const int groups = (2 * d) >> 3;   // 8-value groups per token row (64 for d = 256)
   const __half* src = kv16 + ((long long)b * S + s0) * ld;
-  // tokens x (32 K' + 32 V); 4 threads per token row move 8 values each per operand
-  for (int i = threadIdx.x; i < kKvChunk * 4; i += 256) {
-    const int t = i >> 2, part4 = i & 3;
-    float kq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, vq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (t < cnt) {
-      load_split8(src + (long long)t * ld, h * 32 + part4 * 8, kq, lo_off);
-      load_split8(src + (long long)t * ld, d + h * 32 + part4 * 8, vq, lo_off);
-    }
+  float acc[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      k_s[t][part4 * 8 + j] = kq[j];
-      v_s[t][part4 * 8 + j] = vq[j];
+  for (int v = 0; v < 32; ++v) acc[v] = 0.f;
+  float ks = 0.f;
+  for (int t0 = 0; t0 < cnt; t0 += kKvSub) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kKvSub * groups; i += 256) {
+      const int t = i / groups, g = i - t * groups;
+      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (t0 + t < cnt) load_split8(src + (long long)(t0 + t) * ld, g * 8, x, lo_off);
+      float4* dst = reinterpret_cast<float4*>(&xs[t][g * 8]);
+      dst[0] = make_float4(x[0], x[1], x[2], x[3]);
+      dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+    }
+    __syncthreads();
+    if (warp < H) {
+#pragma unroll 4
+      for (int t = 0; t < kKvSub; ++t) {
+        const float k = xs[t][warp * 32 + lane];
+        const float4* vrow = reinterpret_cast<const float4*>(&xs[t][d + warp * 32]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 vv = vrow[q];
+          acc[4 * q + 0] = fmaf(k, vv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(k, vv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(k, vv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(k, vv.w, acc[4 * q + 3]);
+        }
+        ks += k;
+      }
     }
   }
-  __syncthreads();
-  const int dd = threadIdx.x >> 3, v0 = (threadIdx.x & 7) * 4;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, ks = 0.f;
-  for (int t = 0; t < kKvChunk; ++t) {
-    const float k = k_s[t][dd];
-    const float4 va = *reinterpret_cast<const float4*>(&v_s[t][v0]);
-    acc[0] = fmaf(k, va.x, acc[0]);
-    acc[1] = fmaf(k, va.y, acc[1]);
-    acc[2] = fmaf(k, va.z, acc[2]);
-    acc[3] = fmaf(k, va.w, acc[3]);
-    ks += k;
+  if (warp < H) {
+    float* dst = part + ((((long long)b * chunks + chunk) * H + warp) * 33) * 32;
+    float4* row = reinterpret_cast<float4*>(dst + lane * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      row[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    dst[32 * 32 + lane] = ks;
   }
-  float* dst = part + ((((long long)b * chunks + chunk) * H + h) * 33) * 32;
-  *reinterpret_cast<float4*>(dst + dd * 32 + v0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-  if ((threadIdx.x & 7) == 0) dst[32 * 32 + dd] = ks;
 }
 
 // mt[b][c][h*32+dd] = sum_v merge_w[c][h*32+v] * KV[b][h][dd][v] / v_len ; ksum[b][h*32+dd]
@@ -344,19 +361,28 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
   if (threadIdx.x < 32) ksum[(long long)b * d + h * 32 + threadIdx.x] = kv_s[32][threadIdx.x];
   for (int c = threadIdx.x; c < d; c += 256) {
     float w[32];
+    const float4* wp = reinterpret_cast<const float4*>(merge_w + (long long)c * d + h * 32);
 #pragma unroll
-    for (int v = 0; v < 32; ++v) w[v] = merge_w[(long long)c * d + h * 32 + v];
-    float o[32];
-#pragma unroll
-    for (int dd = 0; dd < 32; ++dd) {
-      float s = 0.f;
-#pragma unroll
-      for (int v = 0; v < 32; ++v) s = fmaf(w[v], kv_s[dd][v], s);
-      o[dd] = s * inv_vlen;
+    for (int q = 0; q < 8; ++q) {
+      const float4 t = wp[q];
+      w[4 * q] = t.x;
+      w[4 * q + 1] = t.y;
+      w[4 * q + 2] = t.z;
+      w[4 * q + 3] = t.w;
     }
     __half* dst = mt + ((long long)b * d + c) * (lo_off ? 2 * d : d);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) store_split8(dst, h * 32 + g * 8, o + g * 8, lo_off);
+    for (int g = 0; g < 4; ++g) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int v = 0; v < 32; ++v) sacc = fmaf(w[v], kv_s[g * 8 + j][v], sacc);
+        o[j] = sacc * inv_vlen;
+      }
+      store_split8(dst, h * 32 + g * 8, o, lo_off);
+    }
   }
 }
 
@@ -727,7 +753,8 @@ int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int s
                    opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");
   OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
-  dim3 grid((s + kKvChunk - 1) / kKvChunk, d / 32, batch);
+  OPP_REQUIRE(d == 256, "kv_partial is built for d = 256 (8 heads x 32), got %d", d);
+  dim3 grid((s + kKvChunk - 1) / kKvChunk, batch);
   kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d,
                                                             split ? 2 * d : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
