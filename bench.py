@@ -270,7 +270,8 @@ def main():
 
     # dominant kernel: the tcgen05 implicit-GEMM conv engine (21 launches / forward), timed live
     # with CUDA events around the backbone on the launching stream
-    conv_ms = None
+    conv_ms = attn_ms = None
+    S_tok = (H // 8) * (W // 8)
     if rank == 0:
         img_f = imgs_dev.contiguous().float()
         for _ in range(2):
@@ -283,6 +284,24 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         conv_ms = e0.elapsed_time(e1) / 3
+        # coarse attention (BASELINE.json "coarse-attn tensor-pipe %"): the 6-layer linear-attention
+        # transformer on both sequences = 60 tcgen05 GEMM launches + the KV-state kernels
+        q2, _, (hc, wc) = model._backbone(img_f)
+        S_tok = hc * wc
+        pl = 2 if model.split else 1
+        d3 = torch.randn(B, N_POINTS, 256, device=dev)
+        from onepose_plus_plus_b200 import ops as _ops
+        d3p = _ops.to_planes(d3, model.split)
+        q2c = q2.clone()
+        for _ in range(2):
+            model._coarse_transformer(q2c.clone(), d3p.clone(), B, S_tok, N_POINTS)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(3):
+            model._coarse_transformer(q2c, d3p, B, S_tok, N_POINTS)
+        e1.record()
+        torch.cuda.synchronize()
+        attn_ms = e0.elapsed_time(e1) / 3
         if args.profile_ops:
             _lib.profile_ops(lambda: step_resident(), sys.stderr)
 
@@ -303,6 +322,8 @@ def main():
         flops = conv_flops_table(B)
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
         passes = 3 if model.split else 1
+        attn_flops = 2.0 * ((S_tok + N_POINTS) * 6 * 10 * 256 * 256 + (S_tok + N_POINTS) * 6 * 2 * 256 * 32) * B
+        attn_tf = attn_flops / (attn_ms * 1e-3) / 1e12
         line = {
             "metric": "query images/sec (512x512, 5k 3D pts)",
             "value": total_imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
@@ -329,6 +350,12 @@ def main():
                          "issued_frac": ach * passes / peak_tf if ach else None,
                          "note": "achieved counts ALGORITHMIC conv flops (reference fp32 math, true channel "
                                  "counts); the fp32-grade mode issues mma_passes x that on the tensor pipe"},
+            "coarse_attention": {
+                "kernels": "gemm_kernel<A_ROWS,{EpiStoreF16,EpiQ,EpiLN}> x60 + kv_partial/kv_finalize x12",
+                "ms": attn_ms, "algorithmic_tflops": attn_tf, "issued_tensor_tflops": attn_tf * passes,
+                "frac_of_peak_algorithmic": attn_tf / peak_tf, "frac_of_peak_issued": attn_tf * passes / peak_tf,
+                "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
+                "tensor_pipe_pct_ncu": "see profiles/r1_ncu_summary.md (per-launch sm__pipe_tensor_cycles_active)"},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))
