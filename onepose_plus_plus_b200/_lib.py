@@ -10,7 +10,7 @@ from ctypes import c_float, c_int, c_longlong, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libopp_b200.so")
+LIB_PATH = os.environ.get("OPP_B200_LIB") or os.path.join(_HERE, "libopp_b200.so")
 
 _lib = None
 

@@ -377,29 +377,36 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                  "+r"(r[30]), "+r"(r[31])::"memory");
 }
 // Walk the accumulator row of this thread in 32-column chunks with one chunk of lookahead:
-// f(col, v[32]) is called for col = 0, 32, ... < ncols (ncols warp-uniform).
+// f(col, v[32]) is called for col = first, first+step, ... < ncols (all warp-uniform).  Two
+// epilogue warp groups share a tile by taking alternate chunks (first = 32*group, step = 64).
 template <class F>
-__device__ __forceinline__ void tmem_foreach32(uint32_t tbase, int ncols, F&& f) {
+__device__ __forceinline__ void tmem_foreach32(uint32_t tbase, int ncols, int first, int step,
+                                               F&& f) {
+  if (first >= ncols) return;
   uint32_t ra[32], rb[32];
   float v[32];
-  tmem_ld32_issue(tbase, ra);
+  tmem_ld32_issue(tbase + first, ra);
   tmem_ld_wait(ra);
-  for (int col = 0; col < ncols; col += 64) {
-    const bool has_b = col + 32 < ncols;
-    if (has_b) tmem_ld32_issue(tbase + col + 32, rb);
+  for (int col = first; col < ncols; col += 2 * step) {
+    const bool has_b = col + step < ncols;
+    if (has_b) tmem_ld32_issue(tbase + col + step, rb);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
     f(col, v);
     if (has_b) {
       tmem_ld_wait(rb);
-      const bool has_a = col + 64 < ncols;
-      if (has_a) tmem_ld32_issue(tbase + col + 64, ra);
+      const bool has_a = col + 2 * step < ncols;
+      if (has_a) tmem_ld32_issue(tbase + col + 2 * step, ra);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rb[i]);
-      f(col + 32, v);
+      f(col + step, v);
       if (has_a) tmem_ld_wait(ra);
     }
   }
+}
+template <class F>
+__device__ __forceinline__ void tmem_foreach32(uint32_t tbase, int ncols, F&& f) {
+  tmem_foreach32(tbase, ncols, 0, 32, f);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];

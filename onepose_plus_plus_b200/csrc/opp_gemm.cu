@@ -130,7 +130,7 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
   const int n_clusters = (int)(total < max_clusters ? total : max_clusters);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(n_clusters * s.cluster);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads(Epi::kGroups));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -388,6 +388,9 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
   return launch<A_ROWS, EpiConf>(maps, s, ep, (cudaStream_t)stream);
 }
 
-int opp_sim_tiles(int cols) { return (cols + pick_block_n(cols) - 1) / pick_block_n(cols); }
+// partial slots per row written by opp_sim_lse / opp_sim_conf: one per column tile and epilogue warp group
+int opp_sim_tiles(int cols) {
+  return EpiLse::kGroups * ((cols + pick_block_n(cols) - 1) / pick_block_n(cols));
+}
 
 }  // extern "C"

@@ -20,8 +20,9 @@
 // Everything after the accumulator (bias / BN / activation / residual / LayerNorm / elu+1 /
 // linear-attention normaliser / dual-softmax statistics) is a fused epilogue functor.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (lane 0), warp 1 = TMEM owner + MMA issuer
-// (lane 0), warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4) .. +31, one row per thread).
+// Warp roles (64 + 128*groups threads): warps 0..4g-1 = epilogue (warp w owns TMEM lanes
+// 32*(w%4) .. +31, one row per thread; two groups take alternate 32-column chunks), then the TMA
+// producer warp and, with the highest id, the TMEM owner + MMA issuer warp.
 //
 // Reference semantics implemented by the epilogues are cited at each functor
 // (paths relative to the reference repo zju3dv/OnePose_Plus_Plus).
@@ -29,15 +30,27 @@
 
 #include "opp_common.cuh"
 
+#ifndef OPP_CONV_GROUPS
+#define OPP_CONV_GROUPS 1
+#endif
+#ifndef OPP_LN_GROUPS
+#define OPP_LN_GROUPS 1
+#endif
+#ifndef OPP_ROW_GROUPS
+#define OPP_ROW_GROUPS 2   // EpiStoreF16 / EpiQ / EpiLse / EpiConf
+#endif
+
 namespace opp {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;               // 64 fp16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kMaxStages = 8;
-constexpr int kEpiParamBytes = 4096;            // bias / gamma,beta / lse vectors
-constexpr int kEpiSmemBytes = kEpiParamBytes + 4 * 4608;   // + one transpose buffer per epilogue warp
-constexpr int kGemmThreads = 192;
+constexpr int kEpiParamBytes = 4096;   // bias / gamma,beta / lse vectors: 2 KB per epilogue group
+constexpr int kMaxEpiWarps = 8;
+constexpr int kEpiSmemBytes = kEpiParamBytes + kMaxEpiWarps * 2560;   // + transpose buffer per warp
+// 64 threads (producer + MMA warps) + 128 per epilogue warp group (Epi::kGroups = 1 or 2)
+constexpr int gemm_threads(int groups) { return 64 + 128 * groups; }
 
 enum AMode : int { A_ROWS = 0, A_CONV = 1 };
 
@@ -89,11 +102,17 @@ struct EpiCtx {
   int n0;          // first global column of the tile
   int ncols;       // valid columns in this tile (multiple of 8)
   int etid;        // 0..127 within the epilogue group
-  float* smem;     // kEpiParamBytes of scratch shared by the epilogue group
+  float* smem;     // 2 KB of scratch shared by this epilogue group
   uint8_t* wstage; // kWarpStageBytes private to this warp (transpose buffer for coalesced I/O)
+  int group;       // epilogue warp group (0/1); groups take alternate 32-column chunks
+  int col_first, col_step;
+  // rows (lane>>2) + 8*i, i = 0..3 of this warp's quarter: element offset grow*ld is NOT stored,
+  // only grow (row index in the output) and validity, computed once per tile
+  long long sgrow[4];
+  unsigned svalid;
 };
 
-__device__ __forceinline__ void epi_sync() { named_bar_sync(1, 128); }
+__device__ __forceinline__ void epi_sync(const EpiCtx& c) { named_bar_sync(1 + c.group, 128); }
 
 // (global row, validity) of row `rr` (0..31) of this warp's quarter of the tile
 __device__ __forceinline__ bool epi_row_info(const GemmShape& s, const EpiCtx& c, int rr,
@@ -122,8 +141,7 @@ __device__ __forceinline__ bool epi_row_info(const GemmShape& s, const EpiCtx& c
 // transpose buffer (row stride padded by 16 B so both access directions are conflict-light).
 // ---------------------------------------------------------------------------------------------
 constexpr int kStageRowH = 80;    // 32 fp16 (64 B) + 16 B pad
-constexpr int kStageRowF = 144;   // 32 fp32 (128 B) + 16 B pad
-constexpr int kWarpStageBytes = 32 * kStageRowF;   // 4608 B >= 32*80
+constexpr int kWarpStageBytes = 32 * kStageRowH;   // 2560 B
 
 // fp16 planes: v = this lane's 32 values for global columns [gcol, gcol+32); nvalid = valid
 // columns of the chunk (multiple of 8).  Writes hi (and lo when lo_off != 0).
@@ -162,78 +180,12 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int rr = (lane >> 2) + 8 * i;
-      long long grow;
-      int row;
-      const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 8 < nvalid;
-      if (ok)
-        *reinterpret_cast<uint4*>(out + grow * ld + plane * lo_off + gcol + seg * 8) =
+      if (((c.svalid >> i) & 1u) && seg * 8 < nvalid)
+        *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + plane * lo_off + gcol + seg * 8) =
             *reinterpret_cast<const uint4*>(st + rr * kStageRowH + seg * 16);
     }
     __syncwarp();
   }
-}
-
-// r[32] += (hi + lo) of this lane's row, global columns [gcol, gcol+32), read coalesced
-__device__ __forceinline__ void staged_load_add_h32(const GemmShape& s, const EpiCtx& c,
-                                                    const __half* src, long long ld, int lo_off,
-                                                    int gcol, float* r, int nvalid) {
-  const int lane = threadIdx.x & 31;
-  uint8_t* st = c.wstage;
-#pragma unroll
-  for (int plane = 0; plane < 2; ++plane) {
-    if (plane == 1 && lo_off == 0) break;
-    const int seg = lane & 3;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = (lane >> 2) + 8 * i;
-      long long grow;
-      int row;
-      const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 8 < nvalid;
-      uint4 u = make_uint4(0, 0, 0, 0);
-      if (ok)
-        u = *reinterpret_cast<const uint4*>(src + grow * ld + plane * lo_off + gcol + seg * 8);
-      *reinterpret_cast<uint4*>(st + rr * kStageRowH + seg * 16) = u;
-    }
-    __syncwarp();
-    const uint4* mine = reinterpret_cast<const uint4*>(st + lane * kStageRowH);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint4 u = mine[g];
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        r[8 * g + 2 * j] += f.x;
-        r[8 * g + 2 * j + 1] += f.y;
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// fp32 rows: out[grow*ld + gcol + j] = v[j]; requires 16-byte aligned row segments
-__device__ __forceinline__ void staged_store_f32(const GemmShape& s, const EpiCtx& c, float* out,
-                                                 long long ld, int gcol, const float* v,
-                                                 int nvalid) {
-  const int lane = threadIdx.x & 31;
-  uint8_t* st = c.wstage;
-  float4* mine = reinterpret_cast<float4*>(st + lane * kStageRowF);
-#pragma unroll
-  for (int g = 0; g < 8; ++g)
-    mine[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-  __syncwarp();
-  const int seg = lane & 7;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int rr = (lane >> 3) + 4 * i;
-    long long grow;
-    int row;
-    const bool ok = epi_row_info(s, c, rr, grow, row) && seg * 4 < nvalid;
-    if (ok)
-      *reinterpret_cast<float4*>(out + grow * ld + gcol + seg * 4) =
-          *reinterpret_cast<const float4*>(st + rr * kStageRowF + seg * 16);
-  }
-  __syncwarp();
 }
 
 // =============================================================================================
@@ -244,6 +196,7 @@ __device__ __forceinline__ void staged_store_f32(const GemmShape& s, const EpiCt
 // Plain store with an optional activation on the leading `act_cols` columns.
 //   act 1 = ReLU  (transformer.py:41-45 mlp ReLU), act 2 = elu(x)+1 (linear_attention.py:10-11)
 struct EpiStoreF16 {
+  static constexpr int kGroups = OPP_ROW_GROUPS;
   struct Params {
     __half* out;
     long long ld;   // row stride in elements
@@ -251,8 +204,9 @@ struct EpiStoreF16 {
     int act;
     int act_cols;   // multiple of 32
   };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int act = g0 < p.act_cols ? p.act : 0;
       if (act == 1) {
@@ -272,6 +226,7 @@ struct EpiStoreF16 {
 // state is pre-divided by v_length (linear_attention.py:55-56), so (Q*Z*v_length) @ (KV/v_length)
 // reproduces the reference product.
 struct EpiQ {
+  static constexpr int kGroups = OPP_ROW_GROUPS;
   struct Params {
     __half* out;
     long long ld;
@@ -280,12 +235,13 @@ struct EpiQ {
     float v_len;
     float eps;
   };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    epi_sync();
+    epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128)
       c.smem[i] = p.ksum[(long long)c.b * s.n_total + c.n0 + i];
-    epi_sync();
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    epi_sync(c);
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       float dot = 0.f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -303,6 +259,7 @@ struct EpiQ {
 // LayerNorm over the full output row (the tile spans all N columns), optional residual add
 // (transformer.py:86-94: norm1 after merge; norm2 then x + msg).
 struct EpiLN {
+  static constexpr int kGroups = OPP_LN_GROUPS;
   struct Params {
     const float* gamma;
     const float* beta;
@@ -313,23 +270,33 @@ struct EpiLN {
     int out_lo;
     float* out32;         // fp32 [rows][n_total] or null
   };
-  // Row-per-thread loads/stores measured faster here than the warp-staged path (the three TMEM
-  // passes already saturate the instruction budget of the four epilogue warps).
+  __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    if (!p.resid || !c.valid) return;
+    const char* row = reinterpret_cast<const char*>(p.resid + c.grow * p.ld);
+    for (int o = c.group * 128; o < c.ncols * 2; o += 256) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+      if (p.out_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * p.out_lo + o));
+    }
+  }
+  // Two warp groups share every row (alternate 32-column chunks).  Each thread accumulates shifted
+  // sums over its half, the halves are merged with Chan's parallel-variance formula (group 0
+  // first, so both threads of a row compute bit-identical statistics), then each group
+  // normalises and writes its own chunks.  Row-per-thread loads/stores measured faster here than
+  // the warp-staged path.
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     float* g_s = c.smem;
     float* b_s = c.smem + 256;
-    epi_sync();
+    epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128) {
       g_s[i] = p.gamma[i];
       b_s[i] = p.beta[i];
     }
-    epi_sync();
-    // one statistics pass: shifted sums (x0 = first element of the row) keep the single-pass
-    // variance free of cancellation; a second pass normalises and writes.
-    const float inv_n = 1.f / (float)c.ncols;
+    epi_sync(c);
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
-      if (col == 0) x0 = v[0];
+    int cnt = 0;
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+      if (cnt == 0) x0 = v[0];
+      cnt += 32;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float d = v[j] - x0;
@@ -337,16 +304,40 @@ struct EpiLN {
         s2 = fmaf(d, d, s2);
       }
     });
-    const float dm = s1 * inv_n;
-    const float mean = x0 + dm;
-    const float sq = fmaxf(s2 - s1 * dm, 0.f);   // = sum (x - mean)^2
-    const float rstd = 1.f / sqrtf(sq * inv_n + p.eps);
-    for (int col = 0; col < c.ncols; col += 32) {
-      float v[32];
-      tmem_ld32(c.tmem + col, v);
+    // exchange (x0, s1, s2, cnt) with the thread of the other group that owns the same row
+    float4 ga = make_float4(x0, s1, s2, (float)cnt), gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kGroups == 2) {
+      const int lane = threadIdx.x & 31;
+      float4* mine = reinterpret_cast<float4*>(c.wstage) + lane;
+      const float4* other = reinterpret_cast<const float4*>(
+                                c.wstage + (c.group ? -4 : 4) * kWarpStageBytes) + lane;
+      *mine = ga;
+      named_bar_sync(3, 256);
+      const float4 o = *other;
+      if (c.group == 0) {
+        gb = o;
+      } else {
+        gb = ga;
+        ga = o;
+      }
+    }
+    float mean, m2;
+    {
+      const float na = ga.w, nb = gb.w;
+      const float mean_a = na > 0.f ? ga.x + ga.y / na : 0.f;
+      const float m2a = na > 0.f ? fmaxf(ga.z - ga.y * ga.y / na, 0.f) : 0.f;
+      const float mean_b = nb > 0.f ? gb.x + gb.y / nb : mean_a;
+      const float m2b = nb > 0.f ? fmaxf(gb.z - gb.y * gb.y / nb, 0.f) : 0.f;
+      const float n = na + nb;
+      const float delta = mean_b - mean_a;
+      mean = mean_a + delta * (nb / n);
+      m2 = m2a + m2b + delta * delta * (na * nb / n);
+    }
+    const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g_s[col + j] + b_s[col + j];
-      if (!c.valid) continue;
+      if (!c.valid) return;
       if (p.resid) {
         const __half* rrow = p.resid + c.grow * p.ld;
 #pragma unroll
@@ -368,7 +359,8 @@ struct EpiLN {
 #pragma unroll
         for (int g = 0; g < 4; ++g) store_split8(row, col + g * 8, v + g * 8, p.out_lo);
       }
-    }
+    });
+    if (kGroups == 2) named_bar_sync(3, 256);   // the exchange slots are reused by the next tile
   }
 };
 
@@ -376,6 +368,7 @@ struct EpiLN {
 // 141-147).  Optionally also emits the coarse tokens  x3_out + pe  in token-major order
 // (position_encoding.py:37-42 + OnePosePlusModel.py:137-142: NHWC *is* 'n (h w) c').
 struct EpiConv {
+  static constexpr int kGroups = OPP_CONV_GROUPS;
   struct Params {
     __half* out;          // NHWC, pixel stride ld (or null)
     long long ld;
@@ -387,16 +380,53 @@ struct EpiConv {
     __half* tok;          // [B*H*W] rows with the same (ld, out_lo) layout, or null
     const float* pe;      // [H*W][n_total]
   };
+  // Called before the accumulator wait: pull this row of the residual towards L2 while the MMAs
+  // of the tile are still running (the conv2 of a BasicBlock was epilogue-bound on this read).
+  __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    if (!p.resid || !c.valid) return;
+    const char* row = reinterpret_cast<const char*>(p.resid + c.grow * p.ld + c.n0);
+    const int bytes = c.ncols * 2;
+    for (int o = 0; o < bytes; o += 128) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
+      if (p.out_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * p.out_lo + o));
+    }
+  }
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    epi_sync();
+    epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128) c.smem[i] = p.bias[c.n0 + i];
-    epi_sync();
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    epi_sync(c);
+    // residual: row-per-thread 16 B loads, issued one 32-column chunk ahead of their use
+    const bool has_res = p.resid != nullptr && c.valid;
+    uint4 rq[8];
+    auto issue = [&](int col) {
+      const __half* rrow = p.resid + c.grow * p.ld + c.n0 + col;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const bool in = col + g * 8 < c.ncols;
+        rq[g] = in ? *reinterpret_cast<const uint4*>(rrow + g * 8) : make_uint4(0, 0, 0, 0);
+        rq[4 + g] = (in && p.out_lo) ? *reinterpret_cast<const uint4*>(rrow + p.out_lo + g * 8)
+                                     : make_uint4(0, 0, 0, 0);
+      }
+    };
+    if (has_res && c.col_first < c.ncols) issue(c.col_first);
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] += c.smem[(col + j) & 255];
-      if (p.resid) staged_load_add_h32(s, c, p.resid, p.ld, p.out_lo, g0, v, nvalid);
+      if (has_res) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const __half2* h = reinterpret_cast<const __half2*>(&rq[g]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            v[(g & 3) * 8 + 2 * j] += f.x;
+            v[(g & 3) * 8 + 2 * j + 1] += f.y;
+          }
+        }
+        if (col + c.col_step < c.ncols) issue(col + c.col_step);
+      }
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -421,27 +451,30 @@ struct EpiConv {
 // Dual-softmax statistics (coarse_matching.py:102-115): per row, over this tile's columns,
 // (max, sum exp) of sim = acc*scale.  Partials [grow][n_tile] are merged by a finalize kernel.
 struct EpiLse {
+  static constexpr int kGroups = OPP_ROW_GROUPS;   // partial slot = kGroups*n_tile + group
   struct Params {
     float* part_m;
     float* part_s;
     float scale;
   };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     float m = -INFINITY;
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col + j < c.ncols) m = fmaxf(m, v[j] * p.scale);
     });
     float sum = 0.f;
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col + j < c.ncols) sum += __expf(v[j] * p.scale - m);
     });
     if (c.valid) {
-      p.part_m[c.grow * s.n_tiles + c.n_tile] = m;
-      p.part_s[c.grow * s.n_tiles + c.n_tile] = sum;
+      // a group that saw no column of a ragged last tile leaves (m = -inf, s = 0): neutral in the merge
+      p.part_m[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = m;
+      p.part_s[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = sum;
     }
   }
 };
@@ -452,6 +485,7 @@ struct EpiLse {
 // (coarse_matching.py:157-165).  `own_is_pt` says whether rows are 3D points (pass A) or
 // query cells (pass B); the expression is evaluated in the same order in both passes.
 struct EpiConf {
+  static constexpr int kGroups = OPP_ROW_GROUPS;   // partial slot = kGroups*n_tile + group
   struct Params {
     const float* lse_own;    // [batches*rows]
     const float* lse_other;  // [batches][n_total]
@@ -461,16 +495,17 @@ struct EpiConf {
     float* part_val;         // [batches*rows][n_tiles]
     int* part_idx;
   };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    epi_sync();
+    epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128)
       c.smem[i] = p.lse_other[(long long)c.b * s.n_total + c.n0 + i];
-    epi_sync();
+    epi_sync(c);
     const float lown = c.valid ? p.lse_own[c.grow] : 0.f;
     float best = -1.f;
     int best_idx = c.n0;
     const bool vec_ok = (s.n_total & 3) == 0;
-    tmem_foreach32(c.tmem, c.ncols, [&](int col, float* v) {
+    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x2 = 2.f * (v[j] * p.scale);
@@ -498,8 +533,8 @@ struct EpiConf {
       }
     });
     if (c.valid) {
-      p.part_val[c.grow * s.n_tiles + c.n_tile] = best;
-      p.part_idx[c.grow * s.n_tiles + c.n_tile] = best_idx;
+      p.part_val[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = best;
+      p.part_idx[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = best_idx;
     }
   }
 };
@@ -508,7 +543,7 @@ struct EpiConf {
 // The kernel
 // =============================================================================================
 template <int A_MODE, class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
 gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
             const typename Epi::Params ep) {
   extern __shared__ uint8_t smem_raw[];
@@ -531,6 +566,14 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+  // Warp roles. The SM's warp arbiter favours the highest warp id on each sub-partition, so the
+  // two latency-critical single-issuer roles get the highest ids and the epilogue warps (long
+  // unrolled ALU streams) the lowest; with the MMA issuer as warp 1 it was starved by epilogue
+  // warps of the same sub-partition and the epilogue cost added to the wall time instead of
+  // overlapping with the next tile's MMAs.
+  constexpr int kEpiWarps = 4 * Epi::kGroups;   // warp w: TMEM lane quarter w % 4, group w / 4
+  constexpr int kProducerWarp = kEpiWarps;
+  constexpr int kMmaWarp = kEpiWarps + 1;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int acc_stride = s.block_n <= 128 ? 128 : 256;
@@ -546,11 +589,11 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   const int tiles_per_batch = s.msup * s.n_tiles;
   const int total_tiles = s.batches * tiles_per_batch;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&maps.a[0]);
     tma_prefetch_desc(&maps.b);
   }
-  if (warp == 2 && lane == 0) {
+  if (warp == 0 && lane == 0) {
     for (int i = 0; i < s.stages; ++i) {
       mbar_init(&full[i], 1);
       // multicast clusters: one tcgen05.commit arrival from every CTA; pair: the leader's commit
@@ -558,11 +601,12 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], pair ? 256 : 128);   // pair: epilogue threads of both CTAs -> leader
+      // every epilogue thread arrives; pair: the threads of both CTAs arrive on the leader's barrier
+      mbar_init(&tempty[i], 128 * Epi::kGroups * (pair ? 2 : 1));
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     if (pair) {
       tmem_alloc2(tmem_slot, tmem_cols);
       tmem_relinquish2();
@@ -580,7 +624,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   // addresses, coordinates and descriptors, so they live in uniform registers) and only the
   // asynchronous-issue instructions sit under elect_one().  A single divergent lane doing the
   // whole loop made instruction issue, not the tensor pipe, the limiter (~110 clk per MMA).
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
@@ -688,7 +732,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
     // The tensor-core instruction queue is shallow: whatever this warp executes between the last
     // MMA of one chunk and the first MMA of the next is tensor-pipe idle time, so the loop keeps
@@ -777,11 +821,14 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     EpiCtx c;
-    c.etid = (warp - 2) * 32 + lane;
-    c.smem = epi_smem;
+    c.etid = (warp & 3) * 32 + lane;
     c.q = q;
     c.a_mode = A_MODE;
-    c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + (warp - 2) * kWarpStageBytes;
+    c.group = warp >> 2;
+    c.col_first = 32 * c.group;
+    c.col_step = 32 * Epi::kGroups;
+    c.smem = epi_smem + c.group * (kEpiParamBytes / 8);   // 2 KB (512 floats) per group
+    c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + warp * kWarpStageBytes;
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
       const int acc = it & 1;
@@ -795,10 +842,26 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
       const int rem = s.n_total - c.n0;
       c.ncols = rem < s.block_n ? rem : s.block_n;
       c.valid = epi_row_info(s, c, lane, c.grow, c.row);
+      c.svalid = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int rdummy;
+        if (epi_row_info(s, c, (lane >> 2) + 8 * i, c.sgrow[i], rdummy)) c.svalid |= 1u << i;
+      }
       c.tmem = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * acc_stride;
+      Epi::prefetch(ep, s, c);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      if (!(s.debug_skip & 4)) Epi::run(ep, s, c);   // bit 2: timing experiment, no epilogue at all
+      if (s.debug_skip & 32) {   // bit 5: timing experiment, ONLY the TMEM reads of the epilogue
+        float acc_sink = 0.f;
+        tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc_sink += v[j];
+        });
+        if (acc_sink == 12345.678f) c.smem[0] = acc_sink;
+      } else if (!(s.debug_skip & 4)) {
+        Epi::run(ep, s, c);   // bit 2: timing experiment, no epilogue at all
+      }
       tc_fence_before();
       if (pair) mbar_arrive_cluster(&tempty[acc], 0); else mbar_arrive(&tempty[acc]);
     }
@@ -807,7 +870,7 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
   tc_fence_before();
   // a CTA must outlive every multicast write / remote barrier arrival aimed at it
   if (csize > 1) cluster_sync_all(); else __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     if (pair) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }

@@ -409,9 +409,10 @@ __global__ void best_finalize_kernel(const float* __restrict__ pv, const int* __
   int idx = pi[r * tiles];
   for (int t = 1; t < tiles; ++t) {
     const float v = pv[r * tiles + t];
-    if (v > best) {
+    const int vi = pi[r * tiles + t];
+    if (v > best || (v == best && vi < idx)) {   // ties -> lowest index, whatever the slot order
       best = v;
-      idx = pi[r * tiles + t];
+      idx = vi;
     }
   }
   bv[r] = best;

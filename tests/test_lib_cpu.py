@@ -34,7 +34,8 @@ def test_library_exports_every_declared_symbol():
 def test_version_and_tiles_without_gpu():
     lib = _lib.load()
     assert lib.opp_version() >= 100
-    assert lib.opp_sim_tiles(4096) == 16 and lib.opp_sim_tiles(5000) == 20 and lib.opp_sim_tiles(100) == 1
+    g = lib.opp_sim_tiles(100)   # partial slots per column tile = epilogue warp groups (1 or 2)
+    assert g in (1, 2) and lib.opp_sim_tiles(4096) == 16 * g and lib.opp_sim_tiles(5000) == 20 * g
     assert lib.opp_kv_chunks(4096) * 128 >= 4096
 
 
