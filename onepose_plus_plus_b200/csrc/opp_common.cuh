@@ -422,6 +422,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// explicit shared-space accesses (32-bit shared addresses): pointers kept in structs decay to
+// generic LD/ST, which showed up as long-scoreboard stalls all over the epilogues
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // named barrier among a subset of warps (id 0 is __syncthreads)
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -457,7 +481,14 @@ __device__ __forceinline__ void load_half8(const __half* src, float* v) {
 __device__ __forceinline__ float elu_plus_one(float x) { return x > 0.f ? x + 1.f : expf(x); }
 // Epilogue variant on the SFU (ex2.approx): |rel err| <= ~(2 + |1.44 x|) ulp, i.e. < 2e-6 for the
 // arguments that matter (x in (-10, 0]); one instruction pair instead of ~25.
-__device__ __forceinline__ float elu_plus_one_fast(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+// exp(x) as one FMUL + MUFU.EX2 (flush-to-zero): relative error ~2^-22 from ex2.approx plus
+// |x| * 6e-8 from the log2(e) product, i.e. <= 1e-5 for |x| <= 100.
+__device__ __forceinline__ float fast_exp(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+  return y;
+}
+__device__ __forceinline__ float elu_plus_one_fast(float x) { return x > 0.f ? x + 1.f : fast_exp(x); }
 
 // ---------------------------------------------------------------------------------------------
 // split-precision activations.  Every tensor that feeds a tensor-core GEMM is stored as a pair of

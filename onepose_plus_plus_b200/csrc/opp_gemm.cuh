@@ -104,6 +104,7 @@ struct EpiCtx {
   int etid;        // 0..127 within the epilogue group
   float* smem;     // 2 KB of scratch shared by this epilogue group
   uint8_t* wstage; // kWarpStageBytes private to this warp (transpose buffer for coalesced I/O)
+  uint32_t smem_s, wstage_s;   // the same two regions as 32-bit shared-space addresses
   int group;       // epilogue warp group (0/1); groups take alternate 32-column chunks
   int col_first, col_step;
   // rows (lane>>2) + 8*i, i = 0..3 of this warp's quarter: element offset grow*ld is NOT stored,
@@ -150,11 +151,11 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
                                                  const float* v, int nvalid) {
   if (s.debug_skip & 8) return;   // bit 3: timing experiment, epilogue math without the stores
   const int lane = threadIdx.x & 31;
-  uint8_t* st = c.wstage;
+  const uint32_t st = c.wstage_s;
 #pragma unroll
   for (int plane = 0; plane < 2; ++plane) {
     if (plane == 1 && lo_off == 0) break;
-    uint4* mine = reinterpret_cast<uint4*>(st + lane * kStageRowH);
+    const uint32_t mine = st + lane * kStageRowH;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       uint4 u;
@@ -173,7 +174,7 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
         u.z = pack_half2(l[4], l[5]);
         u.w = pack_half2(l[6], l[7]);
       }
-      mine[g] = u;
+      sts128(mine + g * 16, u);
     }
     __syncwarp();
     const int seg = lane & 3;
@@ -182,7 +183,7 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
       const int rr = (lane >> 2) + 8 * i;
       if (((c.svalid >> i) & 1u) && seg * 8 < nvalid)
         *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + plane * lo_off + gcol + seg * 8) =
-            *reinterpret_cast<const uint4*>(st + rr * kStageRowH + seg * 16);
+            lds128(st + rr * kStageRowH + seg * 16);
     }
     __syncwarp();
   }
@@ -239,14 +240,20 @@ struct EpiQ {
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128)
-      c.smem[i] = p.ksum[(long long)c.b * s.n_total + c.n0 + i];
+      sts32f(c.smem_s + 4 * i, p.ksum[(long long)c.b * s.n_total + c.n0 + i]);
     epi_sync(c);
     tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = elu_plus_one_fast(v[j]);
-        dot = fmaf(v[j], c.smem[col + j], dot);
+      for (int g = 0; g < 8; ++g) {
+        const uint4 kq = lds128(c.smem_s + 4 * (col + 4 * g));
+        const float kk[4] = {__uint_as_float(kq.x), __uint_as_float(kq.y), __uint_as_float(kq.z),
+                             __uint_as_float(kq.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[4 * g + j] = elu_plus_one_fast(v[4 * g + j]);
+          dot = fmaf(v[4 * g + j], kk[j], dot);
+        }
       }
       const float z = p.v_len / (dot + p.eps);
 #pragma unroll
@@ -284,12 +291,10 @@ struct EpiLN {
   // normalises and writes its own chunks.  Row-per-thread loads/stores measured faster here than
   // the warp-staged path.
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    float* g_s = c.smem;
-    float* b_s = c.smem + 256;
     epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128) {
-      g_s[i] = p.gamma[i];
-      b_s[i] = p.beta[i];
+      sts32f(c.smem_s + 4 * i, p.gamma[i]);
+      sts32f(c.smem_s + 4 * (256 + i), p.beta[i]);
     }
     epi_sync(c);
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;
@@ -336,7 +341,14 @@ struct EpiLN {
     const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
     tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * g_s[col + j] + b_s[col + j];
+      for (int g = 0; g < 8; ++g) {
+        const uint4 gq = lds128(c.smem_s + 4 * (col + 4 * g));
+        const uint4 bq = lds128(c.smem_s + 4 * (256 + col + 4 * g));
+        v[4 * g + 0] = (v[4 * g + 0] - mean) * rstd * __uint_as_float(gq.x) + __uint_as_float(bq.x);
+        v[4 * g + 1] = (v[4 * g + 1] - mean) * rstd * __uint_as_float(gq.y) + __uint_as_float(bq.y);
+        v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * __uint_as_float(gq.z) + __uint_as_float(bq.z);
+        v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * __uint_as_float(gq.w) + __uint_as_float(bq.w);
+      }
       if (!c.valid) return;
       if (p.resid) {
         const __half* rrow = p.resid + c.grow * p.ld;
@@ -393,7 +405,7 @@ struct EpiConv {
   }
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     epi_sync(c);
-    for (int i = c.etid; i < c.ncols; i += 128) c.smem[i] = p.bias[c.n0 + i];
+    for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
     epi_sync(c);
     // residual: row-per-thread 16 B loads, issued one 32-column chunk ahead of their use
     const bool has_res = p.resid != nullptr && c.valid;
@@ -413,7 +425,13 @@ struct EpiConv {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] += c.smem[(col + j) & 255];
+      for (int g = 0; g < 8; ++g) {
+        const uint4 bq = lds128(c.smem_s + 4 * ((col + 4 * g) & 255));
+        v[4 * g + 0] += __uint_as_float(bq.x);
+        v[4 * g + 1] += __uint_as_float(bq.y);
+        v[4 * g + 2] += __uint_as_float(bq.z);
+        v[4 * g + 3] += __uint_as_float(bq.w);
+      }
       if (has_res) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -469,7 +487,7 @@ struct EpiLse {
     tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col + j < c.ncols) sum += __expf(v[j] * p.scale - m);
+        if (col + j < c.ncols) sum += fast_exp(v[j] * p.scale - m);
     });
     if (c.valid) {
       // a group that saw no column of a ragged last tile leaves (m = -inf, s = 0): neutral in the merge
@@ -499,7 +517,7 @@ struct EpiConf {
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128)
-      c.smem[i] = p.lse_other[(long long)c.b * s.n_total + c.n0 + i];
+      sts32f(c.smem_s + 4 * i, p.lse_other[(long long)c.b * s.n_total + c.n0 + i]);
     epi_sync(c);
     const float lown = c.valid ? p.lse_own[c.grow] : 0.f;
     float best = -1.f;
@@ -509,9 +527,9 @@ struct EpiConf {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x2 = 2.f * (v[j] * p.scale);
-        const float lo = c.smem[(col + j) & 255];
+        const float lo = lds32f(c.smem_s + 4 * ((col + j) & 255));
         const float e = p.own_is_pt ? (x2 - lown) - lo : (x2 - lo) - lown;
-        v[j] = __expf(e);
+        v[j] = fast_exp(e);
         if (col + j < c.ncols && v[j] > best) {
           best = v[j];
           best_idx = c.n0 + col + j;
@@ -829,6 +847,8 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
     c.col_step = 32 * Epi::kGroups;
     c.smem = epi_smem + c.group * (kEpiParamBytes / 8);   // 2 KB (512 floats) per group
     c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + warp * kWarpStageBytes;
+    c.smem_s = smem_u32(c.smem);
+    c.wstage_s = smem_u32(c.wstage);
     int it = 0;
     for (int t = cluster_id; t < total_tiles; t += n_clusters, ++it) {
       const int acc = it & 1;

@@ -305,17 +305,33 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restric
 #pragma unroll
   for (int v = 0; v < 32; ++v) acc[v] = 0.f;
   float ks = 0.f;
+  // software pipeline: the global loads of sub-chunk i+1 are in flight (registers) while the
+  // warps run the FMAs of sub-chunk i out of shared memory
+  constexpr int kPer = kKvSub * 64 / 256;   // 8-value groups per thread per sub-chunk (d = 256)
+  float x[kPer][8];
+  auto fetch = [&](int t0) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = threadIdx.x + u * 256;
+      const int t = i / groups, g = i - t * groups;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
+      if (t0 + t < cnt) load_split8(src + (long long)(t0 + t) * ld, g * 8, x[u], lo_off);
+    }
+  };
+  fetch(0);
   for (int t0 = 0; t0 < cnt; t0 += kKvSub) {
     __syncthreads();
-    for (int i = threadIdx.x; i < kKvSub * groups; i += 256) {
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      const int i = threadIdx.x + u * 256;
       const int t = i / groups, g = i - t * groups;
-      float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (t0 + t < cnt) load_split8(src + (long long)(t0 + t) * ld, g * 8, x, lo_off);
       float4* dst = reinterpret_cast<float4*>(&xs[t][g * 8]);
-      dst[0] = make_float4(x[0], x[1], x[2], x[3]);
-      dst[1] = make_float4(x[4], x[5], x[6], x[7]);
+      dst[0] = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+      dst[1] = make_float4(x[u][4], x[u][5], x[u][6], x[u][7]);
     }
     __syncthreads();
+    if (t0 + kKvSub < cnt) fetch(t0 + kKvSub);
     if (warp < H) {
 #pragma unroll 4
       for (int t = 0; t < kKvSub; ++t) {
@@ -352,10 +368,19 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
                                                           int d, float inv_vlen, int lo_off) {
   __shared__ float kv_s[33][33];
   const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
+  // chunk partials are 33.8 KB apart: keep 8 loads in flight per element (a plain loop serialised
+  // ~40 DRAM/L2 round trips per thread and made this tiny kernel cost as much as a GEMM)
+  const long long cstride = (long long)H * 33 * 32;
+  const float* pbase = part + (((long long)b * chunks) * H + h) * 33 * 32;
   for (int i = threadIdx.x; i < 33 * 32; i += 256) {
-    float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += part[((((long long)b * chunks + c) * H + h) * 33) * 32 + i];
-    kv_s[i / 32][i % 32] = s;
+    float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int c = 0;
+    for (; c + 8 <= chunks; c += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc8[u] += pbase[(c + u) * cstride + i];
+    }
+    for (; c < chunks; ++c) acc8[0] += pbase[c * cstride + i];
+    kv_s[i / 32][i % 32] = ((acc8[0] + acc8[1]) + (acc8[2] + acc8[3])) + ((acc8[4] + acc8[5]) + (acc8[6] + acc8[7]));
   }
   __syncthreads();
   if (threadIdx.x < 32) ksum[(long long)b * d + h * 32 + threadIdx.x] = kv_s[32][threadIdx.x];
