@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restric
 
 // mt[b][c][h*32+dd] = sum_v merge_w[c][h*32+v] * KV[b][h][dd][v] / v_len ; ksum[b][h*32+dd]
 // (transformer.py:85 `merge` folded into the per-image KV state)
-__global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restrict__ part,
+__global__ void __launch_bounds__(1024) kv_finalize_kernel(const float* __restrict__ part,
                                                           const float* __restrict__ merge_w,
                                                           __half* __restrict__ mt,
                                                           float* __restrict__ ksum, int chunks,
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
   // ~40 DRAM/L2 round trips per thread and made this tiny kernel cost as much as a GEMM)
   const long long cstride = (long long)H * 33 * 32;
   const float* pbase = part + (((long long)b * chunks) * H + h) * 33 * 32;
-  for (int i = threadIdx.x; i < 33 * 32; i += 256) {
+  for (int i = threadIdx.x; i < 33 * 32; i += 1024) {   // 1024 threads: one pass for 1056 elements
     float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     int c = 0;
     for (; c + 8 <= chunks; c += 8) {
@@ -384,20 +384,20 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
   }
   __syncthreads();
   if (threadIdx.x < 32) ksum[(long long)b * d + h * 32 + threadIdx.x] = kv_s[32][threadIdx.x];
-  for (int c = threadIdx.x; c < d; c += 256) {
-    float w[32];
-    const float4* wp = reinterpret_cast<const float4*>(merge_w + (long long)c * d + h * 32);
+  // thread (c, g): output row c of the merge-folded state, columns h*32 + 8g .. +7
+  {
+    const int c = threadIdx.x & 255, g = threadIdx.x >> 8;
+    if (c < d) {
+      float w[32];
+      const float4* wp = reinterpret_cast<const float4*>(merge_w + (long long)c * d + h * 32);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 t = wp[q];
-      w[4 * q] = t.x;
-      w[4 * q + 1] = t.y;
-      w[4 * q + 2] = t.z;
-      w[4 * q + 3] = t.w;
-    }
-    __half* dst = mt + ((long long)b * d + c) * (lo_off ? 2 * d : d);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = wp[q];
+        w[4 * q] = t.x;
+        w[4 * q + 1] = t.y;
+        w[4 * q + 2] = t.z;
+        w[4 * q + 3] = t.w;
+      }
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(256) kv_finalize_kernel(const float* __restric
         for (int v = 0; v < 32; ++v) sacc = fmaf(w[v], kv_s[g * 8 + j][v], sacc);
         o[j] = sacc * inv_vlen;
       }
-      store_split8(dst, h * 32 + g * 8, o, lo_off);
+      store_split8(mt + ((long long)b * d + c) * (lo_off ? 2 * d : d), h * 32 + g * 8, o, lo_off);
     }
   }
 }
@@ -790,9 +790,9 @@ int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int s
 int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ksum, int batch,
                     int chunks, int d, float v_len, int split, opp_stream_t stream) {
   OPP_REQUIRE(part && merge_w && mt && ksum, "null pointer");
-  OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
+  OPP_REQUIRE(d % 32 == 0 && d <= 256, "d=%d must be a multiple of the head size 32, <= 256", d);
   dim3 grid(d / 32, batch);
-  kv_finalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(part, merge_w, (__half*)mt, ksum,
+  kv_finalize_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(part, merge_w, (__half*)mt, ksum,
                                                              chunks, d, 1.f / v_len,
                                                              split ? d : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
