@@ -33,7 +33,8 @@ def test_golden_parity(case):
 
 @pytest.mark.parametrize("shape", [(512, 512, 5000, 3000, 1, True),    # BASELINE configs[0]/[1]
                                    (480, 640, 2500, 1500, 1, False),   # config 5 image shape (S = 4800)
-                                   (256, 320, 1500, 700, 3, True)])
+                                   (256, 320, 1500, 700, 3, True),
+                                   (192, 264, 1501, 500, 2, False)])    # odd point count, 24x33 cells
 def test_planted_parity_vs_oracle(shape):
     h, w, n, npl, B, with_scale = shape
     sd = _sd()
