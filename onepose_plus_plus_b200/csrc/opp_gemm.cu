@@ -118,11 +118,14 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
   }
   const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair);
   auto kern = gemm_kernel<A_MODE, Epi>;
-  static bool attr_set = false;  // one per template instantiation
-  if (!attr_set) {
+  // function attributes are per device: set once per (template instantiation, device)
+  static unsigned long long attr_done = 0;
+  int dev = 0;
+  OPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !((attr_done >> dev) & 1ull)) {
     OPP_CHECK_CUDA(
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    attr_done |= 1ull << dev;
   }
   const long long total = (long long)s.batches * s.msup * s.n_tiles;   // super tiles
   if (total == 0) return OPP_OK;

@@ -729,11 +729,13 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
   OPP_REQUIRE(image && w_t && bias && out, "null pointer");
   OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
   const int smem = (49 * c_out + c_out + 37 * 37) * 4;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_done = 0;   // per device
+  int dev = 0;
+  OPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !((attr_done >> dev) & 1ull)) {
     OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
+    attr_done |= 1ull << dev;
   }
   dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
   conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,

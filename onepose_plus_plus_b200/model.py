@@ -373,6 +373,10 @@ class OnePosePlus_model(nn.Module):
             self._ws[key] = t
         return t
 
+    def clear_workspace(self):
+        """Drop the cached per-shape workspace tensors (they are re-created on the next forward)."""
+        self._ws = {}
+
     # ------------------------------------------------------------------ stages
     def _backbone(self, img):
         """ResNetFPN_8_2.forward (backbone/resnet.py:141-164) -> coarse tokens (+pe), fine map."""
@@ -580,7 +584,8 @@ class OnePosePlus_model(nn.Module):
         if not img.is_cuda:
             raise RuntimeError("OnePosePlus_model (B200) has no CPU path: move the model and data to "
                                "a CUDA device")
-        with torch.no_grad():
+        # kernels are enqueued on the current stream of the tensors' device
+        with torch.no_grad(), torch.cuda.device(img.device):
             dev = img.device
             sig = self._signature()
             if self._plan is None or self._plan_sig != sig:

@@ -33,7 +33,7 @@ WANT = [("gpu__time_duration.sum", "time"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
         ("launch__registers_per_thread", "regs"), ("launch__cluster_size", "cluster")]
-for rep in ("prof_conv", "prof_xfmr"):
+for rep in ("prof_conv", "prof_xfmr", "prof_simt"):
     try:
         txt = subprocess.run(["ncu", "-i", f"gpurun_out/{rep}.ncu-rep", "--page", "raw", "--csv"],
                              capture_output=True, text=True).stdout
