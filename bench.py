@@ -185,6 +185,7 @@ def main():
     except OSError:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_burst = peaks.get("bf16_tflops", 1590.0)   # for a kernel timed alone (B200_PROFILING.md)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
 
     B = args.batch
@@ -270,7 +271,7 @@ def main():
 
     # dominant kernel: the tcgen05 implicit-GEMM conv engine (21 launches / forward), timed live
     # with CUDA events around the backbone on the launching stream
-    conv_ms = attn_ms = None
+    conv_ms = attn_ms = l1_ms = None
     S_tok = (H // 8) * (W // 8)
     if rank == 0:
         img_f = imgs_dev.contiguous().float()
@@ -284,6 +285,23 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         conv_ms = e0.elapsed_time(e1) / 3
+        # the dominant kernel launch: layer1 3x3 conv 128->128 at 1/2 resolution (4 identical launches
+        # per forward = 30 % of the conv flops), timed alone on the launching stream.  Its input
+        # (batch x 256 x 256 x 2 planes x 128 ch fp16 = 2.1 GB at batch 64) exceeds L2.
+        from onepose_plus_plus_b200 import ops as _ops
+        pl_ = 2 if model.split else 1
+        x0 = model._buf("x0", (B, H // 2, W // 2, pl_ * 128), torch.float16, dev)
+        y0 = model._buf("l1a_t", (B, H // 2, W // 2, pl_ * 128), torch.float16, dev)
+        wl1, bl1 = model._plan["layer1.0.conv1"]
+        for _ in range(3):
+            _ops.conv2d_nhwc(x0, wl1, bl1, y0, 3, 1, model.split, act=1)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            _ops.conv2d_nhwc(x0, wl1, bl1, y0, 3, 1, model.split, act=1)
+        e1.record()
+        torch.cuda.synchronize()
+        l1_ms = e0.elapsed_time(e1) / 5
         # coarse attention (BASELINE.json "coarse-attn tensor-pipe %"): the 6-layer linear-attention
         # transformer on both sequences = 60 tcgen05 GEMM launches + the KV-state kernels
         q2, _, (hc, wc) = model._backbone(img_f)
@@ -322,6 +340,8 @@ def main():
         flops = conv_flops_table(B)
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
         passes = 3 if model.split else 1
+        l1_flops = 2.0 * B * (H // 2) * (W // 2) * 128 * 128 * 9
+        l1_tf = l1_flops / (l1_ms * 1e-3) / 1e12
         attn_flops = 2.0 * ((S_tok + N_POINTS) * 6 * 10 * 256 * 256 + (S_tok + N_POINTS) * 6 * 2 * 256 * 32) * B
         attn_tf = attn_flops / (attn_ms * 1e-3) / 1e12
         line = {
@@ -341,15 +361,20 @@ def main():
             "e2e": {"value": total_imgs / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_kernel<A_CONV,EpiConv> (21 launches/forward, "
-                         "timed with the conv1/upsample kernels of the backbone)",
-                         "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach / peak_tf if ach else None, "traffic": None, "peak_source": peak_src,
-                         "backbone_ms": conv_ms, "mma_passes": passes,
-                         "issued_tensor_tflops": ach * passes if ach else None,
-                         "issued_frac": ach * passes / peak_tf if ach else None,
-                         "note": "achieved counts ALGORITHMIC conv flops (reference fp32 math, true channel "
-                                 "counts); the fp32-grade mode issues mma_passes x that on the tensor pipe"},
+            "roofline": {"bound": "tensor",
+                         "kernel": "gemm_kernel<A_CONV,EpiConv>: layer1 3x3 conv 128->128 @256x256 (one launch, whole batch)",
+                         "achieved": l1_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": l1_tf / peak_burst,
+                         "traffic": 496.7e6 * B / 8,
+                         "peak_source": peak_src.replace("bf16_tflops_sustained", "bf16_tflops (burst: kernel timed alone)"), "ms_per_launch": l1_ms,
+                         "algorithmic_flops_per_launch": l1_flops, "mma_passes": passes,
+                         "issued_tensor_tflops": l1_tf * passes, "issued_frac": l1_tf * passes / peak_burst,
+                         "note": "achieved = algorithmic flops (2*B*256*256*128*128*9, reference fp32 math) / CUDA-event "
+                                 "time of the launch; the fp32-grade mode issues mma_passes x that on the tensor pipe; "
+                                 "traffic = dram read+write of this launch from ncu --set full at batch 8 (269.1 + 227.6 MB, "
+                                 "profiles/r1_ncu_summary.md) scaled to the batch",
+                         "backbone": {"kernels": "21 conv launches + conv1_7x7 + 2 upsample2x_add", "ms": conv_ms,
+                                      "algorithmic_tflops": ach, "frac": ach / peak_tf if ach else None,
+                                      "issued_frac": ach * passes / peak_tf if ach else None}},
             "coarse_attention": {
                 "kernels": "gemm_kernel<A_ROWS,{EpiStoreF16,EpiQ,EpiLN}> x60 + kv_partial/kv_finalize x12",
                 "ms": attn_ms, "algorithmic_tflops": attn_tf, "issued_tensor_tflops": attn_tf * passes,
