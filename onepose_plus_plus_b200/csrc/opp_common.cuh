@@ -408,6 +408,24 @@ template <class F>
 __device__ __forceinline__ void tmem_foreach32(uint32_t tbase, int ncols, F&& f) {
   tmem_foreach32(tbase, ncols, 0, 32, f);
 }
+// Same walk without the lookahead chunk (32 fewer live registers).  Meant for epilogues that run
+// two warp groups: 320 threads cap a thread at 168 registers, and the second warp resident on
+// each SM sub-partition hides the TMEM load latency instead.
+template <class F>
+__device__ __forceinline__ void tmem_foreach32_lean(uint32_t tbase, int ncols, int first, int step,
+                                                    F&& f) {
+  float v[32];
+  for (int col = first; col < ncols; col += step) {
+    tmem_ld32(tbase + col, v);
+    f(col, v);
+  }
+}
+template <bool LOOKAHEAD, class F>
+__device__ __forceinline__ void tmem_foreach32_sel(uint32_t tbase, int ncols, int first, int step,
+                                                   F&& f) {
+  if constexpr (LOOKAHEAD) tmem_foreach32(tbase, ncols, first, step, f);
+  else tmem_foreach32_lean(tbase, ncols, first, step, f);
+}
 // explicit shared-space accesses (32-bit shared addresses): pointers kept in structs decay to
 // generic LD/ST, which showed up as long-scoreboard stalls all over the epilogues
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {

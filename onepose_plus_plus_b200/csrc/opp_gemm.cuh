@@ -299,7 +299,7 @@ struct EpiLN {
     epi_sync(c);
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;
     int cnt = 0;
-    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+    tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       if (cnt == 0) x0 = v[0];
       cnt += 32;
 #pragma unroll
@@ -339,7 +339,7 @@ struct EpiLN {
       m2 = m2a + m2b + delta * delta * (na * nb / n);
     }
     const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
-    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+    tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const uint4 gq = lds128(c.smem_s + 4 * (col + 4 * g));
@@ -421,7 +421,7 @@ struct EpiConv {
       }
     };
     if (has_res && c.col_first < c.ncols) issue(c.col_first);
-    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+    tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
 #pragma unroll

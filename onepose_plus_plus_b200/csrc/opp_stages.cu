@@ -4,6 +4,7 @@
 // fine-window gather, per-match linear attention and the correlation soft-argmax.
 // Each kernel cites the reference code it replaces (paths relative to zju3dv/OnePose_Plus_Plus).
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/opp_b200.h"
 #include "opp_common.cuh"
@@ -356,6 +357,155 @@ __global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restric
     for (int q = 0; q < 8; ++q)
       row[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     dst[32 * 32 + lane] = ks;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the same state (selected by $OPP_KV_MMA, see opp_kv_partial).
+// Per head the state is a 32x32 GEMM over the tokens of the chunk, KV[d][v] = sum_t K'[t][d] V[t][v]:
+// M = d, N = v, K = token.  The tile is far too small for tcgen05 (M = 128 would compute 8x the
+// needed head blocks and wants token-major operands transposed), so each warp (= head) runs
+// mma.sync m16n8k16 on fragments fetched with ldmatrix.trans straight from the token-major rows:
+// the kernel is a pure stream over kv16 (2 KB per token in split mode) and should sit on the HBM
+// roofline instead of the shared-memory/FMA issue limit of the SIMT version.
+//   split: K' = Kh + Kl, V = Vh + Vl  ->  Kh*Vh + Kh*Vl + Kl*Vh (fp32 accumulate, lo*lo dropped)
+//   ksum:  one extra n-tile whose B fragment is the constant 1.0 (no loads): C[d][*] = sum_t K'[t][d]
+// Rows are staged by cp.async (16 B, zero-filled past the end of the sequence) into a 3-stage
+// ring of 16-token slabs; the 16 B row padding makes the 8 row addresses of every ldmatrix 8x8
+// block fall into distinct bank groups.
+// ---------------------------------------------------------------------------------------------
+constexpr int kKvmTok = 16;     // tokens per pipeline stage = one k16 MMA step
+constexpr int kKvmStages = 3;
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr)
+               : "memory");
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, "
+      "{%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) kv_partial_mma_kernel(const __half* __restrict__ kv16,
+                                                             float* __restrict__ part, int S) {
+  extern __shared__ __align__(16) uint8_t kvm_smem[];
+  constexpr int kRowB = SPLIT ? 2048 : 1024;      // [K'(256) V(256)] fp16, x2 planes when split
+  constexpr int kStride = kRowB + 16;
+  constexpr int kStageB = kKvmTok * kStride;
+  constexpr int kUnitsPerRow = kRowB / 16;
+  constexpr int kUnits = kKvmTok * kUnitsPerRow;   // 16-byte units per stage
+  constexpr int kLoB = 1024;                       // byte offset of the lo plane inside a row
+  const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s0 = chunk * kKvChunk;
+  const int cnt = min(kKvChunk, S - s0);
+  const int nsteps = (cnt + kKvmTok - 1) / kKvmTok;
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(kv16) + ((long long)b * S + s0) * kRowB;
+  const uint32_t sbase = smem_u32(kvm_smem);
+
+  auto load_stage = [&](int step) {
+    if (step < nsteps) {
+      const uint32_t st = sbase + (step % kKvmStages) * kStageB;
+      const int t0 = step * kKvmTok;
+#pragma unroll
+      for (int j = 0; j < kUnits / 256; ++j) {
+        const int u = threadIdx.x + j * 256;
+        const int t = u / kUnitsPerRow, o = (u % kUnitsPerRow) * 16;
+        const bool ok = t0 + t < cnt;
+        cp_async16_zfill(st + t * kStride + o, src + (long long)(ok ? t0 + t : 0) * kRowB + o,
+                         ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();   // an empty group keeps the wait_group arithmetic uniform
+  };
+
+  float acc[2][4][4], ks[2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ks[mt][i] = 0.f;
+  }
+  // ldmatrix row addresses of this lane: matrix q = lane / 8, row r = lane % 8
+  const int q = lane >> 3, r = lane & 7;
+  //   A (K', M = d): q -> (token half q >> 1, d half q & 1)
+  const uint32_t a_off = (uint32_t)(((q >> 1) * 8 + r) * kStride + (warp * 32 + (q & 1) * 8) * 2);
+  //   B (V, N = v):  q -> (token half q & 1, n-tile q >> 1 of the pair)
+  const uint32_t b_off = (uint32_t)(((q & 1) * 8 + r) * kStride + (256 + warp * 32 + (q >> 1) * 8) * 2);
+  const uint32_t ones = 0x3C003C00u;   // half2(1, 1)
+
+  load_stage(0);
+  load_stage(1);
+  for (int step = 0; step < nsteps; ++step) {
+    load_stage(step + 2);
+    cp_async_wait<2>();
+    __syncthreads();
+    const uint32_t st = sbase + (step % kKvmStages) * kStageB;
+    uint32_t ah[2][4], al[2][4], bh[2][4], bl[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      ldsm_x4_trans(ah[mt], st + a_off + mt * 32);
+      if (SPLIT) ldsm_x4_trans(al[mt], st + a_off + kLoB + mt * 32);
+    }
+#pragma unroll
+    for (int np = 0; np < 2; ++np) {
+      ldsm_x4_trans(bh[np], st + b_off + np * 32);
+      if (SPLIT) ldsm_x4_trans(bl[np], st + b_off + kLoB + np * 32);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int np = nt >> 1, o = (nt & 1) * 2;
+        mma_16816(acc[mt][nt], ah[mt], bh[np][o], bh[np][o + 1]);
+        if (SPLIT) {
+          mma_16816(acc[mt][nt], ah[mt], bl[np][o], bl[np][o + 1]);
+          mma_16816(acc[mt][nt], al[mt], bh[np][o], bh[np][o + 1]);
+        }
+      }
+      mma_16816(ks[mt], ah[mt], ones, ones);
+      if (SPLIT) mma_16816(ks[mt], al[mt], ones, ones);
+    }
+    __syncthreads();   // the slab is refilled by the load issued at the top of the next iteration
+  }
+  cp_async_wait<0>();
+  // C fragment: c0,c1 = (row g, cols 2tg, 2tg+1), c2,c3 = (row g + 8, same cols)
+  const int g = lane >> 2, tg = lane & 3;
+  float* dst = part + ((((long long)b * chunks + chunk) * 8 + warp) * 33) * 32;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      *reinterpret_cast<float2*>(dst + (mt * 16 + g) * 32 + nt * 8 + 2 * tg) =
+          make_float2(acc[mt][nt][0], acc[mt][nt][1]);
+      *reinterpret_cast<float2*>(dst + (mt * 16 + g + 8) * 32 + nt * 8 + 2 * tg) =
+          make_float2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+    if (tg == 0) {
+      dst[32 * 32 + mt * 16 + g] = ks[mt][0];
+      dst[32 * 32 + mt * 16 + g + 8] = ks[mt][2];
+    }
   }
 }
 
@@ -777,14 +927,48 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
 
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 
+// $OPP_KV_MMA selects the linear-attention state kernel: 1 = mma.sync tensor-core stream,
+// 0 = SIMT (fp32 FMA).  Both write the same partial layout.
+#ifndef OPP_KV_MMA_DEFAULT
+#define OPP_KV_MMA_DEFAULT 0
+#endif
+static int kv_mma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OPP_KV_MMA");
+    v = e ? atoi(e) : OPP_KV_MMA_DEFAULT;
+  }
+  return v;
+}
+
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");
   OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
   OPP_REQUIRE(d == 256, "kv_partial is built for d = 256 (8 heads x 32), got %d", d);
   dim3 grid((s + kKvChunk - 1) / kKvChunk, batch);
-  kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d,
-                                                            split ? 2 * d : 0);
+  if (kv_mma_enabled()) {
+    const int smem = kKvmStages * kKvmTok * ((split ? 2048 : 1024) + 16);
+    static unsigned long long attr_done = 0;   // per device
+    int dev = 0;
+    OPP_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && !((attr_done >> dev) & 1ull)) {
+      OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<true>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<false>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_done |= 1ull << dev;
+    }
+    if (split)
+      kv_partial_mma_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16,
+                                                                              part, s);
+    else
+      kv_partial_mma_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16,
+                                                                               part, s);
+  } else {
+    kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d,
+                                                              split ? 2 * d : 0);
+  }
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
