@@ -269,6 +269,27 @@ def main():
     h2d = imgs_host.numel() * 4 + scale_host.numel() * 4 + sum(v.numel() * 4 for v in bank_host.values())
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
+    # BASELINE configs[1] (one image per forward): latency view of the same path, wall clock incl.
+    # host launch overhead and the per-forward match-count sync
+    b1 = None
+    if rank == 0:
+        try:
+            d1 = {"query_image": imgs_dev[:1].contiguous(), "query_image_scale": scale_dev[:1].contiguous(), **bank}
+            for _ in range(3):
+                model(dict(d1))
+            torch.cuda.synchronize()
+            n1, t_b1 = 20, time.perf_counter()
+            for _ in range(n1):
+                o1 = dict(d1)
+                model(o1)
+            torch.cuda.synchronize()
+            dt1 = (time.perf_counter() - t_b1) / n1
+            b1 = {"workload": "BASELINE configs[1]: one 512x512 image vs the 5000-pt bank (batch 1)",
+                  "ms_per_image": dt1 * 1e3, "images_per_s": 1.0 / dt1, "matches": int(o1["b_ids"].numel()),
+                  "timing": f"wall clock over {n1} back-to-back forwards (host launches + match-count sync included)"}
+        except Exception as e:  # noqa: BLE001  (auxiliary number: never lose the bench line over it)
+            b1 = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+
     # dominant kernel: the tcgen05 implicit-GEMM conv engine (21 launches / forward), timed live
     # with CUDA events around the backbone on the launching stream
     conv_ms = attn_ms = l1_ms = None
@@ -381,6 +402,8 @@ def main():
                 "frac_of_peak_algorithmic": attn_tf / peak_tf, "frac_of_peak_issued": attn_tf * passes / peak_tf,
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
                 "tensor_pipe_pct_ncu": "see profiles/r1_ncu_summary.md (per-launch sm__pipe_tensor_cycles_active)"},
+            "latency_b1": b1,
+            "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH), "kv_mma": _lib.get_option("kv_mma")},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

@@ -33,6 +33,13 @@ int opp_version(void);
 const char* opp_last_error(void);
 int opp_num_sms(void);
 
+/* Process-wide kernel selection switches (no reference counterpart: the reference picks its
+ * kernels inside PyTorch).  "kv_mma": 1 = opp_kv_partial runs the mma.sync tensor-core stream,
+ * 0 = the SIMT fp32 kernel (initial value: $OPP_KV_MMA, else the build default).
+ * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */
+int opp_set_option(const char* name, int value);
+int opp_get_option(const char* name);
+
 /* ------------------------------------------------------------------------------------------
  * Backbone — ResNetFPN_8_2.forward (backbone/resnet.py:141-164), BatchNorm folded on the host
  * ---------------------------------------------------------------------------------------- */

@@ -5,6 +5,7 @@
 // Each kernel cites the reference code it replaces (paths relative to zju3dv/OnePose_Plus_Plus).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/opp_b200.h"
 #include "opp_common.cuh"
@@ -927,18 +928,33 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
 
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 
-// $OPP_KV_MMA selects the linear-attention state kernel: 1 = mma.sync tensor-core stream,
-// 0 = SIMT (fp32 FMA).  Both write the same partial layout.
+// $OPP_KV_MMA (or opp_set_option("kv_mma", v)) selects the linear-attention state kernel:
+// 1 = mma.sync tensor-core stream, 0 = SIMT (fp32 FMA).  Both write the same partial layout.
 #ifndef OPP_KV_MMA_DEFAULT
 #define OPP_KV_MMA_DEFAULT 0
 #endif
+static int g_kv_mma = -1;
 static int kv_mma_enabled() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_kv_mma < 0) {
     const char* e = getenv("OPP_KV_MMA");
-    v = e ? atoi(e) : OPP_KV_MMA_DEFAULT;
+    g_kv_mma = e ? atoi(e) : OPP_KV_MMA_DEFAULT;
   }
-  return v;
+  return g_kv_mma;
+}
+
+int opp_set_option(const char* name, int value) {
+  OPP_REQUIRE(name, "null option name");
+  if (strcmp(name, "kv_mma") == 0) {
+    g_kv_mma = value ? 1 : 0;
+    return OPP_OK;
+  }
+  set_last_error("unknown option '%s'", name);
+  return OPP_ERR_INVALID;
+}
+
+int opp_get_option(const char* name) {
+  if (name && strcmp(name, "kv_mma") == 0) return kv_mma_enabled();
+  return -1;
 }
 
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,

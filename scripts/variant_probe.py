@@ -1,0 +1,106 @@
+"""One library variant on the GPU: kernel checks of every tcgen05 epilogue + the KV-state kernels
+(SIMT and mma.sync), golden end-to-end parity, and batch-64 forward timing with both KV kernels.
+
+    OPP_B200_LIB=variants/libopp_<name>.so python scripts/variant_probe.py <tag>
+
+Prints one JSON line (also written to gpurun_out/variants/<tag>.json)."""
+import io
+import json
+import os
+import sys
+import time
+import traceback
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from onepose_plus_plus_b200 import OnePosePlus_model, _lib  # noqa: E402
+from oracle import oracle, workload  # noqa: E402
+from tests import golden_io, kernel_checks, parity  # noqa: E402
+
+tag = sys.argv[1] if len(sys.argv) > 1 else "probe"
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+res = {"tag": tag, "lib": _lib.LIB_PATH, "checks": {}, "timing": {}}
+t_start = time.time()
+
+
+def guarded(name, fn):
+    try:
+        fn()
+        torch.cuda.synchronize()
+        res["checks"][name] = "ok"
+    except BaseException as e:  # noqa: BLE001  (a device trap surfaces as RuntimeError)
+        res["checks"][name] = f"FAIL: {type(e).__name__}: {str(e)[:300]}"
+        traceback.print_exc()
+
+
+def golden(kv):
+    for case in golden_io.cases():
+        data, z = golden_io.load(case)
+        got = parity.run_cuda(data)
+        rep = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
+        res.setdefault("golden", {})[f"{case}[kv_mma={kv}]"] = rep
+
+
+_STEP = {}
+
+
+def make_step():
+    """the bench's resident step (batch B, 512x512, shared 5000-point planted bank)"""
+    if _STEP:
+        return _STEP["fn"]
+    sd = workload.synthetic_state_dict(0)
+    model = parity.cuda_model()
+    data, _ = workload.planted_workload(sd, 512, 512, 5000, 3000, batch=1)
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(100)
+    imgs = (data["query_image"] + 0.02 * torch.randn(B, 1, 512, 512, generator=g)).clamp(0, 1).to(dev)
+    scale = data["query_image_scale"].expand(B, -1).contiguous().to(dev)
+    bank = {k: data[k].to(dev) for k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db")}
+
+    def step():
+        d = {"query_image": imgs, "query_image_scale": scale,
+             **{k: v.expand(B, -1, -1) for k, v in bank.items()}}
+        model(d)
+        return d
+
+    _STEP["fn"] = step
+    return step
+
+
+def timing(kv):
+    step = make_step()
+    for _ in range(3):
+        d = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        d = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    rows = _lib.profile_ops(step, io.StringIO())
+    res["timing"][f"kv_mma={kv}"] = {
+        "batch": B, "ms_per_forward": ms, "images_per_s": B / ms * 1e3, "M": int(d["b_ids"].numel()),
+        "ops_ms": {k: round(v[1], 3) for k, v in sorted(rows.items(), key=lambda kv_: -kv_[1][1])}}
+
+
+# everything with the SIMT KV kernel first: a device-side fault in the new mma kernel then only
+# costs its own results
+for kv in (0, 1):
+    _lib.set_option("kv_mma", kv)
+    guarded(f"kv_state[kv_mma={kv}]", kernel_checks.check_kv_state)
+    if kv == 0:
+        for name in ("linear_ln", "conv", "linear_act", "linear_q", "sim"):
+            guarded(name, kernel_checks.CHECKS[name])
+    guarded(f"golden[kv_mma={kv}]", lambda kv=kv: golden(kv))
+    if res["checks"][f"kv_state[kv_mma={kv}]"] == "ok":
+        guarded(f"timing[kv_mma={kv}]", lambda kv=kv: timing(kv))
+
+res["seconds"] = round(time.time() - t_start, 1)
+os.makedirs(os.path.join(ROOT, "gpurun_out", "variants"), exist_ok=True)
+line = json.dumps(res)
+open(os.path.join(ROOT, "gpurun_out", "variants", tag + ".json"), "w").write(line + "\n")
+print(line)
