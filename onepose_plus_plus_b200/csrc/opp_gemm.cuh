@@ -34,10 +34,22 @@
 #define OPP_CONV_GROUPS 1
 #endif
 #ifndef OPP_LN_GROUPS
-#define OPP_LN_GROUPS 1
+#define OPP_LN_GROUPS 2   // two groups + register-lean TMEM walk: no spills at the 168-register cap
 #endif
 #ifndef OPP_ROW_GROUPS
 #define OPP_ROW_GROUPS 2   // EpiStoreF16 / EpiQ / EpiLse / EpiConf
+#endif
+// Coalesced (warp-staged) global I/O in the LayerNorm epilogue / for the fp32 conf_matrix store
+// instead of row-per-thread 16 B accesses (32 L1 wavefronts per instruction).
+#ifndef OPP_LN_STAGED
+#define OPP_LN_STAGED 0
+#endif
+#ifndef OPP_CONF_STAGED
+#define OPP_CONF_STAGED 0
+#endif
+// positional-encoding add of the token epilogue with 16 B loads instead of scalar ones
+#ifndef OPP_PE_VEC
+#define OPP_PE_VEC 0
 #endif
 
 namespace opp {
@@ -189,6 +201,82 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
   }
 }
 
+// Inverse of staged_store_h32: r[0..31] = the fp32 value (hi + lo) of this lane's row at global
+// columns [gcol, gcol+32).  Global reads are coalesced (one instruction = 8 rows x 64 B); the
+// row-per-thread form (one instruction = 32 rows x 16 B) costs 32 L1 wavefronts per instruction and
+// made the LayerNorm epilogues wavefront-bound.  Rows / columns outside the tensor read as 0.
+// `pre` holds loads issued earlier by staged_load_issue (so their latency overlaps other work).
+struct StagedRows {
+  uint4 hi[4], lo[4];
+};
+__device__ __forceinline__ void staged_load_issue(const EpiCtx& c, const __half* src, long long ld,
+                                                  int lo_off, int gcol, int nvalid, StagedRows& pre) {
+  const int lane = threadIdx.x & 31;
+  const int seg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool in = ((c.svalid >> i) & 1u) && seg * 8 < nvalid;
+    const __half* row = src + c.sgrow[i] * ld + gcol + seg * 8;
+    pre.hi[i] = in ? *reinterpret_cast<const uint4*>(row) : make_uint4(0, 0, 0, 0);
+    pre.lo[i] = (in && lo_off) ? *reinterpret_cast<const uint4*>(row + lo_off) : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void staged_load_add(const EpiCtx& c, int lo_off, const StagedRows& pre,
+                                                float* v) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t st = c.wstage_s;
+  const uint32_t mine = st + lane * kStageRowH;
+  const int seg = lane & 3;
+#pragma unroll
+  for (int plane = 0; plane < 2; ++plane) {
+    if (plane == 1 && lo_off == 0) break;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      sts128(st + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16, plane == 0 ? pre.hi[i] : pre.lo[i]);
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 u = lds128(mine + g * 16);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[8 * g + 2 * j] += f.x;
+        v[8 * g + 2 * j + 1] += f.y;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 rows (conf_matrix): v = this lane's 32 values for global columns [gcol, gcol+32), written in
+// two 16-column halves through the same transpose buffer (16 fp32 = 64 B = one staging row), so a
+// store instruction covers 8 rows x 64 B instead of 32 rows x 16 B.  nvalid: multiple of 4.
+__device__ __forceinline__ void staged_store_f32(const EpiCtx& c, float* out, long long ld, int gcol,
+                                                 const float* v, int nvalid) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t st = c.wstage_s;
+  const uint32_t mine = st + lane * kStageRowH;
+  const int seg = lane & 3;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      sts128(mine + g * 16,
+             make_uint4(__float_as_uint(v[16 * half + 4 * g]), __float_as_uint(v[16 * half + 4 * g + 1]),
+                        __float_as_uint(v[16 * half + 4 * g + 2]), __float_as_uint(v[16 * half + 4 * g + 3])));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      if (((c.svalid >> i) & 1u) && 16 * half + seg * 4 < nvalid)
+        *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + gcol + 16 * half + seg * 4) =
+            lds128(st + rr * kStageRowH + seg * 16);
+    }
+    __syncwarp();
+  }
+}
+
 // =============================================================================================
 // Epilogues.  Outputs that feed later GEMMs are written as (hi|lo) plane pairs when
 // `out_lo` != 0: row layout [hi(n_total) | lo(n_total)], out_lo = n_total.
@@ -319,6 +407,9 @@ struct EpiLN {
       *mine = ga;
       named_bar_sync(3, 256);
       const float4 o = *other;
+#if OPP_LN_STAGED
+      named_bar_sync(3, 256);   // the slots live in the transpose buffers the second pass reuses
+#endif
       if (c.group == 0) {
         gb = o;
       } else {
@@ -340,6 +431,10 @@ struct EpiLN {
     }
     const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+#if OPP_LN_STAGED
+      StagedRows pre;
+      if (p.resid) staged_load_issue(c, p.resid, p.ld, p.out_lo, c.n0 + col, c.ncols - col, pre);
+#endif
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const uint4 gq = lds128(c.smem_s + 4 * (col + 4 * g));
@@ -349,6 +444,17 @@ struct EpiLN {
         v[4 * g + 2] = (v[4 * g + 2] - mean) * rstd * __uint_as_float(gq.z) + __uint_as_float(bq.z);
         v[4 * g + 3] = (v[4 * g + 3] - mean) * rstd * __uint_as_float(gq.w) + __uint_as_float(bq.w);
       }
+#if OPP_LN_STAGED
+      // every lane takes part in the warp-staged transposes; row validity is per staged row
+      if (p.resid) staged_load_add(c, p.out_lo, pre, v);
+      if (p.out32 && c.valid) {
+        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + col);
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          o4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      if (p.out16) staged_store_h32(s, c, p.out16, p.ld, p.out_lo, c.n0 + col, v, c.ncols - col);
+#else
       if (!c.valid) return;
       if (p.resid) {
         const __half* rrow = p.resid + c.grow * p.ld;
@@ -371,6 +477,7 @@ struct EpiLN {
 #pragma unroll
         for (int g = 0; g < 4; ++g) store_split8(row, col + g * 8, v + g * 8, p.out_lo);
       }
+#endif
     });
     if (kGroups == 2) named_bar_sync(3, 256);   // the exchange slots are reused by the next tile
   }
@@ -455,10 +562,24 @@ struct EpiConv {
       if (p.out) staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, nvalid);
       if (p.tok) {
         if (c.valid) {
+#if OPP_PE_VEC
+          // 8 x 16 B loads per chunk (scalar loads cost 32 L1 wavefronts each: rows are 1 KB apart)
+          const float4* pe4 = reinterpret_cast<const float4*>(p.pe + (long long)c.row * s.n_total + g0);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (4 * g < nvalid) {
+              const float4 q4 = pe4[g];
+              v[4 * g + 0] += q4.x;
+              v[4 * g + 1] += q4.y;
+              v[4 * g + 2] += q4.z;
+              v[4 * g + 3] += q4.w;
+            }
+#else
           const float* pe = p.pe + (long long)c.row * s.n_total + g0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (j < nvalid) v[j] += pe[j];
+#endif
         }
         staged_store_h32(s, c, p.tok, p.ld, p.out_lo, g0, v, nvalid);
       }
@@ -523,7 +644,7 @@ struct EpiConf {
     float best = -1.f;
     int best_idx = c.n0;
     const bool vec_ok = (s.n_total & 3) == 0;
-    tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+    tmem_foreach32_sel<!OPP_CONF_STAGED>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const float x2 = 2.f * (v[j] * p.scale);
@@ -535,6 +656,11 @@ struct EpiConf {
           best_idx = c.n0 + col + j;
         }
       }
+#if OPP_CONF_STAGED
+      if (p.conf && vec_ok) {
+        staged_store_f32(c, p.conf, (long long)s.n_total, c.n0 + col, v, c.ncols - col);
+      } else
+#endif
       if (p.conf && c.valid) {
         float* dst = p.conf + c.grow * (long long)s.n_total + c.n0 + col;
         if (vec_ok) {

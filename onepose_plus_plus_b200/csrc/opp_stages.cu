@@ -931,7 +931,7 @@ int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 // $OPP_KV_MMA (or opp_set_option("kv_mma", v)) selects the linear-attention state kernel:
 // 1 = mma.sync tensor-core stream, 0 = SIMT (fp32 FMA).  Both write the same partial layout.
 #ifndef OPP_KV_MMA_DEFAULT
-#define OPP_KV_MMA_DEFAULT 0
+#define OPP_KV_MMA_DEFAULT 1
 #endif
 static int g_kv_mma = -1;
 static int kv_mma_enabled() {
