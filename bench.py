@@ -403,7 +403,8 @@ def main():
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
                 "tensor_pipe_pct_ncu": "see profiles/r1_ncu_summary.md (per-launch sm__pipe_tensor_cycles_active)"},
             "latency_b1": b1,
-            "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH), "kv_mma": _lib.get_option("kv_mma")},
+            "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH), "kv_mma": _lib.get_option("kv_mma"),
+                               "conv1_staged": _lib.get_option("conv1_staged")},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

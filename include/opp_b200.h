@@ -34,8 +34,12 @@ const char* opp_last_error(void);
 int opp_num_sms(void);
 
 /* Process-wide kernel selection switches (no reference counterpart: the reference picks its
- * kernels inside PyTorch).  "kv_mma": 1 = opp_kv_partial runs the mma.sync tensor-core stream,
- * 0 = the SIMT fp32 kernel (initial value: $OPP_KV_MMA, else the build default).
+ * kernels inside PyTorch).
+ *   "kv_mma":       1 = opp_kv_partial runs the mma.sync tensor-core stream, 0 = the SIMT fp32
+ *                   kernel (initial value: $OPP_KV_MMA, else the build default)
+ *   "conv1_staged": 1 = opp_conv1_7x7 writes its output through a per-warp transpose buffer
+ *                   (8 pixels x 64 B per store instruction), 0 = one 16 B store per pixel
+ *                   (initial value: $OPP_CONV1_STAGED, else the build default)
  * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */
 int opp_set_option(const char* name, int value);
 int opp_get_option(const char* name);

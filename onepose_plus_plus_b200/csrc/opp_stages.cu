@@ -75,6 +75,108 @@ __global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict_
   }
 }
 
+// Same convolution with warp-staged output stores (selected by opp_set_option("conv1_staged") /
+// $OPP_CONV1_STAGED).  In the kernel above every 16 B store instruction of a warp touches 32
+// different pixels = 32 L1 wavefronts, 32 such instructions per thread: the store stream, not the
+// FMAs, bounds it.  Here a warp collects 32 channels (4 groups of 8) of its 32 pixels in a
+// shared-memory transpose buffer and writes them as 8 pixels x 64 B per instruction (4x fewer
+// wavefronts).  Requires C % 32 == 0.
+constexpr int kC1StageRow = 80;   // 32 fp16 (64 B) + 16 B pad per pixel row of the transpose buffer
+
+__global__ void __launch_bounds__(256, 3) conv1_7x7_staged_kernel(const float* __restrict__ img,
+                                                               const float* __restrict__ w_t,
+                                                               const float* __restrict__ bias,
+                                                               __half* __restrict__ out, int H, int W,
+                                                               int C, int lo_off) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                 // [49][C]
+  float* b_s = w_s + 49 * C;       // [C]
+  float* p_s = b_s + C;            // [37][37] input patch
+  constexpr int P = 2 * kC1Tile + 5;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(p_s + ((P * P + 3) & ~3));   // [8 warps][2 planes][32][80 B]
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
+  const int OH = H / 2, OW = W / 2;
+  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
+  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
+  const float* im = img + (long long)b * H * W;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < P * P; i += 256) {
+    const int py = i / P, px = i - py * P;
+    const int y = iy0 + py, x = ix0 + px;
+    p_s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / kC1Tile, lx = threadIdx.x % kC1Tile;
+  float x[49];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) x[ky * 7 + kx] = p_s[(2 * ly + ky) * P + 2 * lx + kx];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t st_hi = smem_u32(stage) + warp * (2 * 32 * kC1StageRow);
+  const uint32_t st_lo = st_hi + 32 * kC1StageRow;
+  const int ld = lo_off ? 2 * C : C;
+  // the four pixels this lane writes back: local index rr = (lane >> 2) + 8 i of the warp's 32
+  // pixels (warp w = tile rows 2w, 2w+1; pixel rr -> row 2w + rr / 16, column rr % 16)
+  long long pix_off[4];
+  unsigned pix_ok = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = (lane >> 2) + 8 * i;
+    const int oy = oy0 + 2 * warp + rr / kC1Tile, ox = ox0 + rr % kC1Tile;
+    if (oy < OH && ox < OW) pix_ok |= 1u << i;
+    pix_off[i] = (((long long)b * OH + oy) * OW + ox) * ld;
+  }
+  const int seg = lane & 3;
+  for (int cq = 0; cq < C; cq += 32) {
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg) {
+      const int c0 = cq + cg * 8;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = b_s[c0 + j];
+#pragma unroll
+      for (int t = 0; t < 49; ++t) {
+        const float4 wa = *reinterpret_cast<const float4*>(w_s + t * C + c0);
+        const float4 wb = *reinterpret_cast<const float4*>(w_s + t * C + c0 + 4);
+        acc[0] = fmaf(x[t], wa.x, acc[0]);
+        acc[1] = fmaf(x[t], wa.y, acc[1]);
+        acc[2] = fmaf(x[t], wa.z, acc[2]);
+        acc[3] = fmaf(x[t], wa.w, acc[3]);
+        acc[4] = fmaf(x[t], wb.x, acc[4]);
+        acc[5] = fmaf(x[t], wb.y, acc[5]);
+        acc[6] = fmaf(x[t], wb.z, acc[6]);
+        acc[7] = fmaf(x[t], wb.w, acc[7]);
+      }
+      float lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = fmaxf(acc[j], 0.f);
+        lo[j] = acc[j] - __half2float(__float2half_rn(acc[j]));
+      }
+      sts128(st_hi + lane * kC1StageRow + cg * 16,
+             make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
+                        pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7])));
+      if (lo_off)
+        sts128(st_lo + lane * kC1StageRow + cg * 16,
+               make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]),
+                          pack_half2(lo[6], lo[7])));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = (lane >> 2) + 8 * i;
+      if ((pix_ok >> i) & 1u) {
+        __half* dst = out + pix_off[i] + cq + seg * 8;
+        *reinterpret_cast<uint4*>(dst) = lds128(st_hi + rr * kC1StageRow + seg * 16);
+        if (lo_off) *reinterpret_cast<uint4*>(dst + lo_off) = lds128(st_lo + rr * kC1StageRow + seg * 16);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // =============================================================================================
 // out = a + bilinear_x2(b), align_corners=True   (backbone/resnet.py:151-152,155-156)
 // torch semantics: src = dst * (in-1)/(out-1); i0 = floor(src); i1 = min(i0+1, in-1)
@@ -875,22 +977,43 @@ extern "C" {
 int opp_version(void) { return 100; }
 int opp_num_sms(void) { return opp::num_sms(); }
 
+#ifndef OPP_CONV1_STAGED_DEFAULT
+#define OPP_CONV1_STAGED_DEFAULT 0
+#endif
+static int g_conv1_staged = -1;
+static int conv1_staged_enabled() {
+  if (g_conv1_staged < 0) {
+    const char* e = getenv("OPP_CONV1_STAGED");
+    g_conv1_staged = e ? atoi(e) : OPP_CONV1_STAGED_DEFAULT;
+  }
+  return g_conv1_staged;
+}
+
 int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
                   int h, int w, int c_out, int split, opp_stream_t stream) {
   OPP_REQUIRE(image && w_t && bias && out, "null pointer");
   OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
-  const int smem = (49 * c_out + c_out + 37 * 37) * 4;
+  const bool staged = conv1_staged_enabled() && c_out % 32 == 0;
+  const int patch = (37 * 37 + 3) & ~3;
+  const int smem = staged ? (49 * c_out + c_out + patch) * 4 + 8 * 2 * 32 * kC1StageRow
+                          : (49 * c_out + c_out + 37 * 37) * 4;
   static unsigned long long attr_done = 0;   // per device
   int dev = 0;
   OPP_CHECK_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !((attr_done >> dev) & 1ull)) {
     OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_staged_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr_done |= 1ull << dev;
   }
   dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
-  conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
-                                                              c_out, split ? c_out : 0);
+  if (staged)
+    conv1_7x7_staged_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+        image, w_t, bias, (__half*)out, h, w, c_out, split ? c_out : 0);
+  else
+    conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
+                                                                c_out, split ? c_out : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -948,12 +1071,17 @@ int opp_set_option(const char* name, int value) {
     g_kv_mma = value ? 1 : 0;
     return OPP_OK;
   }
+  if (strcmp(name, "conv1_staged") == 0) {
+    g_conv1_staged = value ? 1 : 0;
+    return OPP_OK;
+  }
   set_last_error("unknown option '%s'", name);
   return OPP_ERR_INVALID;
 }
 
 int opp_get_option(const char* name) {
   if (name && strcmp(name, "kv_mma") == 0) return kv_mma_enabled();
+  if (name && strcmp(name, "conv1_staged") == 0) return conv1_staged_enabled();
   return -1;
 }
 

@@ -1,7 +1,8 @@
-"""Reads gpurun_out/variants/{base,ln2conv2}.json (scripts/variant_probe.py) and decides, kernel by
-kernel, which build options pay off: LayerNorm epilogue warp groups (opp_linear_ln time), conv
-epilogue warp groups (opp_conv2d_nhwc time) and the KV-state kernel (kv_mma).  Prints shell
-assignments selecting the matching prebuilt library: `export OPP_B200_LIB=... OPP_KV_MMA=...`."""
+"""Reads gpurun_out/variants/{f000,f111}.json (scripts/variant_probe.py) and decides feature by
+feature from the per-op times: L = coalesced LayerNorm-epilogue I/O (opp_linear_ln), C = coalesced
+conf_matrix store (opp_sim_conf), V = conv epilogue on two warp groups + vectorised pe
+(opp_conv2d_nhwc), and the runtime option conv1_staged (opp_conv1_7x7).  Prints shell assignments
+selecting the matching prebuilt library: `export OPP_B200_LIB=... OPP_CONV1_STAGED=...`."""
 import json
 import os
 import sys
@@ -21,34 +22,41 @@ def log(*a):
     print("#", *a, file=sys.stderr)
 
 
-base, two = load("base"), load("ln2conv2")
+base, full = load("f000"), load("f111")
 if base is None:
-    log("no base probe result")
+    log("no f000 probe result")
     sys.exit(1)
-for r in (base, two):
+for r in (base, full):
     if r:
-        log(r["tag"], {k: (v if v == "ok" else v[:80]) for k, v in r["checks"].items()},
-            {k: round(v["ms_per_forward"], 2) for k, v in r["timing"].items() if isinstance(v, dict)})
+        log(r["tag"], {k: (v if v == "ok" else v[:90]) for k, v in r["checks"].items()},
+            {k: round(v["ms_per_forward"], 2) for k, v in r["timing"].items()})
+
+D0, D1 = "conv1_staged=0", "conv1_staged=1"
 
 
 def ok(r, *names):
     return r is not None and all(r["checks"].get(n) == "ok" for n in names)
 
 
-kv = 0
-t0, t1 = base["timing"].get("kv_mma=0"), base["timing"].get("kv_mma=1")
-if ok(base, "kv_state[kv_mma=1]", "golden[kv_mma=1]") and t1 and (t0 is None or
-                                                                  t1["ms_per_forward"] < t0["ms_per_forward"]):
-    kv = 1
-ln = conv = 1
-key = "kv_mma=0" if (two and "kv_mma=0" in two["timing"] and t0) else "kv_mma=1"
-if two and key in two["timing"] and key in base["timing"] and ok(two, "golden[kv_mma=0]"):
-    ob, ot = base["timing"][key]["ops_ms"], two["timing"][key]["ops_ms"]
-    log("linear_ln ms base/2-group:", ob.get("opp_linear_ln"), ot.get("opp_linear_ln"),
-        " conv ms base/2-group:", ob.get("opp_conv2d_nhwc"), ot.get("opp_conv2d_nhwc"))
-    if ok(two, "linear_ln") and ot["opp_linear_ln"] < 0.97 * ob["opp_linear_ln"]:
-        ln = 2
-    if ok(two, "conv") and ot["opp_conv2d_nhwc"] < 0.97 * ob["opp_conv2d_nhwc"]:
-        conv = 2
-name = {(1, 1): "base", (2, 1): "ln2", (1, 2): "conv2", (2, 2): "ln2conv2"}[(ln, conv)]
-print(f"export OPP_B200_LIB={ROOT}/variants/libopp_{name}.so OPP_KV_MMA={kv}  # ln_groups={ln} conv_groups={conv}")
+def ops(r, label):
+    return r["timing"][label]["ops_ms"] if r and label in r["timing"] else None
+
+
+L = C = V = S = 0
+b0, f0 = ops(base, D0), ops(full, D0)
+if b0 and f0 and ok(full, f"golden[{D0}]", f"kv_state[{D0}]", f"conv1[{D0}]"):
+    log("linear_ln", b0["opp_linear_ln"], "->", f0["opp_linear_ln"], " sim_conf", b0["opp_sim_conf"], "->",
+        f0["opp_sim_conf"], " conv2d", b0["opp_conv2d_nhwc"], "->", f0["opp_conv2d_nhwc"])
+    if ok(full, "linear_ln") and f0["opp_linear_ln"] < 0.99 * b0["opp_linear_ln"]:
+        L = 1
+    if ok(full, "sim") and f0["opp_sim_conf"] < 0.99 * b0["opp_sim_conf"]:
+        C = 1
+    if ok(full, "conv") and f0["opp_conv2d_nhwc"] <= 1.005 * b0["opp_conv2d_nhwc"]:
+        V = 1
+b1 = ops(base, D1)
+if b0 and b1 and ok(base, f"conv1[{D1}]", f"golden[{D1}]"):
+    log("conv1_7x7", b0["opp_conv1_7x7"], "->", b1["opp_conv1_7x7"])
+    if b1["opp_conv1_7x7"] < 0.95 * b0["opp_conv1_7x7"]:
+        S = 1
+print(f"export OPP_B200_LIB={ROOT}/variants/libopp_f{L}{C}{V}.so OPP_CONV1_STAGED={S}"
+      f"  # ln_staged={L} conf_staged={C} conv2+pe_vec={V} conv1_staged={S}")

@@ -1,7 +1,8 @@
-"""One library variant on the GPU: kernel checks of every tcgen05 epilogue + the KV-state kernels
-(SIMT and mma.sync), golden end-to-end parity, and batch-64 forward timing with both KV kernels.
+"""One library build on the GPU: kernel checks of every tcgen05 epilogue and of the kernels behind
+runtime options, golden end-to-end parity, and batch-64 forward timing with a per-op breakdown,
+for each option set given on the command line.
 
-    OPP_B200_LIB=variants/libopp_<name>.so python scripts/variant_probe.py <tag>
+    OPP_B200_LIB=variants/libopp_<name>.so python scripts/variant_probe.py <tag> [opt=val,opt=val ...]
 
 Prints one JSON line (also written to gpurun_out/variants/<tag>.json)."""
 import io
@@ -15,13 +16,15 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from onepose_plus_plus_b200 import OnePosePlus_model, _lib  # noqa: E402
-from oracle import oracle, workload  # noqa: E402
+from onepose_plus_plus_b200 import _lib  # noqa: E402
+from oracle import workload  # noqa: E402
 from tests import golden_io, kernel_checks, parity  # noqa: E402
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "probe"
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-res = {"tag": tag, "lib": _lib.LIB_PATH, "checks": {}, "timing": {}}
+configs = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in a.split(",") if kv)
+           for a in (sys.argv[2:] or [""])]
+B = 64
+res = {"tag": tag, "lib": _lib.LIB_PATH, "checks": {}, "timing": {}, "golden": {}}
 t_start = time.time()
 
 
@@ -35,12 +38,11 @@ def guarded(name, fn):
         traceback.print_exc()
 
 
-def golden(kv):
+def golden(label):
     for case in golden_io.cases():
         data, z = golden_io.load(case)
         got = parity.run_cuda(data)
-        rep = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
-        res.setdefault("golden", {})[f"{case}[kv_mma={kv}]"] = rep
+        res["golden"][f"{case}[{label}]"] = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
 
 
 _STEP = {}
@@ -69,7 +71,7 @@ def make_step():
     return step
 
 
-def timing(kv):
+def timing(label):
     step = make_step()
     for _ in range(3):
         d = step()
@@ -82,22 +84,24 @@ def timing(kv):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     rows = _lib.profile_ops(step, io.StringIO())
-    res["timing"][f"kv_mma={kv}"] = {
+    res["timing"][label] = {
         "batch": B, "ms_per_forward": ms, "images_per_s": B / ms * 1e3, "M": int(d["b_ids"].numel()),
         "ops_ms": {k: round(v[1], 3) for k, v in sorted(rows.items(), key=lambda kv_: -kv_[1][1])}}
 
 
-# everything with the SIMT KV kernel first: a device-side fault in the new mma kernel then only
-# costs its own results
-for kv in (0, 1):
-    _lib.set_option("kv_mma", kv)
-    guarded(f"kv_state[kv_mma={kv}]", kernel_checks.check_kv_state)
-    if kv == 0:
+first = True
+for cfg in configs:
+    label = ",".join(f"{k}={v}" for k, v in cfg.items()) or "default"
+    for k, v in cfg.items():
+        _lib.set_option(k, v)
+    if first:   # the tcgen05 epilogues do not depend on the runtime options
         for name in ("linear_ln", "conv", "linear_act", "linear_q", "sim"):
             guarded(name, kernel_checks.CHECKS[name])
-    guarded(f"golden[kv_mma={kv}]", lambda kv=kv: golden(kv))
-    if res["checks"][f"kv_state[kv_mma={kv}]"] == "ok":
-        guarded(f"timing[kv_mma={kv}]", lambda kv=kv: timing(kv))
+        first = False
+    guarded(f"kv_state[{label}]", kernel_checks.check_kv_state)
+    guarded(f"conv1[{label}]", kernel_checks.CHECKS["conv1"])
+    guarded(f"golden[{label}]", lambda label=label: golden(label))
+    guarded(f"timing[{label}]", lambda label=label: timing(label))
 
 res["seconds"] = round(time.time() - t_start, 1)
 os.makedirs(os.path.join(ROOT, "gpurun_out", "variants"), exist_ok=True)
