@@ -31,7 +31,7 @@
 #include "opp_common.cuh"
 
 #ifndef OPP_CONV_GROUPS
-#define OPP_CONV_GROUPS 1
+#define OPP_CONV_GROUPS 2
 #endif
 #ifndef OPP_LN_GROUPS
 #define OPP_LN_GROUPS 2   // two groups + register-lean TMEM walk: no spills at the 168-register cap
@@ -42,14 +42,14 @@
 // Coalesced (warp-staged) global I/O in the LayerNorm epilogue / for the fp32 conf_matrix store
 // instead of row-per-thread 16 B accesses (32 L1 wavefronts per instruction).
 #ifndef OPP_LN_STAGED
-#define OPP_LN_STAGED 0
+#define OPP_LN_STAGED 1
 #endif
 #ifndef OPP_CONF_STAGED
-#define OPP_CONF_STAGED 0
+#define OPP_CONF_STAGED 1
 #endif
 // positional-encoding add of the token epilogue with 16 B loads instead of scalar ones
 #ifndef OPP_PE_VEC
-#define OPP_PE_VEC 0
+#define OPP_PE_VEC 1
 #endif
 
 namespace opp {

@@ -978,7 +978,7 @@ int opp_version(void) { return 100; }
 int opp_num_sms(void) { return opp::num_sms(); }
 
 #ifndef OPP_CONV1_STAGED_DEFAULT
-#define OPP_CONV1_STAGED_DEFAULT 0
+#define OPP_CONV1_STAGED_DEFAULT 1
 #endif
 static int g_conv1_staged = -1;
 static int conv1_staged_enabled() {
