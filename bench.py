@@ -401,7 +401,7 @@ def main():
                 "ms": attn_ms, "algorithmic_tflops": attn_tf, "issued_tensor_tflops": attn_tf * passes,
                 "frac_of_peak_algorithmic": attn_tf / peak_tf, "frac_of_peak_issued": attn_tf * passes / peak_tf,
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
-                "tensor_pipe_pct_ncu": "see profiles/r1_ncu_summary.md (per-launch sm__pipe_tensor_cycles_active)"},
+                "tensor_pipe_pct_ncu": "per launch in profiles/r1_ncu_summary_staged.md (sm__pipe_tensor_cycles_active at batch 8: mlp.0 70-74 %, [Wk;Wv] 45-47 %, mlp.2+LN 35-37 %, q_proj / Mt+LN 28-30 %; dual-softmax lse passes 94 %)"},
             "latency_b1": b1,
             "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH), "kv_mma": _lib.get_option("kv_mma"),
                                "conv1_staged": _lib.get_option("conv1_staged")},

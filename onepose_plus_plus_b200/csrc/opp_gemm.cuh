@@ -376,8 +376,10 @@ struct EpiLN {
   // Two warp groups share every row (alternate 32-column chunks).  Each thread accumulates shifted
   // sums over its half, the halves are merged with Chan's parallel-variance formula (group 0
   // first, so both threads of a row compute bit-identical statistics), then each group
-  // normalises and writes its own chunks.  Row-per-thread loads/stores measured faster here than
-  // the warp-staged path.
+  // normalises and writes its own chunks.  Residual loads and fp16 stores go through the per-warp
+  // transpose buffer (OPP_LN_STAGED): a row-per-thread 16 B access touches 32 cache lines per
+  // instruction = 32 L1 wavefronts at ~2 clk each, which made this epilogue wavefront-bound
+  // (28-34 k clk per tile against 6-12 k clk of MMA work).
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128) {
