@@ -157,6 +157,13 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
                  int own_is_pt, float* conf, float* part_val, int* part_idx, int batches,
                  int rows, int cols, int k, float scale, int split, opp_stream_t stream);
 
+/* opp_sim_conf for rows = 3D points with the column maxima folded in (saves the second conf pass):
+ * colmax uint32 [B][cols] receives the float bits of max_l conf[b, l, s] (zeroed inside, then
+ * atomicMax per 32-row group; conf >= 0 so the bits order like the values). */
+int opp_sim_conf_colmax(const void* a, const void* b, const float* lse_own, const float* lse_other,
+                        float* conf, float* part_val, int* part_idx, unsigned* colmax, int batches,
+                        int rows, int cols, int k, float scale, int split, opp_stream_t stream);
+
 /* best[r] = max over tiles (ties -> lowest index) */
 int opp_best_finalize(const float* part_val, const int* part_idx, float* best_val, int* best_idx,
                       long long rows, int tiles, opp_stream_t stream);
@@ -173,6 +180,15 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
                      int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
                      long long* j_ids, float* mconf, float* mkpts3d, float* mkpts_c,
                      int* count_out, opp_stream_t stream);
+
+/* opp_match_select with the mutual-nearest test on values (coarse_matching.py:157-165 compares
+ * conf == conf.max(dim) the same way): row l keeps its argmax cell j iff pt_val[b][l] has the same
+ * float bits as colmax[b][j] (from opp_sim_conf_colmax). */
+int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsigned* colmax,
+                            const float* kpts, const float* img_scale, int batch, int l, int hc,
+                            int wc, float thr, int border, float cell, int* scratch,
+                            long long* b_ids, long long* i_ids, long long* j_ids, float* mconf,
+                            float* mkpts3d, float* mkpts_c, int* count_out, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fine level — FinePreprocess (loftr_module/fine_preprocess.py:32-55), loftr_fine,

@@ -37,8 +37,10 @@ SIGNATURES = {
     "opp_sim_lse": [P, P, P, P, I, I, I, I, F, I, P],
     "opp_lse_finalize": [P, P, P, L, I, P],
     "opp_sim_conf": [P, P, P, P, I, P, P, P, I, I, I, I, F, I, P],
+    "opp_sim_conf_colmax": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     "opp_best_finalize": [P, P, P, P, L, I, P],
     "opp_match_select": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, P],
+    "opp_match_select_colmax": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, P],
     "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, P],
     "opp_fine_attention": [P, P, I, I, F, I, P],
     "opp_fine_match": [P, P, P, P, P, P, I, F, P],
@@ -91,7 +93,7 @@ def stream():
 
 
 # kernels launched per entry point (bench.py reports the per-step total as gpu_launches)
-KERNELS_PER_CALL = {"opp_match_select": 3}
+KERNELS_PER_CALL = {"opp_match_select": 3, "opp_match_select_colmax": 3}
 LAUNCHES = 0
 _PROFILE = None
 

@@ -391,6 +391,20 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
   return launch<A_ROWS, EpiConf>(maps, s, ep, (cudaStream_t)stream);
 }
 
+int opp_sim_conf_colmax(const void* a, const void* b, const float* lse_own, const float* lse_other,
+                        float* conf, float* part_val, int* part_idx, unsigned* colmax, int batches,
+                        int rows, int cols, int k, float scale, int split, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
+  if (rc) return rc;
+  OPP_REQUIRE(lse_own && lse_other && part_val && part_idx && colmax, "null pointer");
+  OPP_CHECK_CUDA(cudaMemsetAsync(colmax, 0, (size_t)batches * cols * sizeof(unsigned),
+                                 (cudaStream_t)stream));
+  EpiConfCol::Params ep{lse_own, lse_other, scale, conf, part_val, part_idx, colmax};
+  return launch<A_ROWS, EpiConfCol>(maps, s, ep, (cudaStream_t)stream);
+}
+
 // partial slots per row written by opp_sim_lse / opp_sim_conf: one per column tile and epilogue warp group
 int opp_sim_tiles(int cols) {
   return EpiLse::kGroups * ((cols + pick_block_n(cols) - 1) / pick_block_n(cols));

@@ -685,6 +685,79 @@ struct EpiConf {
   }
 };
 
+// conf pass with the column maxima folded in (replaces the second conf pass): rows are 3D points,
+// conf is stored as in EpiConf, and for every 32x32 chunk the warp reduces each COLUMN over its 32
+// rows with a butterfly (at offset o a lane keeps one half of its 2o values and exchanges the other
+// half with lane ^ o: 31 shuffles, lane j ends with the maximum of column j) followed by one
+// atomicMax per lane on colmax[b][column] (conf >= 0, so its float bits order like unsigned ints).
+// The mutual-nearest test (coarse_matching.py:157-165) is then  rowmax(i) == colmax(argmax_j(i)),
+// an exact comparison of two copies of the same register value.
+struct EpiConfCol {
+  static constexpr int kGroups = OPP_ROW_GROUPS;   // partial slot = kGroups*n_tile + group
+  struct Params {
+    const float* lse_own;    // [batches*rows]   (3D points)
+    const float* lse_other;  // [batches][n_total] (query cells)
+    float scale;
+    float* conf;             // [batches*rows][n_total] or null
+    float* part_val;         // [batches*rows][kGroups*n_tiles]
+    int* part_idx;
+    unsigned* colmax;        // [batches][n_total], zero-initialised
+  };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    epi_sync(c);
+    for (int i = c.etid; i < c.ncols; i += 128)
+      sts32f(c.smem_s + 4 * i, p.lse_other[(long long)c.b * s.n_total + c.n0 + i]);
+    epi_sync(c);
+    const float lown = c.valid ? p.lse_own[c.grow] : 0.f;
+    float best = -1.f;
+    int best_idx = c.n0;
+    const bool vec_ok = (s.n_total & 3) == 0;
+    const int lane = threadIdx.x & 31;
+    unsigned* cm = p.colmax + (long long)c.b * s.n_total + c.n0;
+    tmem_foreach32_lean(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x2 = 2.f * (v[j] * p.scale);
+        const float lo = lds32f(c.smem_s + 4 * ((col + j) & 255));
+        v[j] = fast_exp((x2 - lown) - lo);   // same expression order as EpiConf with own_is_pt
+        if (col + j < c.ncols && v[j] > best) {
+          best = v[j];
+          best_idx = c.n0 + col + j;
+        }
+      }
+      if (p.conf && vec_ok) {
+        staged_store_f32(c, p.conf, (long long)s.n_total, c.n0 + col, v, c.ncols - col);
+      } else if (p.conf && c.valid) {
+        float* dst = p.conf + c.grow * (long long)s.n_total + c.n0 + col;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col + j < c.ncols) dst[j] = v[j];
+      }
+      // column maxima over this warp's 32 rows (rows outside the tensor contribute 0)
+      if (!c.valid) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+          const float keep = up ? v[o + k] : v[k];
+          const float send = up ? v[k] : v[o + k];
+          v[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+      }
+      if (col + lane < c.ncols && v[0] > 0.f) atomicMax(cm + col + lane, __float_as_uint(v[0]));
+    });
+    if (c.valid) {
+      p.part_val[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = best;
+      p.part_idx[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = best_idx;
+    }
+  }
+};
+
 // =============================================================================================
 // The kernel
 // =============================================================================================

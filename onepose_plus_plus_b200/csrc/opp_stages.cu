@@ -218,6 +218,54 @@ __global__ void __launch_bounds__(256) upsample2x_add_kernel(const __half* __res
   }
 }
 
+// Row-mapped variant (opp_set_option("upsample_rows") / $OPP_UPSAMPLE_ROWS): one block per output
+// row, one warp per output pixel at a time, lane = 8-channel group.  The kernel above spends most
+// of its issue slots (ncu: SM 65 %, DRAM 47 %) on 64-bit div/mod index arithmetic per element;
+// here all index math is warp-uniform and division-free, the two source rows stay hot in L1, and
+// the arithmetic on the data is the same expression (bit-identical results).  C <= 256.
+__global__ void __launch_bounds__(256) upsample2x_add_rows_kernel(const __half* __restrict__ a,
+                                                                  const __half* __restrict__ bsrc,
+                                                                  __half* __restrict__ out, int B,
+                                                                  int h, int w, int C, int lo_off) {
+  const int cg = C / 8;
+  const int ld = lo_off ? 2 * C : C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H2 = 2 * h, W2 = 2 * w;
+  const float sy = (float)(h - 1) / (float)(2 * h - 1);
+  const float sx = (float)(w - 1) / (float)(2 * w - 1);
+  const long long rows = (long long)B * H2;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / H2);
+    const int y = (int)(row - (long long)b * H2);
+    const float fy = sy * (float)y;
+    const int y0 = (int)fy;
+    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
+    const float ly = fy - (float)y0, hy = 1.f - ly;
+    const __half* r0 = bsrc + ((long long)b * h + y0) * w * ld;
+    const __half* r1 = bsrc + ((long long)b * h + y1) * w * ld;
+    const long long obase = row * W2 * ld;
+    for (int x = warp; x < W2; x += 8) {
+      const float fx = sx * (float)x;
+      const int x0 = (int)fx;
+      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
+      const float lx = fx - (float)x0, hx = 1.f - lx;
+      if (lane < cg) {
+        float v00[8], v01[8], v10[8], v11[8], va[8], r[8];
+        load_split8(r0 + (long long)x0 * ld, lane * 8, v00, lo_off);
+        load_split8(r0 + (long long)x1 * ld, lane * 8, v01, lo_off);
+        load_split8(r1 + (long long)x0 * ld, lane * 8, v10, lo_off);
+        load_split8(r1 + (long long)x1 * ld, lane * 8, v11, lo_off);
+        const long long off = obase + (long long)x * ld;
+        load_split8(a + off, lane * 8, va, lo_off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          r[j] = va[j] + (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]));
+        store_split8(out + off, lane * 8, r, lo_off);
+      }
+    }
+  }
+}
+
 // =============================================================================================
 // 3D keypoint normalisation statistics   (utils/normalize.py:16-26)
 // stats[b] = (mean xyz over points of batch b, 0.6 * max extent of batch element 0)
@@ -715,6 +763,34 @@ __device__ __forceinline__ bool match_flag(const float* pt_val, const int* pt_id
   return px_idx[b * s + j] == i;
 }
 
+// Same selection with the mutual test expressed on values: row i keeps its argmax cell j iff its
+// row maximum IS the column maximum of j (colmax holds the float bits written by EpiConfCol from
+// the very same conf values, so the comparison is exact; coarse_matching.py:157-165 compares
+// conf == conf.max(dim) the same way).
+__device__ __forceinline__ bool match_flag_colmax(const float* pt_val, const int* pt_idx,
+                                                  const unsigned* colmax, long long r, int l, int s,
+                                                  int wc, float thr, int border) {
+  const float v = pt_val[r];
+  if (!(v > thr)) return false;
+  const int j = pt_idx[r];
+  const int jy = j / wc, jx = j - jy * wc;
+  if (jy < border || jx < border) return false;
+  const long long b = r / l;
+  return colmax[b * s + j] == __float_as_uint(v);
+}
+
+__global__ void __launch_bounds__(1024) match_count_colmax_kernel(const float* pt_val,
+                                                                  const int* pt_idx,
+                                                                  const unsigned* colmax,
+                                                                  long long rows, int l, int s, int wc,
+                                                                  float thr, int border,
+                                                                  int* block_counts) {
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag_colmax(pt_val, pt_idx, colmax, r, l, s, wc, thr, border);
+  const int c = __syncthreads_count(f);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
 __global__ void __launch_bounds__(1024) match_count_kernel(const float* pt_val, const int* pt_idx,
                                                            const int* px_idx, long long rows,
                                                            int l, int s, int wc, float thr,
@@ -775,6 +851,53 @@ match_scatter_kernel(const float* pt_val, const int* pt_idx, const int* px_idx, 
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
+  const unsigned ballot = __ballot_sync(0xffffffffu, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  if (!f) return;
+  const int pos = block_offsets[blockIdx.x] + (warp > 0 ? warp_sums[warp - 1] : 0) +
+                  __popc(ballot & ((1u << lane) - 1u));
+  const long long b = r / l;
+  const int i = (int)(r - b * l);
+  const int j = pt_idx[r];
+  b_ids[pos] = b;
+  i_ids[pos] = i;
+  j_ids[pos] = j;
+  mconf[pos] = pt_val[r];
+  const float* kp = kpts + (b * l + i) * 3;
+  mkpts3d[pos * 3 + 0] = kp[0];
+  mkpts3d[pos * 3 + 1] = kp[1];
+  mkpts3d[pos * 3 + 2] = kp[2];
+  // coarse_matching.py:223-229: [j % w, j // w] * (scale * query_image_scale[b][[1, 0]])
+  float sx = cell, sy = cell;
+  if (img_scale) {
+    sx = cell * img_scale[b * 2 + 1];
+    sy = cell * img_scale[b * 2 + 0];
+  }
+  mkpts_c[pos * 2 + 0] = (float)(j % wc) * sx;
+  mkpts_c[pos * 2 + 1] = (float)(j / wc) * sy;
+}
+
+__global__ void __launch_bounds__(1024)
+match_scatter_colmax_kernel(const float* pt_val, const int* pt_idx, const unsigned* px_idx, const float* kpts,
+                     const float* img_scale, long long rows, int l, int s, int wc, float thr,
+                     int border, float cell, const int* block_offsets, long long* b_ids,
+                     long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
+                     float* mkpts_c) {
+  __shared__ int warp_sums[32];
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag_colmax(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
   const unsigned ballot = __ballot_sync(0xffffffffu, f);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane == 0) warp_sums[warp] = __popc(ballot);
@@ -1018,13 +1141,32 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
   return OPP_OK;
 }
 
+#ifndef OPP_UPSAMPLE_ROWS_DEFAULT
+#define OPP_UPSAMPLE_ROWS_DEFAULT 0
+#endif
+static int g_upsample_rows = -1;
+static int upsample_rows_enabled() {
+  if (g_upsample_rows < 0) {
+    const char* e = getenv("OPP_UPSAMPLE_ROWS");
+    g_upsample_rows = e ? atoi(e) : OPP_UPSAMPLE_ROWS_DEFAULT;
+  }
+  return g_upsample_rows;
+}
+
 int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
                        int split, opp_stream_t stream) {
   OPP_REQUIRE(a && b && out, "null pointer");
   OPP_REQUIRE(c % 8 == 0 && h > 1 && w > 1, "bad upsample shape");
-  const long long total = (long long)batch * 4 * h * w * (c / 8);
-  upsample2x_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
+  if (upsample_rows_enabled() && c <= 256) {
+    const long long rows = (long long)batch * 2 * h;
+    const long long cap = (long long)opp::num_sms() * 8;
+    upsample2x_add_rows_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
+  } else {
+    const long long total = (long long)batch * 4 * h * w * (c / 8);
+    upsample2x_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
+  }
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1075,6 +1217,10 @@ int opp_set_option(const char* name, int value) {
     g_conv1_staged = value ? 1 : 0;
     return OPP_OK;
   }
+  if (strcmp(name, "upsample_rows") == 0) {
+    g_upsample_rows = value ? 1 : 0;
+    return OPP_OK;
+  }
   set_last_error("unknown option '%s'", name);
   return OPP_ERR_INVALID;
 }
@@ -1082,6 +1228,7 @@ int opp_set_option(const char* name, int value) {
 int opp_get_option(const char* name) {
   if (name && strcmp(name, "kv_mma") == 0) return kv_mma_enabled();
   if (name && strcmp(name, "conv1_staged") == 0) return conv1_staged_enabled();
+  if (name && strcmp(name, "upsample_rows") == 0) return upsample_rows_enabled();
   return -1;
 }
 
@@ -1163,6 +1310,26 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
   match_scatter_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, kpts, img_scale, rows, l,
                                                  s, wc, thr, border, cell, scratch, b_ids, i_ids,
                                                  j_ids, mconf, mkpts3d, mkpts_c);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsigned* colmax,
+                            const float* kpts, const float* img_scale, int batch, int l, int hc,
+                            int wc, float thr, int border, float cell, int* scratch,
+                            long long* b_ids, long long* i_ids, long long* j_ids, float* mconf,
+                            float* mkpts3d, float* mkpts_c, int* count_out, opp_stream_t stream) {
+  OPP_REQUIRE(pt_val && pt_idx && colmax && kpts && scratch && count_out, "null pointer");
+  const long long rows = (long long)batch * l;
+  const int nblocks = (int)((rows + 1023) / 1024);
+  const int s = hc * wc;
+  cudaStream_t st = (cudaStream_t)stream;
+  match_count_colmax_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, rows, l, s, wc, thr,
+                                                      border, scratch);
+  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
+  match_scatter_colmax_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, kpts, img_scale, rows,
+                                                        l, s, wc, thr, border, cell, scratch, b_ids,
+                                                        i_ids, j_ids, mconf, mkpts3d, mkpts_c);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

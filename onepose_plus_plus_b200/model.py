@@ -271,6 +271,9 @@ class OnePosePlus_model(nn.Module):
         self._plan = None
         self._plan_sig = None
         self._ws = {}
+        # experimental (not yet validated on a GPU, off by default): take the column maxima of
+        # conf from the first conf pass (warp butterfly + atomicMax) instead of a second GEMM pass
+        self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "0") == "1"
 
     @property
     def split(self):
@@ -494,10 +497,6 @@ class OnePosePlus_model(nn.Module):
         pt_idx = self._buf("pt_idx", (B, N), i32, dev)
         px_val = self._buf("px_val", (B, S), f32, dev)
         px_idx = self._buf("px_idx", (B, S), i32, dev)
-        ops.sim_conf(d3, q2, lse_pt, lse_px, True, conf, B, N, S, 256, scale, pm_pt, pi_pt,
-                     pt_val, pt_idx, split)
-        ops.sim_conf(q2, d3, lse_px, lse_pt, False, None, B, S, N, 256, scale, pm_px, pi_px,
-                     px_val, px_idx, split)
         cap = B * min(N, S)
         scratch = self._buf("match_scratch", ((B * N + 1023) // 1024 + 2,), i32, dev)
         count = self._buf("match_count", (1,), i32, dev)
@@ -511,9 +510,21 @@ class OnePosePlus_model(nn.Module):
         if img_scale is not None:
             img_scale = img_scale.to(device=dev, dtype=f32).contiguous()
         cell = float(data["q_hw_i"][0] / hc)
-        ops.match_select(pt_val, pt_idx, px_idx, data["keypoints3d"], img_scale, B, N, hc, wc,
-                         cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf, mk3, mkc,
-                         count)
+        if self.coarse_colmax:
+            colmax = self._buf("colmax", (B, S), i32, dev)
+            ops.sim_conf_colmax(d3, q2, lse_pt, lse_px, conf, B, N, S, 256, scale, pm_pt, pi_pt,
+                                pt_val, pt_idx, colmax, split)
+            ops.match_select_colmax(pt_val, pt_idx, colmax, data["keypoints3d"], img_scale, B, N, hc, wc,
+                                    cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf,
+                                    mk3, mkc, count)
+        else:
+            ops.sim_conf(d3, q2, lse_pt, lse_px, True, conf, B, N, S, 256, scale, pm_pt, pi_pt,
+                         pt_val, pt_idx, split)
+            ops.sim_conf(q2, d3, lse_px, lse_pt, False, None, B, S, N, 256, scale, pm_px, pi_px,
+                         px_val, px_idx, split)
+            ops.match_select(pt_val, pt_idx, px_idx, data["keypoints3d"], img_scale, B, N, hc, wc,
+                             cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf, mk3, mkc,
+                             count)
         M = int(count.item())  # the one host sync of the forward (the reference syncs in torch.where)
         data.update({
             "conf_matrix": conf,

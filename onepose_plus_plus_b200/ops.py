@@ -139,6 +139,23 @@ def sim_conf(a, b, lse_own, lse_other, own_is_pt, conf, batches, rows, cols, k, 
          batches * rows, tiles, stream())
 
 
+def sim_conf_colmax(a, b, lse_own, lse_other, conf, batches, rows, cols, k, scale, part_val, part_idx,
+                    best_val, best_idx, colmax, split):
+    """conf pass over rows = 3D points that also leaves max_l conf[b, l, s] (float bits) in colmax."""
+    tiles = sim_tiles(cols)
+    call("opp_sim_conf_colmax", ptr(a), ptr(b), ptr(lse_own), ptr(lse_other), ptr(conf), ptr(part_val),
+         ptr(part_idx), ptr(colmax), batches, rows, cols, k, float(scale), int(split), stream())
+    call("opp_best_finalize", ptr(part_val), ptr(part_idx), ptr(best_val), ptr(best_idx),
+         batches * rows, tiles, stream())
+
+
+def match_select_colmax(pt_val, pt_idx, colmax, kpts, img_scale, batch, l, hc, wc, thr, border, cell,
+                        scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count):
+    call("opp_match_select_colmax", ptr(pt_val), ptr(pt_idx), ptr(colmax), ptr(kpts), ptr(img_scale),
+         batch, l, hc, wc, float(thr), int(border), float(cell), ptr(scratch), ptr(b_ids),
+         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), stream())
+
+
 def match_select(pt_val, pt_idx, px_idx, kpts, img_scale, batch, l, hc, wc, thr, border, cell,
                  scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count):
     call("opp_match_select", ptr(pt_val), ptr(pt_idx), ptr(px_idx), ptr(kpts), ptr(img_scale),

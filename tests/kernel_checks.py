@@ -454,6 +454,54 @@ def check_fine():
     _close("fine_match mkpts_f", mf, mkc + co * 2 * (2.0 * scale[b_ids][:, [1, 0]]), 1e-5, 1e-4)
 
 
+# ------------------------------------------------------------------------------ experimental paths
+# Kernels that are built but not yet selected by default (scripts/variant_probe.py runs these on
+# a GPU before a default is flipped); they are NOT part of CHECKS / the pytest -m gpu suite.
+def check_sim_colmax():
+    for split in (0, 1):
+        for (B, L, S, K) in [(2, 700, 520, 256), (1, 300, 100, 256), (1, 5000, 4096, 256)]:
+            af = _rand(B, L, K, scale=0.9, seed=1)
+            bf = _rand(B, S, K, scale=0.9, seed=2)
+            a, b = _planes(af, split), _planes(bf, split)
+            scale = 1.0 / (256 * 0.0801)
+            sim = (torch.einsum("blk,bsk->bls", _q(af, split).double(), _q(bf, split).double()) * scale)
+            lib = _lib.load()
+            ts, tl = lib.opp_sim_tiles(S), lib.opp_sim_tiles(L)
+            lse_pt, lse_px = torch.empty(B, L, device=DEV), torch.empty(B, S, device=DEV)
+            ops.sim_lse(a, b, B, L, S, K, scale, torch.empty(B * L, ts, device=DEV),
+                        torch.empty(B * L, ts, device=DEV), lse_pt, split)
+            ops.sim_lse(b, a, B, S, L, K, scale, torch.empty(B * S, tl, device=DEV),
+                        torch.empty(B * S, tl, device=DEV), lse_px, split)
+            conf = torch.full((B, L, S), float("nan"), device=DEV)
+            pv = torch.empty(B * L, ts, device=DEV)
+            pi = torch.empty(B * L, ts, device=DEV, dtype=torch.int32)
+            bv = torch.empty(B, L, device=DEV)
+            bi = torch.empty(B, L, device=DEV, dtype=torch.int32)
+            colmax = torch.full((B, S), -1, device=DEV, dtype=torch.int32)   # the call must zero it
+            ops.sim_conf_colmax(a, b, lse_pt, lse_px, conf, B, L, S, K, scale, pv, pi, bv, bi, colmax, split)
+            torch.cuda.synchronize()
+            conf_ref = (torch.softmax(sim, 1) * torch.softmax(sim, 2)).float()
+            _close(f"sim_colmax conf split={split} B={B} L={L} S={S}", conf, conf_ref, 5e-4, 1e-7)
+            v, i = conf.max(2)
+            assert torch.equal(bi.long(), i) and torch.equal(bv, v), "row max / argmax mismatch"
+            cm = conf.max(1).values
+            assert torch.equal(colmax, cm.view(torch.int32)), "column maxima are not the bits of conf.max(1)"
+            # the value-based mutual test selects exactly the cells that are row- and column-maximal
+            mutual = (conf == conf.max(2, keepdim=True).values) & (conf == conf.max(1, keepdim=True).values)
+            sel = torch.gather(colmax, 1, bi.long()) == bv.view(torch.int32)
+            assert torch.equal(sel, mutual.any(2)), "mutual-nearest selection differs"
+
+
+def check_upsample_rows():
+    _lib.set_option("upsample_rows", 1)
+    try:
+        check_upsample()
+    finally:
+        _lib.set_option("upsample_rows", 0)
+
+
+EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "upsample_rows": check_upsample_rows}
+
 CHECKS = {
     "linear_act": check_linear_act,
     "linear_ln": check_linear_ln,
