@@ -40,6 +40,11 @@ int opp_num_sms(void);
  *   "conv1_staged": 1 = opp_conv1_7x7 writes its output through a per-warp transpose buffer
  *                   (8 pixels x 64 B per store instruction), 0 = one 16 B store per pixel
  *                   (initial value: $OPP_CONV1_STAGED, else the build default)
+ *   "conv1_px4":    1 = opp_conv1_7x7 computes 4 adjacent output pixels per thread (one pair of
+ *                   weight loads per 32 FMAs); takes precedence over "conv1_staged"
+ *                   (initial value: $OPP_CONV1_PX4, else 0 — not yet validated on a GPU)
+ *   "upsample_rows": 1 = opp_upsample2x_add uses the division-free row-mapped kernel
+ *                   (initial value: $OPP_UPSAMPLE_ROWS, else 0 — not yet validated on a GPU)
  * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */
 int opp_set_option(const char* name, int value);
 int opp_get_option(const char* name);

@@ -177,6 +177,126 @@ __global__ void __launch_bounds__(256, 3) conv1_7x7_staged_kernel(const float* _
   }
 }
 
+// Register-tiled variant (opp_set_option("conv1_px4") / $OPP_CONV1_PX4; not yet validated on a
+// GPU).  ncu of the kernels above: L1 LSU wavefronts 85 %, FMA pipe 36 % — every 8 FMAs of a lane
+// need two 16-byte broadcast loads of the weights from shared memory, so the load/store unit, not
+// the FMA pipe, is the limiter.  Here a thread computes 4 horizontally adjacent output pixels
+// (7 x 13 input values in registers), so one pair of weight loads feeds 32 FMAs.  CTA tile:
+// 64 x 16 output pixels; output through per-warp transpose buffers as in the staged kernel.
+constexpr int kC4TileX = 64, kC4TileY = 16;
+constexpr int kC4PatchW = 2 * kC4TileX + 5;          // 133 input columns
+constexpr int kC4PatchS = 136;                        // padded row stride (floats)
+constexpr int kC4PatchH = 2 * kC4TileY + 5;          // 37 input rows
+
+__global__ void __launch_bounds__(256, 1) conv1_7x7_px4_kernel(const float* __restrict__ img,
+                                                               const float* __restrict__ w_t,
+                                                               const float* __restrict__ bias,
+                                                               __half* __restrict__ out, int H, int W,
+                                                               int C, int lo_off) {
+  extern __shared__ float sm[];
+  float* w_s = sm;                 // [49][C]
+  float* b_s = w_s + 49 * C;       // [C]
+  float* p_s = b_s + C;            // [37][136] input patch
+  uint8_t* stage = reinterpret_cast<uint8_t*>(p_s + kC4PatchH * kC4PatchS);   // [8 warps][4 px][2 planes][32][80 B]
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kC4TileY, ox0 = blockIdx.x * kC4TileX;
+  const int OH = H / 2, OW = W / 2;
+  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
+  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
+  const float* im = img + (long long)b * H * W;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < kC4PatchH * kC4PatchS; i += 256) {
+    const int py = i / kC4PatchS, px = i - py * kC4PatchS;
+    const int y = iy0 + py, x = ix0 + px;
+    p_s[i] = (px < kC4PatchW && y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x >> 4, lx4 = threadIdx.x & 15;   // pixels (oy0 + ly, ox0 + 4 lx4 + p)
+  float x[7][13];
+#pragma unroll
+  for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+    for (int j = 0; j < 13; ++j) x[ky][j] = p_s[(2 * ly + ky) * kC4PatchS + 8 * lx4 + j];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kPlane = 32 * kC1StageRow;                    // one [32 pixels][80 B] buffer
+  const uint32_t st0 = smem_u32(stage) + warp * (4 * 2 * kPlane);   // + p * 2 kPlane (+ kPlane for lo)
+  const int ld = lo_off ? 2 * C : C;
+  // write-back: lane -> pixels rr = (lane >> 2) + 8 i of the warp's 32 lanes, 16 B segment seg;
+  // lane rr owns row 2 warp + rr / 16 and columns 4 (rr % 16) + p
+  long long pix_off[4];
+  int pix_x[4];
+  unsigned row_ok = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = (lane >> 2) + 8 * i;
+    const int oy = oy0 + 2 * warp + (rr >> 4);
+    pix_x[i] = ox0 + 4 * (rr & 15);
+    if (oy < OH) row_ok |= 1u << i;
+    pix_off[i] = (((long long)b * OH + oy) * OW + pix_x[i]) * ld;
+  }
+  const int seg = lane & 3;
+  for (int cq = 0; cq < C; cq += 32) {
+#pragma unroll 1
+    for (int cg = 0; cg < 4; ++cg) {
+      const int c0 = cq + cg * 8;
+      float acc[4][8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[p][j] = b_s[c0 + j];
+#pragma unroll
+      for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+          const float4 wa = *reinterpret_cast<const float4*>(w_s + (ky * 7 + kx) * C + c0);
+          const float4 wb = *reinterpret_cast<const float4*>(w_s + (ky * 7 + kx) * C + c0 + 4);
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const float xv = x[ky][2 * p + kx];
+            acc[p][0] = fmaf(xv, wa.x, acc[p][0]);
+            acc[p][1] = fmaf(xv, wa.y, acc[p][1]);
+            acc[p][2] = fmaf(xv, wa.z, acc[p][2]);
+            acc[p][3] = fmaf(xv, wa.w, acc[p][3]);
+            acc[p][4] = fmaf(xv, wb.x, acc[p][4]);
+            acc[p][5] = fmaf(xv, wb.y, acc[p][5]);
+            acc[p][6] = fmaf(xv, wb.z, acc[p][6]);
+            acc[p][7] = fmaf(xv, wb.w, acc[p][7]);
+          }
+        }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[p][j] = fmaxf(acc[p][j], 0.f);
+          lo[j] = acc[p][j] - __half2float(__float2half_rn(acc[p][j]));
+        }
+        const uint32_t sp = st0 + p * (2 * kPlane) + lane * kC1StageRow + cg * 16;
+        sts128(sp, make_uint4(pack_half2(acc[p][0], acc[p][1]), pack_half2(acc[p][2], acc[p][3]),
+                              pack_half2(acc[p][4], acc[p][5]), pack_half2(acc[p][6], acc[p][7])));
+        if (lo_off)
+          sts128(sp + kPlane, make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
+                                         pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7])));
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        if (((row_ok >> i) & 1u) && pix_x[i] + p < OW) {
+          __half* dst = out + pix_off[i] + (long long)p * ld + cq + seg * 8;
+          const uint32_t sp = st0 + p * (2 * kPlane) + rr * kC1StageRow + seg * 16;
+          *reinterpret_cast<uint4*>(dst) = lds128(sp);
+          if (lo_off) *reinterpret_cast<uint4*>(dst + lo_off) = lds128(sp + kPlane);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // =============================================================================================
 // out = a + bilinear_x2(b), align_corners=True   (backbone/resnet.py:151-152,155-156)
 // torch semantics: src = dst * (in-1)/(out-1); i0 = floor(src); i1 = min(i0+1, in-1)
@@ -1112,14 +1232,28 @@ static int conv1_staged_enabled() {
   return g_conv1_staged;
 }
 
+#ifndef OPP_CONV1_PX4_DEFAULT
+#define OPP_CONV1_PX4_DEFAULT 0
+#endif
+static int g_conv1_px4 = -1;
+static int conv1_px4_enabled() {
+  if (g_conv1_px4 < 0) {
+    const char* e = getenv("OPP_CONV1_PX4");
+    g_conv1_px4 = e ? atoi(e) : OPP_CONV1_PX4_DEFAULT;
+  }
+  return g_conv1_px4;
+}
+
 int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
                   int h, int w, int c_out, int split, opp_stream_t stream) {
   OPP_REQUIRE(image && w_t && bias && out, "null pointer");
   OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
-  const bool staged = conv1_staged_enabled() && c_out % 32 == 0;
+  const bool px4 = conv1_px4_enabled() && c_out % 32 == 0;
+  const bool staged = !px4 && conv1_staged_enabled() && c_out % 32 == 0;
   const int patch = (37 * 37 + 3) & ~3;
-  const int smem = staged ? (49 * c_out + c_out + patch) * 4 + 8 * 2 * 32 * kC1StageRow
-                          : (49 * c_out + c_out + 37 * 37) * 4;
+  const int smem = px4 ? (49 * c_out + c_out + kC4PatchH * kC4PatchS) * 4 + 8 * 4 * 2 * 32 * kC1StageRow
+                  : staged ? (49 * c_out + c_out + patch) * 4 + 8 * 2 * 32 * kC1StageRow
+                           : (49 * c_out + c_out + 37 * 37) * 4;
   static unsigned long long attr_done = 0;   // per device
   int dev = 0;
   OPP_CHECK_CUDA(cudaGetDevice(&dev));
@@ -1128,7 +1262,16 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_staged_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_px4_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done |= 1ull << dev;
+  }
+  if (px4) {
+    dim3 grid((w / 2 + kC4TileX - 1) / kC4TileX, (h / 2 + kC4TileY - 1) / kC4TileY, batch);
+    conv1_7x7_px4_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
+                                                                    c_out, split ? c_out : 0);
+    OPP_CHECK_CUDA(cudaGetLastError());
+    return OPP_OK;
   }
   dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
   if (staged)
@@ -1217,6 +1360,10 @@ int opp_set_option(const char* name, int value) {
     g_conv1_staged = value ? 1 : 0;
     return OPP_OK;
   }
+  if (strcmp(name, "conv1_px4") == 0) {
+    g_conv1_px4 = value ? 1 : 0;
+    return OPP_OK;
+  }
   if (strcmp(name, "upsample_rows") == 0) {
     g_upsample_rows = value ? 1 : 0;
     return OPP_OK;
@@ -1229,6 +1376,7 @@ int opp_get_option(const char* name) {
   if (name && strcmp(name, "kv_mma") == 0) return kv_mma_enabled();
   if (name && strcmp(name, "conv1_staged") == 0) return conv1_staged_enabled();
   if (name && strcmp(name, "upsample_rows") == 0) return upsample_rows_enabled();
+  if (name && strcmp(name, "conv1_px4") == 0) return conv1_px4_enabled();
   return -1;
 }
 

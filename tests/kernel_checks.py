@@ -245,20 +245,23 @@ def check_sim():
 
 
 # ------------------------------------------------------------------------------------------ SIMT
+def _conv1_case(split, B, H, W, C):
+    img = torch.rand(B, 1, H, W, device=DEV)
+    w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
+    bias = _rand(C, seed=3) * 0.1
+    pl = 2 if split else 1
+    out = torch.full((B, H // 2, W // 2, pl * C), float("nan"), device=DEV, dtype=torch.half)
+    w_t = w.view(C, 49).t().contiguous()
+    _lib.call("opp_conv1_7x7", _lib.ptr(img), _lib.ptr(w_t), _lib.ptr(bias), _lib.ptr(out), B, H, W,
+              C, split, _lib.stream())
+    torch.cuda.synchronize()
+    ref = torch.relu(F.conv2d(img.double(), w.double(), bias.double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
+    _close(f"conv1_7x7 split={split} {H}x{W}", _unplanes(out, split), ref, *_tol(split, (1e-3, 1e-3), (2e-6, 2e-6)))
+
+
 def check_conv1():
     for split in (0, 1):
-        B, H, W, C = 2, 96, 128, 128
-        img = torch.rand(B, 1, H, W, device=DEV)
-        w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
-        bias = _rand(C, seed=3) * 0.1
-        pl = 2 if split else 1
-        out = torch.full((B, H // 2, W // 2, pl * C), float("nan"), device=DEV, dtype=torch.half)
-        w_t = w.view(C, 49).t().contiguous()
-        _lib.call("opp_conv1_7x7", _lib.ptr(img), _lib.ptr(w_t), _lib.ptr(bias), _lib.ptr(out), B, H, W,
-                  C, split, _lib.stream())
-        torch.cuda.synchronize()
-        ref = torch.relu(F.conv2d(img.double(), w.double(), bias.double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
-        _close(f"conv1_7x7 split={split}", _unplanes(out, split), ref, *_tol(split, (1e-3, 1e-3), (2e-6, 2e-6)))
+        _conv1_case(split, 2, 96, 128, 128)
 
 
 def check_upsample():
@@ -500,7 +503,23 @@ def check_upsample_rows():
         _lib.set_option("upsample_rows", 0)
 
 
-EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "upsample_rows": check_upsample_rows}
+def check_conv1_px4():
+    _lib.set_option("conv1_px4", 1)
+    try:
+        for split in (0, 1):
+            _conv1_case(split, 2, 96, 128, 128)
+            _conv1_case(split, 1, 72, 200, 128)    # ragged in x (100 = 64 + 36) and y (36 = 2 x 16 + 4)
+    finally:
+        _lib.set_option("conv1_px4", 0)
+
+
+def check_conv1_ragged():
+    for split in (0, 1):
+        _conv1_case(split, 1, 72, 200, 128)
+
+
+EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "upsample_rows": check_upsample_rows,
+                "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged}
 
 CHECKS = {
     "linear_act": check_linear_act,
