@@ -89,19 +89,43 @@ def timing(label):
         "ops_ms": {k: round(v[1], 3) for k, v in sorted(rows.items(), key=lambda kv_: -kv_[1][1])}}
 
 
+# options: C-ABI switches (opp_set_option) except "colmax", a host-flow switch of the model
+# (column maxima of conf from the first conf pass instead of a second GEMM pass).  Every config
+# starts from the defaults; its label lists the options it turns on.
+EXPERIMENTAL_CHECK = {"upsample_rows": "upsample_rows", "conv1_px4": "conv1_px4", "colmax": "sim_colmax"}
+DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0}
+
+
+def apply(cfg):
+    for k, v in {**DEFAULTS, **cfg}.items():
+        if k == "colmax":
+            try:
+                parity.cuda_model().coarse_colmax = bool(v)
+            except RuntimeError:   # no CUDA device (dry run of the script logic)
+                pass
+        else:
+            _lib.set_option(k, v)
+
+
 first = True
 for cfg in configs:
-    label = ",".join(f"{k}={v}" for k, v in cfg.items()) or "default"
-    for k, v in cfg.items():
-        _lib.set_option(k, v)
+    label = ",".join(f"{k}={v}" for k, v in cfg.items() if v) or "default"
     if first:   # the tcgen05 epilogues do not depend on the runtime options
+        apply({})
         for name in ("linear_ln", "conv", "linear_act", "linear_q", "sim"):
             guarded(name, kernel_checks.CHECKS[name])
+        guarded("conv1_ragged", kernel_checks.EXPERIMENTAL["conv1_ragged"])
         first = False
+    for k, v in cfg.items():
+        if v and k in EXPERIMENTAL_CHECK:   # these set and restore their own option
+            guarded(f"{EXPERIMENTAL_CHECK[k]}[{label}]", kernel_checks.EXPERIMENTAL[EXPERIMENTAL_CHECK[k]])
+    apply(cfg)
     guarded(f"kv_state[{label}]", kernel_checks.check_kv_state)
     guarded(f"conv1[{label}]", kernel_checks.CHECKS["conv1"])
+    guarded(f"upsample[{label}]", kernel_checks.CHECKS["upsample"])
     guarded(f"golden[{label}]", lambda label=label: golden(label))
     guarded(f"timing[{label}]", lambda label=label: timing(label))
+apply({})
 
 res["seconds"] = round(time.time() - t_start, 1)
 os.makedirs(os.path.join(ROOT, "gpurun_out", "variants"), exist_ok=True)
