@@ -162,6 +162,15 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
                  int own_is_pt, float* conf, float* part_val, int* part_idx, int batches,
                  int rows, int cols, int k, float scale, int split, opp_stream_t stream);
 
+/* opp_sim_lse for rows = 3D points that also produces the COLUMN statistics (saves the second lse
+ * pass): col_m/col_s fp32 [B][ceil(rows/32)][cols] = per 32-row group (max, sum exp(x - max)) of
+ * every column; opp_lse_col_finalize merges the groups into lse[b][s] = logsumexp_l sim[b, l, s]. */
+int opp_sim_lse_cols(const void* a, const void* b, float* part_m, float* part_s, float* col_m,
+                     float* col_s, int batches, int rows, int cols, int k, float scale, int split,
+                     opp_stream_t stream);
+int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
+                         int cols, opp_stream_t stream);
+
 /* opp_sim_conf for rows = 3D points with the column maxima folded in (saves the second conf pass):
  * colmax uint32 [B][cols] receives the float bits of max_l conf[b, l, s] (zeroed inside, then
  * atomicMax per 32-row group; conf >= 0 so the bits order like the values). */

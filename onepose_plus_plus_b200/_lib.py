@@ -37,6 +37,8 @@ SIGNATURES = {
     "opp_sim_lse": [P, P, P, P, I, I, I, I, F, I, P],
     "opp_lse_finalize": [P, P, P, L, I, P],
     "opp_sim_conf": [P, P, P, P, I, P, P, P, I, I, I, I, F, I, P],
+    "opp_sim_lse_cols": [P, P, P, P, P, P, I, I, I, I, F, I, P],
+    "opp_lse_col_finalize": [P, P, P, I, I, I, P],
     "opp_sim_conf_colmax": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     "opp_best_finalize": [P, P, P, P, L, I, P],
     "opp_match_select": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, P],

@@ -391,6 +391,18 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
   return launch<A_ROWS, EpiConf>(maps, s, ep, (cudaStream_t)stream);
 }
 
+int opp_sim_lse_cols(const void* a, const void* b, float* part_m, float* part_s, float* col_m,
+                     float* col_s, int batches, int rows, int cols, int k, float scale, int split,
+                     opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
+  if (rc) return rc;
+  OPP_REQUIRE(part_m && part_s && col_m && col_s, "null pointer");
+  EpiLseCol::Params ep{part_m, part_s, scale, col_m, col_s, (rows + 31) / 32};
+  return launch<A_ROWS, EpiLseCol>(maps, s, ep, (cudaStream_t)stream);
+}
+
 int opp_sim_conf_colmax(const void* a, const void* b, const float* lse_own, const float* lse_other,
                         float* conf, float* part_val, int* part_idx, unsigned* colmax, int batches,
                         int rows, int cols, int k, float scale, int split, opp_stream_t stream) {

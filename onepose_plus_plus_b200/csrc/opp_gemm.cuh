@@ -685,6 +685,80 @@ struct EpiConf {
   }
 };
 
+// lse pass with the COLUMN statistics folded in (replaces the second lse pass): rows are 3D points.
+// Row partials as in EpiLse; in addition every warp reduces each column of its 32x32 chunk over
+// its 32 rows with two butterflies (max, then sum of exp(x - column max of these 32 rows)) and
+// writes the pair to  col_m / col_s [batch][row group][n_total]  (row group = 32 rows; coalesced:
+// lane j owns column j).  opp_lse_col_finalize merges the row groups.
+struct EpiLseCol {
+  static constexpr int kGroups = OPP_ROW_GROUPS;   // row partial slot = kGroups*n_tile + group
+  struct Params {
+    float* part_m;
+    float* part_s;
+    float scale;
+    float* col_m;   // [batches][row_groups][n_total]
+    float* col_s;
+    int row_groups; // ceil(rows / 32)
+  };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    const int lane = threadIdx.x & 31;
+    const int rg = c.m_tile * 4 + c.q;   // 32-row group of this warp inside the batch
+    const bool rg_ok = rg < p.row_groups;
+    const long long cbase = ((long long)c.b * p.row_groups + rg) * s.n_total + c.n0;
+    float m = -INFINITY;
+    tmem_foreach32_lean(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+      float t[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] = (c.valid && col + j < c.ncols) ? v[j] * p.scale : -INFINITY;
+        m = fmaxf(m, v[j]);
+        t[j] = v[j];
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+          const float keep = up ? t[o + k] : t[k];
+          const float send = up ? t[k] : t[o + k];
+          t[k] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, o));
+        }
+      }
+      const float cm = t[0];   // max of column col + lane over this warp's valid rows (-inf: none)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float cmj = __shfl_sync(0xffffffffu, cm, j);
+        t[j] = v[j] == -INFINITY ? 0.f : fast_exp(v[j] - cmj);
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int k = 0; k < o; ++k) {
+          const float keep = up ? t[o + k] : t[k];
+          const float send = up ? t[k] : t[o + k];
+          t[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      if (rg_ok && col + lane < c.ncols) {
+        p.col_m[cbase + col + lane] = cm;
+        p.col_s[cbase + col + lane] = t[0];
+      }
+    });
+    float sum = 0.f;
+    tmem_foreach32_lean(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col + j < c.ncols) sum += fast_exp(v[j] * p.scale - m);
+    });
+    if (c.valid) {
+      p.part_m[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = m;
+      p.part_s[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = sum;
+    }
+  }
+};
+
 // conf pass with the column maxima folded in (replaces the second conf pass): rows are 3D points,
 // conf is stored as in EpiConf, and for every 32x32 chunk the warp reduces each COLUMN over its 32
 // rows with a butterfly (at offset o a lane keeps one half of its 2o values and exchanges the other

@@ -846,6 +846,25 @@ __global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* _
   lse[r] = m + logf(s);
 }
 
+// column side of opp_sim_lse_cols: lse[b][s] = logsumexp over the row groups of (col_m, col_s)
+__global__ void lse_col_finalize_kernel(const float* __restrict__ cm, const float* __restrict__ cs,
+                                        float* __restrict__ lse, int batches, int groups, int cols) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)batches * cols) return;
+  const int b = (int)(idx / cols);
+  const int sidx = (int)(idx - (long long)b * cols);
+  const float* pm = cm + (long long)b * groups * cols + sidx;
+  const float* ps = cs + (long long)b * groups * cols + sidx;
+  float m = -INFINITY;
+  for (int g = 0; g < groups; ++g) m = fmaxf(m, pm[(long long)g * cols]);
+  float sum = 0.f;
+  for (int g = 0; g < groups; ++g) {
+    const float pg = pm[(long long)g * cols];
+    if (pg != -INFINITY) sum += ps[(long long)g * cols] * expf(pg - m);
+  }
+  lse[idx] = m + logf(sum);
+}
+
 __global__ void best_finalize_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
                                      float* __restrict__ bv, int* __restrict__ bi, long long rows,
                                      int tiles) {
@@ -1429,6 +1448,16 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
   OPP_REQUIRE(part_m && part_s && lse, "null pointer");
   lse_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       part_m, part_s, lse, rows, tiles);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
+                         int cols, opp_stream_t stream) {
+  OPP_REQUIRE(col_m && col_s && lse && batches > 0 && groups > 0 && cols > 0, "bad lse_col_finalize arguments");
+  const long long n = (long long)batches * cols;
+  lse_col_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      col_m, col_s, lse, batches, groups, cols);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -274,6 +274,8 @@ class OnePosePlus_model(nn.Module):
         # experimental (not yet validated on a GPU, off by default): take the column maxima of
         # conf from the first conf pass (warp butterfly + atomicMax) instead of a second GEMM pass
         self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "0") == "1"
+        # same status: column log-sum-exp from the first lse pass (two warp butterflies per chunk)
+        self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "0") == "1"
 
     @property
     def split(self):
@@ -488,8 +490,14 @@ class OnePosePlus_model(nn.Module):
         ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
         lse_pt = self._buf("lse_pt", (B, N), f32, dev)
         lse_px = self._buf("lse_px", (B, S), f32, dev)
-        ops.sim_lse(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, split)
-        ops.sim_lse(q2, d3, B, S, N, 256, scale, pm_px, ps_px, lse_px, split)
+        if self.coarse_lse_cols:
+            groups = (N + 31) // 32
+            col_m = self._buf("lse_col_m", (B, groups, S), f32, dev)
+            col_s = self._buf("lse_col_s", (B, groups, S), f32, dev)
+            ops.sim_lse_cols(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, col_m, col_s, lse_px, split)
+        else:
+            ops.sim_lse(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, split)
+            ops.sim_lse(q2, d3, B, S, N, 256, scale, pm_px, ps_px, lse_px, split)
         conf = torch.empty((B, N, S), dtype=f32, device=dev)  # owned by the caller's dict
         pi_pt = self._buf("pi_pt", (B * N, ts), i32, dev)
         pi_px = self._buf("pi_px", (B * S, tl), i32, dev)

@@ -139,6 +139,17 @@ def sim_conf(a, b, lse_own, lse_other, own_is_pt, conf, batches, rows, cols, k, 
          batches * rows, tiles, stream())
 
 
+def sim_lse_cols(a, b, batches, rows, cols, k, scale, part_m, part_s, lse_rows, col_m, col_s, lse_cols,
+                 split):
+    """lse over columns for every row (as sim_lse) AND lse over rows for every column, one GEMM pass."""
+    tiles = sim_tiles(cols)
+    groups = (rows + 31) // 32
+    call("opp_sim_lse_cols", ptr(a), ptr(b), ptr(part_m), ptr(part_s), ptr(col_m), ptr(col_s), batches,
+         rows, cols, k, float(scale), int(split), stream())
+    call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse_rows), batches * rows, tiles, stream())
+    call("opp_lse_col_finalize", ptr(col_m), ptr(col_s), ptr(lse_cols), batches, groups, cols, stream())
+
+
 def sim_conf_colmax(a, b, lse_own, lse_other, conf, batches, rows, cols, k, scale, part_val, part_idx,
                     best_val, best_idx, colmax, split):
     """conf pass over rows = 3D points that also leaves max_l conf[b, l, s] (float bits) in colmax."""

@@ -2,6 +2,7 @@
 option set per experimental feature) and decides feature by feature from the per-op times:
   upsample_rows -> opp_upsample2x_add      conv1_px4 -> opp_conv1_7x7
   colmax        -> opp_sim_conf + opp_sim_conf_colmax + opp_best_finalize + opp_match_select(_colmax)
+  lse_cols      -> opp_sim_lse + opp_sim_lse_cols + opp_lse_finalize + opp_lse_col_finalize
 Prints shell assignments: `export OPP_UPSAMPLE_ROWS=.. OPP_CONV1_PX4=.. OPP_B200_COLMAX=..`."""
 import json
 import os
@@ -19,7 +20,9 @@ base = r["timing"].get("default", {}).get("ops_ms")
 FEATURES = {"upsample_rows": (["opp_upsample2x_add"], "upsample_rows", "OPP_UPSAMPLE_ROWS"),
             "conv1_px4": (["opp_conv1_7x7"], "conv1_px4", "OPP_CONV1_PX4"),
             "colmax": (["opp_sim_conf", "opp_sim_conf_colmax", "opp_best_finalize", "opp_match_select",
-                        "opp_match_select_colmax"], "sim_colmax", "OPP_B200_COLMAX")}
+                        "opp_match_select_colmax"], "sim_colmax", "OPP_B200_COLMAX"),
+            "lse_cols": (["opp_sim_lse", "opp_sim_lse_cols", "opp_lse_finalize", "opp_lse_col_finalize"],
+                         "sim_lse_cols", "OPP_B200_LSECOLS")}
 out = {}
 for opt, (ops_, check, env) in FEATURES.items():
     label = f"{opt}=1"

@@ -89,18 +89,20 @@ def timing(label):
         "ops_ms": {k: round(v[1], 3) for k, v in sorted(rows.items(), key=lambda kv_: -kv_[1][1])}}
 
 
-# options: C-ABI switches (opp_set_option) except "colmax", a host-flow switch of the model
-# (column maxima of conf from the first conf pass instead of a second GEMM pass).  Every config
+# options: C-ABI switches (opp_set_option) except "colmax" / "lse_cols", host-flow switches of the
+# model (column maxima of conf / column log-sum-exp from the first pass instead of a second GEMM).  Every config
 # starts from the defaults; its label lists the options it turns on.
-EXPERIMENTAL_CHECK = {"upsample_rows": "upsample_rows", "conv1_px4": "conv1_px4", "colmax": "sim_colmax"}
-DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0}
+EXPERIMENTAL_CHECK = {"upsample_rows": "upsample_rows", "conv1_px4": "conv1_px4", "colmax": "sim_colmax",
+                      "lse_cols": "sim_lse_cols"}
+DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0, "lse_cols": 0}
+MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols"}
 
 
 def apply(cfg):
     for k, v in {**DEFAULTS, **cfg}.items():
-        if k == "colmax":
+        if k in MODEL_ATTR:
             try:
-                parity.cuda_model().coarse_colmax = bool(v)
+                setattr(parity.cuda_model(), MODEL_ATTR[k], bool(v))
             except RuntimeError:   # no CUDA device (dry run of the script logic)
                 pass
         else:

@@ -495,6 +495,29 @@ def check_sim_colmax():
             assert torch.equal(sel, mutual.any(2)), "mutual-nearest selection differs"
 
 
+def check_sim_lse_cols():
+    for split in (0, 1):
+        for (B, L, S, K) in [(2, 700, 520, 256), (1, 300, 100, 256), (1, 5000, 4096, 256)]:
+            af = _rand(B, L, K, scale=0.9, seed=1)
+            bf = _rand(B, S, K, scale=0.9, seed=2)
+            a, b = _planes(af, split), _planes(bf, split)
+            scale = 1.0 / (256 * 0.0801)
+            sim = (torch.einsum("blk,bsk->bls", _q(af, split).double(), _q(bf, split).double()) * scale)
+            ts = _lib.load().opp_sim_tiles(S)
+            groups = (L + 31) // 32
+            lse_rows = torch.full((B, L), float("nan"), device=DEV)
+            lse_cols = torch.full((B, S), float("nan"), device=DEV)
+            col_m = torch.full((B, groups, S), float("nan"), device=DEV)
+            col_s = torch.full((B, groups, S), float("nan"), device=DEV)
+            ops.sim_lse_cols(a, b, B, L, S, K, scale, torch.empty(B * L, ts, device=DEV),
+                             torch.empty(B * L, ts, device=DEV), lse_rows, col_m, col_s, lse_cols, split)
+            torch.cuda.synchronize()
+            assert not torch.isnan(col_m).any() and not torch.isnan(col_s).any(), "unwritten column partials"
+            _close(f"sim_lse_cols split={split} rows B={B} L={L} S={S}", lse_rows,
+                   torch.logsumexp(sim, 2).float(), 1e-5, 1e-4)
+            _close("sim_lse_cols cols", lse_cols, torch.logsumexp(sim, 1).float(), 1e-5, 1e-4)
+
+
 def check_upsample_rows():
     _lib.set_option("upsample_rows", 1)
     try:
@@ -518,7 +541,7 @@ def check_conv1_ragged():
         _conv1_case(split, 1, 72, 200, 128)
 
 
-EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "upsample_rows": check_upsample_rows,
+EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "sim_lse_cols": check_sim_lse_cols, "upsample_rows": check_upsample_rows,
                 "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged}
 
 CHECKS = {
