@@ -43,6 +43,8 @@ int opp_num_sms(void);
  *   "conv1_px4":    1 = opp_conv1_7x7 computes 4 adjacent output pixels per thread (one pair of
  *                   weight loads per 32 FMAs); takes precedence over "conv1_staged"
  *                   (initial value: $OPP_CONV1_PX4, else 0 — not yet validated on a GPU)
+ *   "fine_attn_vec": 1 = opp_fine_attention moves its rows with 16-byte accesses
+ *                   (initial value: $OPP_FINE_ATTN_VEC, else 0 — not yet validated on a GPU)
  *   "upsample_rows": 1 = opp_upsample2x_add uses the division-free row-mapped kernel
  *                   (initial value: $OPP_UPSAMPLE_ROWS, else 0 — not yet validated on a GPU)
  * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */

@@ -1167,6 +1167,87 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
   }
 }
 
+// Same attention with 16-byte global accesses (opp_set_option("fine_attn_vec") /
+// $OPP_FINE_ATTN_VEC; not yet validated on a GPU): the kernel above moves its 26 x 384 inputs and
+// 26 x 128 outputs with 2-byte loads/stores (about 200 memory instructions per thread for 40 KB
+// per match, ~9x off the HBM time); here rows are fetched as uint4 and the results are packed
+// through shared memory.  The arithmetic is the same code.
+__global__ void __launch_bounds__(128) fine_attention_vec_kernel(const __half* __restrict__ qkv,
+                                                                 __half* __restrict__ msg, int cross,
+                                                                 float eps, int lo_off_in,
+                                                                 int lo_off_out) {
+  __shared__ __align__(16) float q_s[26][128];
+  __shared__ __align__(16) float k_s[26][128];
+  __shared__ __align__(16) float v_s[26][128];
+  const int m = blockIdx.x, c = threadIdx.x;
+  const int ldi = lo_off_in ? 768 : 384;
+  const __half* src = qkv + (long long)m * 26 * ldi;
+  for (int i = c; i < 26 * 48; i += 128) {
+    const int t = i / 48, sg = i - t * 48;
+    float f[8];
+    load_split8(src + (long long)t * ldi, sg * 8, f, lo_off_in);
+    const int col = sg * 8;   // 0..383: q | k | v, 128 each
+    float* dstrow = col < 128 ? &q_s[t][col] : (col < 256 ? &k_s[t][col - 128] : &v_s[t][col - 256]);
+    reinterpret_cast<float4*>(dstrow)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dstrow)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+  __syncthreads();
+  const int h = c >> 4, v = c & 15;
+  float col[16];
+#pragma unroll
+  for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
+  float ksum_c = 0.f;
+  for (int t = 1; t < 26; ++t) {
+    const float vv = v_s[t][c];
+#pragma unroll
+    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(k_s[t][h * 16 + dd], vv, col[dd]);
+    ksum_c += k_s[t][c];
+  }
+  __syncthreads();
+  float (*kv2)[16][16] = reinterpret_cast<float (*)[16][16]>(&v_s[1][0]);
+  float* ks2 = &k_s[1][0];
+#pragma unroll
+  for (int dd = 0; dd < 16; ++dd) kv2[h][dd][v] = col[dd];
+  ks2[c] = ksum_c;
+  __syncthreads();
+  float o[26];
+#pragma unroll
+  for (int t = 0; t < 26; ++t) {
+    const bool use_window = cross ? (t == 0) : (t > 0);
+    float num = 0.f, den = 0.f;
+    if (use_window) {
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd) {
+        const float q = q_s[t][h * 16 + dd];
+        num = fmaf(q, kv2[h][dd][v], num);
+        den = fmaf(q, ks2[h * 16 + dd], den);
+      }
+    } else {
+      float qk = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd) qk = fmaf(q_s[t][h * 16 + dd], k_s[0][h * 16 + dd], qk);
+      num = qk * v_s[0][c];
+      den = qk;
+    }
+    o[t] = num / (den + eps);
+  }
+  __syncthreads();   // every read of q_s is done: reuse it as the output tile
+#pragma unroll
+  for (int t = 0; t < 26; ++t) q_s[t][c] = o[t];
+  __syncthreads();
+  const int ldo = lo_off_out ? 256 : 128;
+  __half* dst = msg + (long long)m * 26 * ldo;
+  for (int i = c; i < 26 * 16; i += 128) {
+    const int t = i >> 4, sg = i & 15;
+    float f[8];
+    const float4 a = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[0];
+    const float4 b = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    store_split8(dst + (long long)t * ldo, sg * 8, f, lo_off_out);
+  }
+}
+
 // =============================================================================================
 // fine matching   (utils/fine_matching.py:78-110): one warp per match
 // =============================================================================================
@@ -1355,6 +1436,18 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
 
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 
+#ifndef OPP_FINE_ATTN_VEC_DEFAULT
+#define OPP_FINE_ATTN_VEC_DEFAULT 0
+#endif
+static int g_fine_attn_vec = -1;
+static int fine_attn_vec_enabled() {
+  if (g_fine_attn_vec < 0) {
+    const char* e = getenv("OPP_FINE_ATTN_VEC");
+    g_fine_attn_vec = e ? atoi(e) : OPP_FINE_ATTN_VEC_DEFAULT;
+  }
+  return g_fine_attn_vec;
+}
+
 // $OPP_KV_MMA (or opp_set_option("kv_mma", v)) selects the linear-attention state kernel:
 // 1 = mma.sync tensor-core stream, 0 = SIMT (fp32 FMA).  Both write the same partial layout.
 #ifndef OPP_KV_MMA_DEFAULT
@@ -1383,6 +1476,10 @@ int opp_set_option(const char* name, int value) {
     g_conv1_px4 = value ? 1 : 0;
     return OPP_OK;
   }
+  if (strcmp(name, "fine_attn_vec") == 0) {
+    g_fine_attn_vec = value ? 1 : 0;
+    return OPP_OK;
+  }
   if (strcmp(name, "upsample_rows") == 0) {
     g_upsample_rows = value ? 1 : 0;
     return OPP_OK;
@@ -1396,6 +1493,7 @@ int opp_get_option(const char* name) {
   if (name && strcmp(name, "conv1_staged") == 0) return conv1_staged_enabled();
   if (name && strcmp(name, "upsample_rows") == 0) return upsample_rows_enabled();
   if (name && strcmp(name, "conv1_px4") == 0) return conv1_px4_enabled();
+  if (name && strcmp(name, "fine_attn_vec") == 0) return fine_attn_vec_enabled();
   return -1;
 }
 
@@ -1527,9 +1625,14 @@ int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, 
                        opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(qkv && msg, "null pointer");
-  fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
-                                                             cross, eps, split ? 384 : 0,
-                                                             split ? 128 : 0);
+  if (fine_attn_vec_enabled())
+    fine_attention_vec_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
+                                                                   cross, eps, split ? 384 : 0,
+                                                                   split ? 128 : 0);
+  else
+    fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
+                                                               cross, eps, split ? 384 : 0,
+                                                               split ? 128 : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -1,6 +1,6 @@
 """Reads gpurun_out/variants/probe.json (scripts/variant_probe.py run on the default build with one
 option set per experimental feature) and decides feature by feature from the per-op times:
-  upsample_rows -> opp_upsample2x_add      conv1_px4 -> opp_conv1_7x7
+  upsample_rows -> opp_upsample2x_add      conv1_px4 -> opp_conv1_7x7      fine_attn_vec -> opp_fine_attention
   colmax        -> opp_sim_conf + opp_sim_conf_colmax + opp_best_finalize + opp_match_select(_colmax)
   lse_cols      -> opp_sim_lse + opp_sim_lse_cols + opp_lse_finalize + opp_lse_col_finalize
 Prints shell assignments: `export OPP_UPSAMPLE_ROWS=.. OPP_CONV1_PX4=.. OPP_B200_COLMAX=..`."""
@@ -21,6 +21,7 @@ FEATURES = {"upsample_rows": (["opp_upsample2x_add"], "upsample_rows", "OPP_UPSA
             "conv1_px4": (["opp_conv1_7x7"], "conv1_px4", "OPP_CONV1_PX4"),
             "colmax": (["opp_sim_conf", "opp_sim_conf_colmax", "opp_best_finalize", "opp_match_select",
                         "opp_match_select_colmax"], "sim_colmax", "OPP_B200_COLMAX"),
+            "fine_attn_vec": (["opp_fine_attention"], "fine_attn_vec", "OPP_FINE_ATTN_VEC"),
             "lse_cols": (["opp_sim_lse", "opp_sim_lse_cols", "opp_lse_finalize", "opp_lse_col_finalize"],
                          "sim_lse_cols", "OPP_B200_LSECOLS")}
 out = {}

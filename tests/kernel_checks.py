@@ -536,13 +536,22 @@ def check_conv1_px4():
         _lib.set_option("conv1_px4", 0)
 
 
+def check_fine_attn_vec():
+    _lib.set_option("fine_attn_vec", 1)
+    try:
+        check_fine()
+    finally:
+        _lib.set_option("fine_attn_vec", 0)
+
+
 def check_conv1_ragged():
     for split in (0, 1):
         _conv1_case(split, 1, 72, 200, 128)
 
 
 EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "sim_lse_cols": check_sim_lse_cols, "upsample_rows": check_upsample_rows,
-                "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged}
+                "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged,
+                "fine_attn_vec": check_fine_attn_vec}
 
 CHECKS = {
     "linear_act": check_linear_act,

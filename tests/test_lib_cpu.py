@@ -41,14 +41,15 @@ def test_version_and_tiles_without_gpu():
 
 def test_runtime_options_roundtrip():
     """opp_set_option / opp_get_option (include/opp_b200.h): known names toggle, unknown names fail."""
-    for name in ("kv_mma", "conv1_staged", "upsample_rows"):
+    for name in ("kv_mma", "conv1_staged", "upsample_rows", "conv1_px4", "fine_attn_vec"):
         before = _lib.get_option(name)
         assert before in (0, 1)
         _lib.set_option(name, 1 - before)
         assert _lib.get_option(name) == 1 - before
         _lib.set_option(name, before)
     assert _lib.get_option("kv_mma") == 1 and _lib.get_option("conv1_staged") == 1   # validated defaults
-    assert _lib.get_option("upsample_rows") == 0                                       # not validated yet
+    for name in ("upsample_rows", "conv1_px4", "fine_attn_vec"):                        # not validated yet
+        assert _lib.get_option(name) == 0
     with pytest.raises(ValueError):
         _lib.set_option("no_such_option", 1)
     assert _lib.get_option("no_such_option") == -1
