@@ -124,3 +124,21 @@ def test_shared_bank_views_match_materialised_bank():
     torch.cuda.synchronize()
     for k in ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f", "conf_matrix"):
         assert torch.equal(a[k], shared[k]), k
+
+
+def test_alternate_kernels_behind_options():
+    """The SIMT kv_partial and the unstaged conv1 kernels stay in the library behind
+    opp_set_option: they must keep passing their kernel checks and the golden end-to-end parity."""
+    from onepose_plus_plus_b200 import _lib
+    from tests import kernel_checks
+    case = golden_io.cases()[0]
+    data, z = golden_io.load(case)
+    for name, check in (("kv_mma", kernel_checks.check_kv_state), ("conv1_staged", kernel_checks.check_conv1)):
+        default = _lib.get_option(name)
+        try:
+            _lib.set_option(name, 1 - default)
+            check()
+            got = parity.run_cuda(data)
+            parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
+        finally:
+            _lib.set_option(name, default)
