@@ -67,9 +67,12 @@ def test_random_workload_has_no_matches():
 
 
 @pytest.mark.skipif(not ref_shims.available(), reason="/root/reference only exists in the build container")
-def test_oracle_matches_reference_live():
+@pytest.mark.parametrize("shape", [(96, 128, 300, 120, 2), (512, 512, 5000, 3000, 1)],
+                         ids=["small_b2", "baseline_512_n5000"])
+def test_oracle_matches_reference_live(shape):
     sd = weights()
-    data, meta = workload.planted_workload(sd, 96, 128, 300, 120, batch=2, seed=5)
+    h, w, n, npl, batch = shape
+    data, meta = workload.planted_workload(sd, h, w, n, npl, batch=batch, seed=5)
     ref = ref_shims.build_reference_model(sd, oracle.DEFAULT_CONFIG)
     d_ref = {k: v.clone() for k, v in data.items()}
     with torch.no_grad():
