@@ -47,6 +47,11 @@
 #ifndef OPP_CONF_STAGED
 #define OPP_CONF_STAGED 1
 #endif
+// BasicBlock residual of the conv epilogue through the transpose buffer (coalesced) instead of
+// row-per-thread 16 B loads — built for the next GPU session, not yet validated
+#ifndef OPP_CONV_RESID_STAGED
+#define OPP_CONV_RESID_STAGED 0
+#endif
 // positional-encoding add of the token epilogue with 16 B loads instead of scalar ones
 #ifndef OPP_PE_VEC
 #define OPP_PE_VEC 1
@@ -516,6 +521,14 @@ struct EpiConv {
     epi_sync(c);
     for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
     epi_sync(c);
+#if OPP_CONV_RESID_STAGED
+    // residual through the transpose buffer (coalesced: 8 rows x 64 B per load instruction), issued
+    // one 32-column chunk ahead of its use; warp-uniform, row validity is per staged row
+    const bool has_res = p.resid != nullptr;
+    StagedRows pre;
+    if (has_res && c.col_first < c.ncols)
+      staged_load_issue(c, p.resid, p.ld, p.out_lo, c.n0 + c.col_first, c.ncols - c.col_first, pre);
+#else
     // residual: row-per-thread 16 B loads, issued one 32-column chunk ahead of their use
     const bool has_res = p.resid != nullptr && c.valid;
     uint4 rq[8];
@@ -530,6 +543,7 @@ struct EpiConv {
       }
     };
     if (has_res && c.col_first < c.ncols) issue(c.col_first);
+#endif
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
@@ -541,6 +555,14 @@ struct EpiConv {
         v[4 * g + 2] += __uint_as_float(bq.z);
         v[4 * g + 3] += __uint_as_float(bq.w);
       }
+#if OPP_CONV_RESID_STAGED
+      if (has_res) {
+        staged_load_add(c, p.out_lo, pre, v);
+        if (col + c.col_step < c.ncols)
+          staged_load_issue(c, p.resid, p.ld, p.out_lo, c.n0 + col + c.col_step,
+                            c.ncols - col - c.col_step, pre);
+      }
+#else
       if (has_res) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
@@ -554,6 +576,7 @@ struct EpiConv {
         }
         if (col + c.col_step < c.ncols) issue(col + c.col_step);
       }
+#endif
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);

@@ -9,6 +9,12 @@ V=gpurun_out/variants
 timeout 200 python scripts/variant_probe.py probe "" upsample_rows=1 conv1_px4=1 colmax=1 lse_cols=1 fine_attn_vec=1 \
   > $V/probe.log 2>&1
 echo "probe exit=$?"
+# compile-time candidate (scripts/build_variants.sh): same probe with default options
+if [ -f variants/libopp_residstaged.so ]; then
+  OPP_B200_LIB=$PWD/variants/libopp_residstaged.so timeout 100 python scripts/variant_probe.py residstaged "" \
+    > $V/residstaged.log 2>&1
+  echo "residstaged exit=$?"
+fi
 python scripts/pick_variant.py > $V/best.env 2> $V/pick.log
 cat $V/pick.log $V/best.env
 [ -s $V/best.env ] || exit 1

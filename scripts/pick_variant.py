@@ -35,4 +35,16 @@ for opt, (ops_, check, env) in FEATURES.items():
         print(f"# {opt}: {tb:.3f} -> {tn:.3f} ms", file=sys.stderr)
         on = int(tn < 0.97 * tb)
     out[env] = on
+# compile-time candidate: the residual-staged conv epilogue (probed with default options)
+try:
+    rs = json.loads(open(os.path.join(ROOT, "gpurun_out", "variants", "residstaged.json")).read())
+    t = rs["timing"].get("default", {}).get("ops_ms")
+    good = all(v == "ok" for v in rs["checks"].values())
+    if base and t and good:
+        print(f"# conv2d default -> resid-staged: {base['opp_conv2d_nhwc']:.3f} -> {t['opp_conv2d_nhwc']:.3f} ms",
+              file=sys.stderr)
+        if t["opp_conv2d_nhwc"] < 0.985 * base["opp_conv2d_nhwc"]:
+            out["OPP_B200_LIB"] = rs["lib"]
+except (OSError, ValueError, KeyError):
+    pass
 print("export " + " ".join(f"{k}={v}" for k, v in out.items()))
