@@ -113,3 +113,19 @@ def test_bn_folding_and_planes_roundtrip():
     got = ops.from_planes(w, 1)[:196]
     assert torch.allclose(got, ref, atol=1e-6)
     assert got.shape[1] == 9 * 128 and ops.from_planes(w, 1)[196:].abs().max() == 0
+
+
+def test_gpu_validated_kernels_are_unchanged():
+    """profiles/r1_validated_sass.txt fingerprints (sha256 of the SASS) the kernels that passed
+    `pytest -m gpu`, smoke() and the bench on a B200.  An edit that changes one of them must be
+    re-validated on a GPU and the file rewritten (`python scripts/sass_hash.py write ...`); new
+    kernels behind off-by-default switches do not count."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_hash.py"), "check",
+                        os.path.join(ROOT, "profiles", "r1_validated_sass.txt")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
