@@ -129,3 +129,43 @@ def test_gpu_validated_kernels_are_unchanged():
                         os.path.join(ROOT, "profiles", "r1_validated_sass.txt")],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+def test_coarse_matching_host_flow(monkeypatch):
+    """Stage sequencing of OnePosePlus_model._coarse_matching with the kernels stubbed out: the
+    default flow is lse x2 -> conf x2 -> match_select; the one-pass switches replace exactly the
+    passes they claim to, and every call binds against the real wrapper's signature."""
+    import inspect
+    from onepose_plus_plus_b200 import ops
+    calls = []
+
+    def stub(name):
+        sig = inspect.signature(getattr(ops, name))
+
+        def f(*a, **k):
+            sig.bind(*a, **k)
+            calls.append(name)
+            if name.startswith("match_select"):
+                a[-1].zero_()   # match count
+        return f
+
+    for n in ("sim_lse", "sim_conf", "match_select", "sim_lse_cols", "sim_conf_colmax", "match_select_colmax"):
+        monkeypatch.setattr(ops, n, stub(n))
+    monkeypatch.setattr(ops, "sim_tiles", lambda c: 2 * ((c + 255) // 256))
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
+    assert not m.coarse_colmax and not m.coarse_lse_cols   # unvalidated paths are opt-in
+    B, N, hc, wc = 2, 300, 12, 16
+    q2 = torch.zeros(B, hc * wc, 512, dtype=torch.half)
+    d3 = torch.zeros(B, N, 512, dtype=torch.half)
+    expect = {(False, False): ["sim_lse", "sim_lse", "sim_conf", "sim_conf", "match_select"],
+              (True, False): ["sim_lse", "sim_lse", "sim_conf_colmax", "match_select_colmax"],
+              (False, True): ["sim_lse_cols", "sim_conf", "sim_conf", "match_select"],
+              (True, True): ["sim_lse_cols", "sim_conf_colmax", "match_select_colmax"]}
+    for flags, want in expect.items():
+        m.coarse_colmax, m.coarse_lse_cols = flags
+        calls.clear()
+        data = {"keypoints3d": torch.zeros(B, N, 3), "query_image_scale": torch.ones(B, 2),
+                "q_hw_i": torch.Size((96, 128))}
+        M, _ = m._coarse_matching(q2, d3, data, B, N, hc, wc)
+        assert M == 0 and calls == want
+        assert data["conf_matrix"].shape == (B, N, hc * wc) and data["b_ids"].numel() == 0
