@@ -169,3 +169,64 @@ def test_coarse_matching_host_flow(monkeypatch):
         M, _ = m._coarse_matching(q2, d3, data, B, N, hc, wc)
         assert M == 0 and calls == want
         assert data["conf_matrix"].shape == (B, N, hc * wc) and data["b_ids"].numel() == 0
+
+
+def test_full_forward_host_flow(monkeypatch):
+    """Every stage of the forward with all kernels stubbed (CPU tensors): checks the host-side
+    sequencing, buffer shapes and wrapper signatures of backbone -> kpt encode -> coarse transformer
+    -> coarse matching -> fine stage, and the launch count per forward the bench reports."""
+    import inspect
+    from onepose_plus_plus_b200 import ops
+    calls = []
+    returns_out = {"conv1_7x7": 3, "conv2d_nhwc": 3, "upsample2x_add": 2, "linear_act": 3, "linear_q": 3}
+
+    def stub(name):
+        sig = inspect.signature(getattr(ops, name))
+
+        def f(*a, **k):
+            bound = sig.bind(*a, **k)
+            calls.append(name)
+            if name.startswith("match_select"):
+                bound.arguments["count"].fill_(5)
+            if name in returns_out:
+                return a[returns_out[name]]
+        return f
+
+    names = [n for n, fn in inspect.getmembers(ops, inspect.isfunction)
+             if n not in ("to_planes", "from_planes", "_chk", "kv_chunks", "sim_tiles")]
+    for n in names:
+        monkeypatch.setattr(ops, n, stub(n))
+    monkeypatch.setattr(ops, "sim_tiles", lambda c: 2 * ((c + 255) // 256))
+    monkeypatch.setattr(ops, "kv_chunks", lambda s_: (s_ + 127) // 128)
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
+    m.load_state_dict(workload.synthetic_state_dict(0))
+    dev = torch.device("cpu")
+    m._plan = m._prepare(dev)
+    B, H, W, N = 2, 64, 96, 200
+    img = torch.rand(B, 1, H, W)
+    q2, fine_map, (hc, wc) = m._backbone(img)
+    assert (hc, wc) == (H // 8, W // 8) and q2.shape == (B, hc * wc, 512)
+    assert fine_map.shape == (B, H // 2, W // 2, 256)
+    assert calls.count("conv2d_nhwc") == 21 and calls.count("upsample2x_add") == 2 and calls.count("conv1_7x7") == 1
+    calls.clear()
+    d3 = torch.zeros(B, N, 512, dtype=torch.half)
+    o2, o3 = m._coarse_transformer(q2, d3, B, hc * wc, N)
+    assert o2.shape == q2.shape and o3.shape == d3.shape
+    # 6 layers x 2 sequences x (kv GEMM, kv_state, q GEMM, Mt+LN, mlp0, mlp2+LN)
+    assert calls.count("linear_act") == 24 and calls.count("linear_ln") == 24
+    assert calls.count("linear_q") == 12 and calls.count("kv_state") == 12
+    calls.clear()
+    data = {"keypoints3d": torch.zeros(B, N, 3), "query_image_scale": torch.ones(B, 2),
+            "q_hw_i": img.shape[2:], "q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3]),
+            "descriptors3d_db": torch.zeros(B, 128, N)}
+    M, img_scale = m._coarse_matching(o2, o3, data, B, N, hc, wc)
+    assert M == 5 and data["b_ids"].shape == (5,) and data["mkpts_3d_db"].shape == (5, 3)
+    calls.clear()
+    m._fine(data, fine_map, M, img_scale, wc)
+    assert data["expec_f"].shape == (5, 3) and data["mkpts_query_f"].shape == (5, 2) and data["W"] == 5
+    assert calls == ["fine_gather"] + ["linear_act", "fine_attention", "linear_ln", "linear_act", "linear_ln"] * 2 \
+        + ["fine_match"]
+    # empty-match path (fine_preprocess.py:34-37, fine_matching.py:46-55)
+    data["mkpts_query_c"] = torch.zeros(0, 2)
+    m._fine(data, fine_map, 0, img_scale, wc)
+    assert data["expec_f"].shape == (0, 3) and data["mkpts_query_f"].shape == (0, 2)
