@@ -111,6 +111,12 @@ int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const voi
                        long long rows, int n, int act, int act_cols, int split,
                        opp_stream_t stream);
 
+/* Same GEMM with split (hi|lo) operands but a single-plane fp16 output [rows][n]: for the K'/V rows
+ * of the linear-attention state, whose consumer sums over thousands of rows (built for the next
+ * GPU session; selected by $OPP_B200_KV1). */
+int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
+                            long long rows, int n, int act, int act_cols, opp_stream_t stream);
+
 /* q_proj + feature map + normaliser (transformer.py:77, linear_attention.py:45,58):
  * out = Q * v_len / (Q . ksum_head + eps), Q = elu(x @ wq^T) + 1, heads of 32 channels.
  * x fp16 [B][rows][256]; ksum fp32 [B][256]; out fp16 [B][rows][256] */

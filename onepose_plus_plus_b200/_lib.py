@@ -30,6 +30,7 @@ SIGNATURES = {
     "opp_kpt_stats": [P, P, I, I, P],
     "opp_kpt_encode": [P] * 12 + [I, I, I, P],
     "opp_linear_act_f16": [P, I, P, I, P, P, L, I, I, I, I, P],
+    "opp_linear_act_f16_out1": [P, I, P, I, P, P, L, I, I, I, P],
     "opp_linear_q_f16": [P, P, P, P, I, I, I, F, F, I, P],
     "opp_linear_ln": [P, I, P, I, P, I, P, P, F, P, P, P, I, L, I, I, P],
     "opp_kv_partial": [P, P, I, I, I, I, P],

@@ -267,6 +267,22 @@ int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const voi
   return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
 }
 
+// split operands (hi|lo, three MMAs per K-step) with a SINGLE-plane fp16 output: for tensors whose
+// consumer averages over thousands of rows (the K'/V rows of the linear-attention state), so that
+// the 2^-12 output rounding is harmless while the row is half as long in HBM.  Same kernel as
+// opp_linear_act_f16 (EpiStoreF16 with out_lo = 0).
+int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
+                            long long rows, int n, int act, int act_cols, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, 1);
+  if (rc) return rc;
+  OPP_REQUIRE(out, "null output");
+  OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
+  EpiStoreF16::Params ep{(__half*)out, (long long)n, 0, act, act_cols};
+  return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
+}
+
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
                      int rows, int d_model, float v_len, float eps, int split,
                      opp_stream_t stream) {

@@ -276,6 +276,9 @@ class OnePosePlus_model(nn.Module):
         self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "0") == "1"
         # same status: column log-sum-exp from the first lse pass (two warp butterflies per chunk)
         self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "0") == "1"
+        # same status: K'/V rows of the coarse attention state stored as ONE fp16 plane (their
+        # consumer sums over thousands of tokens; oracle experiment: conf changes by 1e-4)
+        self.kv_single_plane = os.environ.get("OPP_B200_KV1", "0") == "1"
 
     @property
     def split(self):
@@ -431,12 +434,13 @@ class OnePosePlus_model(nn.Module):
         f16 = torch.float16
         split = self.split
         pl = 2 if split else 1
-        kv16 = self._buf(tag + "kv16", (B * ls, pl * 512), f16, dev)
-        ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split)
+        kv_split = split and not self.kv_single_plane
+        kv16 = self._buf(tag + "kv16", (B * ls, (2 if kv_split else 1) * 512), f16, dev)
+        ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split, out_split=kv_split)
         part = self._buf(tag + "part", (B, ops.kv_chunks(ls), 8, 33, 32), torch.float32, dev)
         mt = self._buf(tag + "mt", (B, 256, pl * 256), f16, dev)
         ksum = self._buf(tag + "ksum", (B, 256), torch.float32, dev)
-        ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split)
+        ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split, kv_split=kv_split)
         qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
         ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split)
         msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)

@@ -77,14 +77,19 @@ def kpt_encode(kpts, desc, mlp, stats, tok, split):
          ptr(w3), ptr(b3), ptr(w4), ptr(b4), ptr(tok), B, N, int(split), stream())
 
 
-def linear_act(a0, a1, w, out, rows, act, act_cols, split):
-    """a_i fp16 [rows, planes*k_i]; w fp16 [n, planes*(k0+k1)]; out fp16 [rows, planes*n]."""
+def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None):
+    """a_i fp16 [rows, planes*k_i]; w fp16 [n, planes*(k0+k1)]; out fp16 [rows, planes*n]
+    (out_split=False with split=True: split operands, single-plane output [rows, n])."""
     _chk(a0, torch.float16, "a0")
     _chk(a1, torch.float16, "a1")
     _chk(w, torch.float16, "w")
     planes = 2 if split else 1
     k0 = a0.shape[-1] // planes
     k1 = a1.shape[-1] // planes if a1 is not None else 0
+    if split and out_split is False:
+        call("opp_linear_act_f16_out1", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
+             act_cols, stream())
+        return out
     call("opp_linear_act_f16", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
          act_cols, int(split), stream())
     return out
@@ -113,8 +118,10 @@ def kv_chunks(s):
     return _lib.load().opp_kv_chunks(s)
 
 
-def kv_state(kv16, part, merge_w, mt, ksum, batches, s, d, v_len, split):
-    call("opp_kv_partial", ptr(kv16), ptr(part), batches, s, d, int(split), stream())
+def kv_state(kv16, part, merge_w, mt, ksum, batches, s, d, v_len, split, kv_split=None):
+    """kv_split: plane mode of the kv16 rows when it differs from the mode of the mt output."""
+    kv_split = split if kv_split is None else kv_split
+    call("opp_kv_partial", ptr(kv16), ptr(part), batches, s, d, int(kv_split), stream())
     call("opp_kv_finalize", ptr(part), ptr(merge_w), ptr(mt), ptr(ksum), batches, kv_chunks(s), d,
          float(v_len), int(split), stream())
 

@@ -6,7 +6,7 @@
 # default for the adopted ones, rebuild, `python scripts/sass_diff.py` against this build.
 mkdir -p gpurun_out/variants
 V=gpurun_out/variants
-timeout 200 python scripts/variant_probe.py probe "" upsample_rows=1 conv1_px4=1 colmax=1 lse_cols=1 fine_attn_vec=1 \
+timeout 200 python scripts/variant_probe.py probe "" upsample_rows=1 conv1_px4=1 colmax=1 lse_cols=1 fine_attn_vec=1 kv1=1 \
   > $V/probe.log 2>&1
 echo "probe exit=$?"
 # compile-time candidate (scripts/build_variants.sh): same probe with default options

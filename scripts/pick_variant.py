@@ -22,6 +22,8 @@ FEATURES = {"upsample_rows": (["opp_upsample2x_add"], "upsample_rows", "OPP_UPSA
             "colmax": (["opp_sim_conf", "opp_sim_conf_colmax", "opp_best_finalize", "opp_match_select",
                         "opp_match_select_colmax"], "sim_colmax", "OPP_B200_COLMAX"),
             "fine_attn_vec": (["opp_fine_attention"], "fine_attn_vec", "OPP_FINE_ATTN_VEC"),
+            "kv1": (["opp_linear_act_f16", "opp_linear_act_f16_out1", "opp_kv_partial"], "kv_single_plane",
+                    "OPP_B200_KV1"),
             "lse_cols": (["opp_sim_lse", "opp_sim_lse_cols", "opp_lse_finalize", "opp_lse_col_finalize"],
                          "sim_lse_cols", "OPP_B200_LSECOLS")}
 out = {}

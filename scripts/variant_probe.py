@@ -93,9 +93,9 @@ def timing(label):
 # model (column maxima of conf / column log-sum-exp from the first pass instead of a second GEMM).  Every config
 # starts from the defaults; its label lists the options it turns on.
 EXPERIMENTAL_CHECK = {"upsample_rows": "upsample_rows", "conv1_px4": "conv1_px4", "colmax": "sim_colmax",
-                      "lse_cols": "sim_lse_cols", "fine_attn_vec": "fine_attn_vec"}
-DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0, "lse_cols": 0, "fine_attn_vec": 0}
-MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols"}
+                      "lse_cols": "sim_lse_cols", "fine_attn_vec": "fine_attn_vec", "kv1": "kv_single_plane"}
+DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0, "lse_cols": 0, "fine_attn_vec": 0, "kv1": 0}
+MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols", "kv1": "kv_single_plane"}
 
 
 def apply(cfg):

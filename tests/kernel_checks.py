@@ -518,6 +518,35 @@ def check_sim_lse_cols():
             _close("sim_lse_cols cols", lse_cols, torch.logsumexp(sim, 1).float(), 1e-5, 1e-4)
 
 
+def check_kv_single_plane():
+    """split operands -> single-plane K'/V rows -> KV state: opp_linear_act_f16_out1 + opp_kv_partial
+    (plain rows) + opp_kv_finalize (split mt).  Tolerances: one fp16 rounding of the rows (5e-4)
+    for the GEMM, and its average over S rows for the state."""
+    B, S, d = 2, 1000, 256
+    xf = _rand(B * S, d, seed=1)
+    wf = _rand(2 * d, d, scale=0.05, seed=2)
+    x, w = _planes(xf, 1), _planes(wf, 1)
+    kv = torch.full((B * S, 2 * d), float("nan"), device=DEV, dtype=torch.half)
+    ops.linear_act(x, None, w, kv, B * S, 2, d, True, out_split=False)
+    torch.cuda.synchronize()
+    ref = (_q(xf, 1).double() @ _q(wf, 1).double().t()).float()
+    ref[:, :d] = _elu1(ref[:, :d])
+    _close("linear_act_out1", kv, ref, 6e-4, 1e-4)
+    mw = _rand(d, d, scale=0.06, seed=3)
+    chunks = _lib.load().opp_kv_chunks(S)
+    part = torch.empty(B, chunks, 8, 33, 32, device=DEV)
+    mt = torch.empty(B, d, 2 * d, device=DEV, dtype=torch.half)
+    ksum = torch.empty(B, d, device=DEV)
+    ops.kv_state(kv, part, mw, mt, ksum, B, S, d, float(S), True, kv_split=False)
+    torch.cuda.synchronize()
+    kvq = kv.double().view(B, S, 2 * d)
+    K, V = kvq[..., :d].view(B, S, 8, 32), kvq[..., d:].view(B, S, 8, 32)
+    KV = torch.einsum("bshd,bshv->bhdv", K, V) / S
+    ref_mt = torch.einsum("chv,bhdv->bchd", mw.double().view(d, 8, 32), KV).reshape(B, d, d).float()
+    _close("kv1 ksum", ksum, K.sum(1).reshape(B, d).float(), 1e-5, 1e-3)
+    _close("kv1 mt", _unplanes(mt, 1), ref_mt, 2e-5, 1e-6)
+
+
 def check_upsample_rows():
     _lib.set_option("upsample_rows", 1)
     try:
@@ -551,7 +580,7 @@ def check_conv1_ragged():
 
 EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "sim_lse_cols": check_sim_lse_cols, "upsample_rows": check_upsample_rows,
                 "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged,
-                "fine_attn_vec": check_fine_attn_vec}
+                "fine_attn_vec": check_fine_attn_vec, "kv_single_plane": check_kv_single_plane}
 
 CHECKS = {
     "linear_act": check_linear_act,

@@ -215,6 +215,12 @@ def test_full_forward_host_flow(monkeypatch):
     # 6 layers x 2 sequences x (kv GEMM, kv_state, q GEMM, Mt+LN, mlp0, mlp2+LN)
     assert calls.count("linear_act") == 24 and calls.count("linear_ln") == 24
     assert calls.count("linear_q") == 12 and calls.count("kv_state") == 12
+    m.kv_single_plane = True    # opt-in: K'/V rows as one fp16 plane (same launches, shorter rows)
+    calls.clear()
+    m._coarse_transformer(q2, d3, B, hc * wc, N)
+    assert calls.count("linear_act") == 24 and calls.count("kv_state") == 12
+    assert m._buf("c2_kv16", (B * hc * wc, 512), torch.float16, dev).shape[1] == 512
+    m.kv_single_plane = False
     calls.clear()
     data = {"keypoints3d": torch.zeros(B, N, 3), "query_image_scale": torch.ones(B, 2),
             "q_hw_i": img.shape[2:], "q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3]),
