@@ -45,6 +45,20 @@ def golden(label):
         res["golden"][f"{case}[{label}]"] = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
 
 
+def c5_shape():
+    """BASELINE configs[4]: 640x480 image (60x80 coarse cells), 20000 points, window 5 — end-to-end
+    parity against the oracle on a planted bank (not yet part of the pytest -m gpu suite)."""
+    from oracle import oracle
+    sd = workload.synthetic_state_dict(0)
+    data, _ = workload.planted_workload(sd, 480, 640, 20000, 3000, batch=1)
+    ref = {k: v.clone() for k, v in data.items()}
+    oracle.forward(sd, ref)
+    got = parity.run_cuda(data)
+    res["golden"]["c5_shape"] = parity.compare(got, ref)
+    err = (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item()
+    assert err <= 1e-3, f"conf_matrix max err {err:.2e}"
+
+
 _STEP = {}
 
 
@@ -117,6 +131,7 @@ for cfg in configs:
         for name in ("linear_ln", "conv", "linear_act", "linear_q", "sim"):
             guarded(name, kernel_checks.CHECKS[name])
         guarded("conv1_ragged", kernel_checks.EXPERIMENTAL["conv1_ragged"])
+        guarded("c5_shape", c5_shape)
         first = False
     for k, v in cfg.items():
         if v and k in EXPERIMENTAL_CHECK:   # these set and restore their own option
