@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op breakdown to stderr")
+    ap.add_argument("--no-c5", action="store_true", help="skip the BASELINE configs[4] block")
     return ap.parse_args()
 
 
@@ -151,9 +152,10 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def conv_flops_table(B):
-    """Algorithmic MACs of the tcgen05 conv launches of one backbone pass (true channel counts)."""
-    h2, h4, h8 = (H // 2) * (W // 2), (H // 4) * (W // 4), (H // 8) * (W // 8)
+def conv_flops_table(B, h=H, w=W):
+    """Algorithmic MACs of the tcgen05 conv launches of one backbone pass (true channel counts;
+    the 7x7 conv1 — 0.41 GMAC/image — is listed separately)."""
+    h2, h4, h8 = (h // 2) * (w // 2), (h // 4) * (w // 4), (h // 8) * (w // 8)
     macs = 0
     macs += 4 * h2 * 128 * 128 * 9                                   # layer1
     macs += h4 * 196 * 128 * 9 + 3 * h4 * 196 * 196 * 9 + h4 * 196 * 128   # layer2 (+downsample)
@@ -161,6 +163,77 @@ def conv_flops_table(B):
     macs += h8 * 256 * 256 + h4 * 256 * 196 + h4 * 256 * 256 * 9 + h4 * 196 * 256 * 9   # fpn 1/4
     macs += h2 * 196 * 128 + h2 * 196 * 196 * 9 + h2 * 128 * 196 * 9                   # fpn 1/2
     return 2.0 * macs * B
+
+
+def ncu_traffic(kernel_substr, launch_index):
+    """DRAM bytes (read + write) of one launch from the committed ncu capture at the bench batch
+    (profiles/r2_ncu_b64_raw.csv: kernel name, launch index, dram__bytes_read.sum, dram__bytes_write.sum),
+    or None when no capture at this batch is committed — never a scaled constant."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_b64_traffic.json")
+    try:
+        t = json.load(open(path))
+        e = t[kernel_substr][launch_index]
+        return e["dram_read_bytes"] + e["dram_write_bytes"]
+    except (OSError, KeyError, IndexError, ValueError):
+        return None
+
+
+def cuda_time(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def bench_c5(model, sd, dev, workload, peaks, steps=5, batch=8):
+    """BASELINE configs[4]: 640x480 images (60x80 = 4800 coarse cells) vs a 20 000-point bank, fine
+    window 5 — the configuration whose (H/8*W/8) x N score matrix stresses HBM: conf_matrix is
+    384 MB per image.  Reports images/s with the matrix materialised (reference contract) and
+    without (lazy), and the dual-softmax passes alone against the measured HBM peak."""
+    h, w, n = 480, 640, 20000
+    data, _ = workload.planted_workload(sd, h, w, n, 6000, batch=1)
+    g = torch.Generator().manual_seed(5)
+    imgs = (data["query_image"] + 0.02 * torch.randn(batch, 1, h, w, generator=g)).clamp(0, 1).to(dev)
+    scale = data["query_image_scale"].expand(batch, -1).contiguous().to(dev)
+    bank = {k: data[k].to(dev) for k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db")}
+    out = {}
+
+    def step():
+        d = {"query_image": imgs, "query_image_scale": scale, **bank}
+        model(d)
+        out["d"] = d
+
+    res = {"workload": f"BASELINE configs[4]: batch {batch} images 640x480 vs shared 20000-pt bank, window 5",
+           "conf_matrix_bytes_per_image": 4 * n * (h // 8) * (w // 8)}
+    for mode in ("eager", "lazy"):
+        model.conf_matrix_mode = mode
+        ms = cuda_time(step, steps)
+        res[f"images_per_s_conf_{mode}"] = batch / ms * 1e3
+        res[f"ms_per_step_conf_{mode}"] = ms
+    res["matches_per_image"] = out["d"]["b_ids"].numel() / batch
+    # the dual-softmax passes alone (coarse_matching.py:102-119) on the final tokens of the last step
+    S = (h // 8) * (w // 8)
+    pl = 2 if model.split else 1
+    q2 = model._buf("q2_0", (batch, S, pl * 256), torch.float16, dev)
+    d3 = model._buf("d3_0", (batch, n, pl * 256), torch.float16, dev)
+    bstate = {"Bb": 1, "N": n, "kpts": bank["keypoints3d"].float().contiguous()}
+    for mode in ("eager", "lazy"):
+        model.conf_matrix_mode = mode
+        ms = cuda_time(lambda: model._coarse_matching(q2, d3, bstate, scale, batch, n, h // 8, w // 8, 8.0, {}), steps)
+        alg = batch * (n + S) * pl * 256 * 2 * 2 + (batch * n * S * 4 if mode == "eager" else 0)
+        res[f"sim_passes_ms_conf_{mode}"] = ms
+        res[f"sim_passes_hbm_gbs_conf_{mode}"] = alg / ms / 1e6
+        res[f"sim_passes_hbm_frac_conf_{mode}"] = alg / ms / 1e6 / peaks.get("hbm_gbs", 6562.6)
+    res["note"] = ("sim-pass bytes = tokens read once per GEMM pass (2 passes) + the fp32 conf_matrix store when "
+                   "materialised; 2*2*20000*4800*256 flop per image and pass on the tensor pipe (x3 issued)")
+    model.conf_matrix_mode = "eager"
+    return res
 
 
 def main():
@@ -172,7 +245,7 @@ def main():
         return run_reference(args, rank)
 
     import torch.distributed as dist
-    from onepose_plus_plus_b200 import OnePosePlus_model, _lib, parallel
+    from onepose_plus_plus_b200 import OnePosePlus_model, _lib, ops, parallel
     from oracle import oracle, workload  # checkpoint + workload generators and the cpu_baseline leg only
 
     torch.cuda.set_device(local_rank)
@@ -205,15 +278,15 @@ def main():
         parallel.broadcast_bank(bank, src=0)
     g = torch.Generator().manual_seed(100 + rank)
     base = data["query_image"]
-    imgs_host = (base + 0.02 * torch.randn(B, 1, H, W, generator=g)).clamp(0, 1).pin_memory()
+    imgs_f = (base + 0.02 * torch.randn(B, 1, H, W, generator=g)).clamp(0, 1)
+    imgs8_host = (imgs_f * 255).round().to(torch.uint8).pin_memory()          # what a camera / decoder delivers
+    imgs_host = (imgs8_host.float() / 255).pin_memory()                       # data_io.py:107 (reference input)
     scale_host = data["query_image_scale"].expand(B, -1).contiguous().pin_memory()
     bank_host = {k: v.cpu().pin_memory() for k, v in bank.items()}
 
     def make_data(images, scale, bk):
-        return {"query_image": images, "query_image_scale": scale,
-                "keypoints3d": bk["keypoints3d"].expand(B, -1, -1),
-                "descriptors3d_db": bk["descriptors3d_db"].expand(B, -1, -1),
-                "descriptors3d_coarse_db": bk["descriptors3d_coarse_db"].expand(B, -1, -1)}
+        # the reference's data dict: the bank rides along with every call (one object, [1, N, .])
+        return {"query_image": images, "query_image_scale": scale, **bk}
 
     imgs_dev = imgs_host.to(dev)
     scale_dev = scale_host.to(dev)
@@ -224,15 +297,33 @@ def main():
         return d
 
     out_host = {}
+    lo = rank * B
 
-    def step_e2e():
+    def read_back(d):
+        if world > 1:    # the one data-plane collective: every rank's matches to every rank
+            out_host["all"] = parallel.gather_matches(d, lo).cpu()
+        else:
+            for k in ("mkpts_3d_db", "mkpts_query_f", "mconf", "m_bids"):
+                out_host[k] = d[k].cpu()
+
+    def step_e2e_refapi():
+        # the reference worker's loop (inference_OnePosePlus_worker.py:54-56): fp32 frames AND the bank
+        # go host -> device with every call
         im = imgs_host.to(dev, non_blocking=True)
         sc = scale_host.to(dev, non_blocking=True)
         bk = {k: v.to(dev, non_blocking=True) for k, v in bank_host.items()}
         d = make_data(im, sc, bk)
         model(d)
-        for k in ("mkpts_3d_db", "mkpts_query_f", "mconf", "m_bids"):
-            out_host[k] = d[k].cpu()
+        read_back(d)
+        return d
+
+    def step_e2e():
+        # this repo's input path: bank resident (set_bank, once per object), uint8 frames
+        im = imgs8_host.to(dev, non_blocking=True)
+        sc = scale_host.to(dev, non_blocking=True)
+        d = {"query_image": im, "query_image_scale": sc}
+        model(d)
+        read_back(d)
         return d
 
     def barrier():
@@ -263,10 +354,23 @@ def main():
     launches = _lib.LAUNCHES
     m_per_img = d["b_ids"].numel() / B
 
+    # same step without materialising conf_matrix (no inference consumer reads it)
+    model.conf_matrix_mode = "lazy"
+    for _ in range(2):
+        step_resident()
+    ms_lazy, _, _, _ = timed(step_resident, args.steps)
+    model.conf_matrix_mode = "eager"
+
+    for _ in range(2):
+        step_e2e_refapi()
+    ms_e2e_ref, _, _, _ = timed(step_e2e_refapi, args.steps)
+    h2d_ref = imgs_host.numel() * 4 + scale_host.numel() * 4 + sum(v.numel() * 4 for v in bank_host.values())
+    model.set_bank(bank["keypoints3d"], bank["descriptors3d_db"], bank["descriptors3d_coarse_db"])
     for _ in range(2):
         step_e2e()
     ms_e2e, d2, _, _ = timed(step_e2e, args.steps)
-    h2d = imgs_host.numel() * 4 + scale_host.numel() * 4 + sum(v.numel() * 4 for v in bank_host.values())
+    model.clear_bank()
+    h2d = imgs8_host.numel() + scale_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
     # BASELINE configs[1] (one image per forward): latency view of the same path, wall clock incl.
@@ -294,55 +398,33 @@ def main():
     # with CUDA events around the backbone on the launching stream
     conv_ms = attn_ms = l1_ms = None
     S_tok = (H // 8) * (W // 8)
+    c5 = None
     if rank == 0:
-        img_f = imgs_dev.contiguous().float()
-        for _ in range(2):
-            model._backbone(img_f)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            model._backbone(img_f)
-        e1.record()
-        torch.cuda.synchronize()
-        conv_ms = e0.elapsed_time(e1) / 3
+        conv_ms = cuda_time(lambda: model._backbone(imgs_dev), 3)
         # the dominant kernel launch: layer1 3x3 conv 128->128 at 1/2 resolution (4 identical launches
         # per forward = 30 % of the conv flops), timed alone on the launching stream.  Its input
         # (batch x 256 x 256 x 2 planes x 128 ch fp16 = 2.1 GB at batch 64) exceeds L2.
-        from onepose_plus_plus_b200 import ops as _ops
         pl_ = 2 if model.split else 1
         x0 = model._buf("x0", (B, H // 2, W // 2, pl_ * 128), torch.float16, dev)
         y0 = model._buf("l1a_t", (B, H // 2, W // 2, pl_ * 128), torch.float16, dev)
         wl1, bl1 = model._plan["layer1.0.conv1"]
-        for _ in range(3):
-            _ops.conv2d_nhwc(x0, wl1, bl1, y0, 3, 1, model.split, act=1)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(5):
-            _ops.conv2d_nhwc(x0, wl1, bl1, y0, 3, 1, model.split, act=1)
-        e1.record()
-        torch.cuda.synchronize()
-        l1_ms = e0.elapsed_time(e1) / 5
+        l1_ms = cuda_time(lambda: ops.conv2d_nhwc(x0, wl1, bl1, y0, 3, 1, model.split, act=1), 5, warm=3)
         # coarse attention (BASELINE.json "coarse-attn tensor-pipe %"): the 6-layer linear-attention
-        # transformer on both sequences = 60 tcgen05 GEMM launches + the KV-state kernels
-        q2, _, (hc, wc) = model._backbone(img_f)
+        # transformer on both sequences (tcgen05 GEMM launches + the KV-state kernels), one object
+        # per image so that nothing is served from the per-object cache
+        q2, _, (hc, wc) = model._backbone(imgs_dev)
         S_tok = hc * wc
-        pl = 2 if model.split else 1
-        d3 = torch.randn(B, N_POINTS, 256, device=dev)
-        from onepose_plus_plus_b200 import ops as _ops
-        d3p = _ops.to_planes(d3, model.split)
+        bstate = {"Bb": B, "N": N_POINTS,
+                  "d3_in": ops.to_planes(torch.randn(B, N_POINTS, 256, device=dev), model.split)}
         q2c = q2.clone()
-        for _ in range(2):
-            model._coarse_transformer(q2c.clone(), d3p.clone(), B, S_tok, N_POINTS)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(3):
-            model._coarse_transformer(q2c, d3p, B, S_tok, N_POINTS)
-        e1.record()
-        torch.cuda.synchronize()
-        attn_ms = e0.elapsed_time(e1) / 3
+        attn_ms = cuda_time(lambda: model._coarse_transformer(q2c, bstate, B, S_tok, N_POINTS), 3)
         if args.profile_ops:
             _lib.profile_ops(lambda: step_resident(), sys.stderr)
+        if world == 1 and not args.no_c5:
+            try:
+                c5 = bench_c5(model, sd, dev, workload, peaks)
+            except Exception as e:  # noqa: BLE001
+                c5 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -377,23 +459,37 @@ def main():
                                    f"5000-pt bank (NCCL-broadcast once when N>1)",
                        "global_batch": B * world, "matches_per_image": m_per_img,
                        "l2": "per-step working set (activations >= 1 GB) exceeds the 126 MB L2; no explicit flush",
-                       "conf_matrix": "materialised fp32 every step (reference API)"},
+                       "conf_matrix": "materialised fp32 every step (reference API); see conf_lazy for the "
+                                      "store-free mode"},
             "clocks": clocks,
             "e2e": {"value": total_imgs / (ms_e2e * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "model.set_bank(...) once per object, then model({'query_image': uint8 frames, "
+                           "'query_image_scale': ...}) per step; pinned host buffers, match lists read back"
+                           + ("; all-gather of every rank's matches (parallel.gather_matches) inside the timed region"
+                              if world > 1 else "")},
+            "e2e_reference_api": {"value": total_imgs / (ms_e2e_ref * 1e-3), "unit": "images/s",
+                                  "h2d_bytes_per_step": h2d_ref, "d2h_bytes_per_step": d2h,
+                                  "api": "the reference worker's call: fp32 frames + the whole bank uploaded with "
+                                         "every model(data) (inference_OnePosePlus_worker.py:54-56)"},
+            "conf_lazy": {"value": total_imgs / (ms_lazy * 1e-3), "unit": "images/s",
+                          "ms_per_step": ms_lazy / args.steps,
+                          "note": "model.conf_matrix_mode='lazy': data['conf_matrix'] is a handle that "
+                                  "materialises on demand; matches identical (tests)"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor",
                          "kernel": "gemm_kernel<A_CONV,EpiConv>: layer1 3x3 conv 128->128 @256x256 (one launch, whole batch)",
                          "achieved": l1_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": l1_tf / peak_burst,
-                         "traffic": 496.7e6 * B / 8,
+                         "traffic": ncu_traffic("EpiConv", 1),
                          "peak_source": peak_src.replace("bf16_tflops_sustained", "bf16_tflops (burst: kernel timed alone)"), "ms_per_launch": l1_ms,
                          "algorithmic_flops_per_launch": l1_flops, "mma_passes": passes,
                          "issued_tensor_tflops": l1_tf * passes, "issued_frac": l1_tf * passes / peak_burst,
                          "note": "achieved = algorithmic flops (2*B*256*256*128*128*9, reference fp32 math) / CUDA-event "
                                  "time of the launch; the fp32-grade mode issues mma_passes x that on the tensor pipe; "
-                                 "traffic = dram read+write of this launch from ncu --set full at batch 8 (269.1 + 227.6 MB, "
-                                 "profiles/r1_ncu_summary.md) scaled to the batch",
-                         "backbone": {"kernels": "21 conv launches + conv1_7x7 + 2 upsample2x_add", "ms": conv_ms,
+                                 "traffic = dram read+write of this launch from the committed ncu --set full capture at "
+                                 "this batch (profiles/r2_ncu_b64_traffic.json), null when absent",
+                         "backbone": {"kernels": "conv1 im2col + 22 tcgen05 GEMM launches (FPN upsample-adds fused)",
+                                      "ms": conv_ms,
                                       "algorithmic_tflops": ach, "frac": ach / peak_tf if ach else None,
                                       "issued_frac": ach * passes / peak_tf if ach else None}},
             "coarse_attention": {
@@ -401,10 +497,12 @@ def main():
                 "ms": attn_ms, "algorithmic_tflops": attn_tf, "issued_tensor_tflops": attn_tf * passes,
                 "frac_of_peak_algorithmic": attn_tf / peak_tf, "frac_of_peak_issued": attn_tf * passes / peak_tf,
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
-                "tensor_pipe_pct_ncu": "per launch in profiles/r1_ncu_summary_staged.md (sm__pipe_tensor_cycles_active at batch 8: mlp.0 70-74 %, [Wk;Wv] 45-47 %, mlp.2+LN 35-37 %, q_proj / Mt+LN 28-30 %; dual-softmax lse passes 94 %)"},
+                "tensor_pipe_pct_ncu": "sm__pipe_tensor_cycles_active per launch at this batch: profiles/r2_ncu_xfmr_b64.md"},
+            "configs": {"c5": c5},
             "latency_b1": b1,
             "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH), "kv_mma": _lib.get_option("kv_mma"),
-                               "conv1_staged": _lib.get_option("conv1_staged")},
+                               "one_pass_dual_softmax": bool(model.coarse_colmax and model.coarse_lse_cols),
+                               "kv_single_plane": bool(model.kv_single_plane)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

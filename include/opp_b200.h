@@ -60,6 +60,15 @@ int opp_get_option(const char* name);
 int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
                   int h, int w, int c_out, int split, opp_stream_t stream);
 
+/* conv1 on the tensor-core engine: im2col of the 7x7 stride-2 pad-3 windows (resnet.py:101-103).
+ * a_out fp16 [B*H/2*W/2][planes*64]: row = (49 taps, 1.0, 14 zeros) of one output pixel, so that
+ * opp_linear_act_f16(a_out, k0 = 64, w = [c_out][planes*64] holding (49 folded-BN taps, folded
+ * bias, zeros), act = ReLU) yields the NHWC map [B][H/2][W/2][planes*c_out] of
+ * relu(bn1(conv1(x))) (resnet.py:143).  image: fp32 [B][1][H][W] in [0,1], or (image_u8 != 0)
+ * uint8 with x = u8 / 255 folded in (the host-side division of data_io.py:107). */
+int opp_conv1_im2col(const void* image, int image_u8, void* a_out, int batch, int h, int w, int split,
+                     opp_stream_t stream);
+
 /* 3x3 (pad 1) or 1x1 (pad 0) convolution, stride 1 or 2, as a tcgen05 implicit GEMM
  * (resnet.py:10-17 conv1x1/conv3x3; BasicBlock resnet.py:36-45; FPN heads resnet.py:109-124).
  *   in    NHWC fp16 [B][in_h][in_w][c_in_pad]
@@ -71,11 +80,14 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
  *   tok/pe: when tok != NULL also writes  out + pe  as coarse tokens
  *          [B][out_h*out_w][planes*c_out_pad]; pe is fp32 [out_h*out_w][c_out_pad]
  *          (PositionEncodingSine.forward position_encoding.py:37-42 + the 'n c h w -> n (h w) c'
- *          rearrange OnePosePlusModel.py:137-142) */
+ *          rearrange OnePosePlusModel.py:137-142)
+ *   up:    when up != NULL the epilogue adds  bilinear_x2(up), align_corners=True  (FPN top-down
+ *          merge, resnet.py:149-157: F.interpolate(..., scale_factor=2, mode="bilinear",
+ *          align_corners=True) + lateral conv); up is NHWC fp16 [B][out_h/2][out_w/2][c_out_pad] */
 int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void* resid,
                     void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
                     int ksize, int stride, int act, float slope, void* tok, const float* pe,
-                    int split, opp_stream_t stream);
+                    const void* up, int split, opp_stream_t stream);
 
 /* out = a + bilinear_x2(b), align_corners=True (resnet.py:151-152,155-156).
  * a, out NHWC fp16 [B][2h][2w][c]; b NHWC fp16 [B][h][w][c]. out may alias a. */
@@ -111,6 +123,13 @@ int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const voi
                        long long rows, int n, int act, int act_cols, int split,
                        opp_stream_t stream);
 
+/* Batched form: a0 / a1 / out are [batches][rows][..]; with a0_shared != 0 the first operand is
+ * [1][rows][k0] — one object's tokens shared by every image of the batch (the 3D side of the
+ * first cross layer, whose x is image-independent: transformer.py:148-159) — and is read once. */
+int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, int k1, const void* w,
+                         void* out, int batches, long long rows, int n, int act, int act_cols,
+                         int split, opp_stream_t stream);
+
 /* Same GEMM with split (hi|lo) operands but a single-plane fp16 output [rows][n]: for the K'/V rows
  * of the linear-attention state, whose consumer sums over thousands of rows (built for the next
  * GPU session; selected by $OPP_B200_KV1). */
@@ -119,19 +138,20 @@ int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, cons
 
 /* q_proj + feature map + normaliser (transformer.py:77, linear_attention.py:45,58):
  * out = Q * v_len / (Q . ksum_head + eps), Q = elu(x @ wq^T) + 1, heads of 32 channels.
- * x fp16 [B][rows][256]; ksum fp32 [B][256]; out fp16 [B][rows][256] */
+ * x fp16 [B][rows][256] (or [1][rows][256] with x_shared != 0); ksum fp32 [B][256];
+ * out fp16 [B][rows][256] */
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
-                     int rows, int d_model, float v_len, float eps, int split,
+                     int rows, int d_model, float v_len, float eps, int split, int x_shared,
                      opp_stream_t stream);
 
 /* y = LayerNorm(concat_K(a0,a1) @ w^T) [+ resid]  (transformer.py:85-94).
  * w fp16 [n][planes*k] or, when w_batched, [B][n][planes*k] (the per-image
  * blockdiag(KV) @ merge^T  matrix).  resid / out16 fp16 [B*rows][planes*n]; out32 fp32
- * [B*rows][n]; either output may be NULL. */
+ * [B*rows][n]; either output may be NULL.  resid_shared != 0: resid is [1][rows][planes*n]. */
 int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w, int w_batched,
                   const float* gamma, const float* beta, float eps, const void* resid,
-                  void* out16, float* out32, int batches, long long rows, int n, int split,
-                  opp_stream_t stream);
+                  int resid_shared, void* out16, float* out32, int batches, long long rows, int n,
+                  int split, opp_stream_t stream);
 
 /* Source side state of linear attention (linear_attention.py:55-57):
  * kv16 fp16 [B][S][planes*2d] holds K' = elu(k)+1 in columns [0,d) and V in [d,2d) of each plane.
@@ -195,13 +215,14 @@ int opp_best_finalize(const float* part_val, const int* part_idx, float* best_va
  *   pt_val/pt_idx [B][l]: row maxima of conf;  px_idx [B][s]: column argmax of conf
  *   kpts fp32 [B][l][3]; img_scale fp32 [B][2] = (h_scale, w_scale) or NULL
  *   scratch int32 [ceil(B*l/1024) + 2]
+ *   bank_shared != 0: one object for the whole batch, kpts is [1][l][3] (no per-image copies)
  * Outputs (ascending (b, i) order): b_ids/i_ids/j_ids int64, mconf fp32, mkpts3d fp32 [.][3],
  * mkpts_c fp32 [.][2]; count_out int32 [1] = number of matches. */
 int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, const float* kpts,
                      const float* img_scale, int batch, int l, int hc, int wc, float thr,
                      int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
                      long long* j_ids, float* mconf, float* mkpts3d, float* mkpts_c,
-                     int* count_out, opp_stream_t stream);
+                     int* count_out, int bank_shared, opp_stream_t stream);
 
 /* opp_match_select with the mutual-nearest test on values (coarse_matching.py:157-165 compares
  * conf == conf.max(dim) the same way): row l keeps its argmax cell j iff pt_val[b][l] has the same
@@ -210,7 +231,8 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
                             const float* kpts, const float* img_scale, int batch, int l, int hc,
                             int wc, float thr, int border, float cell, int* scratch,
                             long long* b_ids, long long* i_ids, long long* j_ids, float* mconf,
-                            float* mkpts3d, float* mkpts_c, int* count_out, opp_stream_t stream);
+                            float* mkpts3d, float* mkpts_c, int* count_out, int bank_shared,
+                            opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fine level — FinePreprocess (loftr_module/fine_preprocess.py:32-55), loftr_fine,
@@ -220,10 +242,12 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
 /* For match m: row 26m = descriptors3d_db[b, :, i]; rows 26m+1+ww = the 5x5 window (ww = ky*5+kx)
  * of the fine map centred on fine pixel (stride*jy, stride*jx), zero outside the map.
  * fine NHWC fp16 [B][hf][wf][planes*128]; desc3d fp32 [B][128][n];
- * x32 fp32 [26 M][128] (may be NULL) / x16 fp16 [26 M][planes*128] */
+ * x32 fp32 [26 M][128] (may be NULL) / x16 fp16 [26 M][planes*128];
+ * bank_shared != 0: desc3d is [1][128][n], shared by every batch element */
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
-                    int hf, int wf, int wc, int stride, int n, int split, opp_stream_t stream);
+                    int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
+                    opp_stream_t stream);
 
 /* Linear attention for the 1 + 25 tokens of each match (linear_attention.py:29-61 with
  * L,S in {1,25}).  qkv fp16 [26 M][planes*384] = (elu(q)+1 | elu(k)+1 | v), 8 heads of 16.

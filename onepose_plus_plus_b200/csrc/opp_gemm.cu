@@ -205,7 +205,7 @@ static int pick_block_n(int n) {
 // A_i rows are [hi(k_i) | lo(k_i)], W rows are [hi(k0+k1) | lo(k0+k1)].
 static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, const void* a1,
                       int k1, const void* w, int w_batched, int batches, long long rows, int n,
-                      int split, int n_align = 16) {
+                      int split, int n_align = 16, int a0_shared = 0) {
   OPP_REQUIRE(a0 && w, "null operand");
   OPP_REQUIRE(k0 > 0 && k0 % 64 == 0 && k1 % 64 == 0, "K (%d,%d) must be multiples of 64", k0,
               k1);
@@ -227,8 +227,9 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   s.a0_lo = k0;
   s.a1_lo = k1;
   s.b_lo = k0 + k1;
+  s.a0_shared = a0_shared ? 1 : 0;
   const long long ld0 = (long long)planes * k0, ld1 = (long long)planes * k1;
-  int rc = map_rows(&maps.a[0], a0, ld0, rows, batches, ld0, rows * ld0, kBlockM);
+  int rc = map_rows(&maps.a[0], a0, ld0, rows, a0_shared ? 1 : batches, ld0, rows * ld0, kBlockM);
   if (rc) return rc;
   if (k1 > 0) {
     OPP_REQUIRE(a1, "null second A operand");
@@ -256,9 +257,15 @@ const char* opp_last_error(void) { return opp::last_error(); }
 int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
                        long long rows, int n, int act, int act_cols, int split,
                        opp_stream_t stream) {
+  return opp_linear_act_f16_b(a0, k0, 0, a1, k1, w, out, 1, rows, n, act, act_cols, split, stream);
+}
+
+int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, int k1, const void* w,
+                         void* out, int batches, long long rows, int n, int act, int act_cols,
+                         int split, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, split);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, batches, rows, n, split, 16, a0_shared);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
@@ -284,13 +291,13 @@ int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, cons
 }
 
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
-                     int rows, int d_model, float v_len, float eps, int split,
+                     int rows, int d_model, float v_len, float eps, int split, int x_shared,
                      opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(d_model == 256, "opp_linear_q_f16 supports d_model 256 (8 heads x 32), got %d",
               d_model);
-  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model, split);
+  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model, split, 16, x_shared);
   if (rc) return rc;
   OPP_REQUIRE(ksum && out, "null pointer");
   EpiQ::Params ep{(__half*)out, (long long)d_model * (split ? 2 : 1), split ? d_model : 0, ksum,
@@ -300,8 +307,8 @@ int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out
 
 int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w, int w_batched,
                   const float* gamma, const float* beta, float eps, const void* resid,
-                  void* out16, float* out32, int batches, long long rows, int n, int split,
-                  opp_stream_t stream) {
+                  int resid_shared, void* out16, float* out32, int batches, long long rows, int n,
+                  int split, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(n == 128 || n == 256, "LayerNorm epilogue needs N in {128,256}, got %d", n);
@@ -309,7 +316,7 @@ int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w,
   if (rc) return rc;
   OPP_REQUIRE(gamma && beta, "null LayerNorm parameters");
   OPP_REQUIRE(out16 || out32, "no output requested");
-  EpiLN::Params ep{gamma, beta, eps, (const __half*)resid, (__half*)out16,
+  EpiLN::Params ep{gamma, beta, eps, (const __half*)resid, resid_shared, (__half*)out16,
                    (long long)n * (split ? 2 : 1), split ? n : 0, out32};
   return launch<A_ROWS, EpiLN>(maps, s, ep, (cudaStream_t)stream);
 }
@@ -317,7 +324,7 @@ int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w,
 int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void* resid,
                     void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
                     int ksize, int stride, int act, float slope, void* tok, const float* pe,
-                    int split, opp_stream_t stream) {
+                    const void* up, int split, opp_stream_t stream) {
   OPP_REQUIRE(in && w && bias, "null operand");
   OPP_REQUIRE(ksize == 1 || ksize == 3, "kernel size %d unsupported (1 or 3)", ksize);
   OPP_REQUIRE(stride == 1 || stride == 2, "stride %d unsupported", stride);
@@ -381,8 +388,14 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   pick_grouping(s);
   rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n / s.cluster);
   if (rc) return rc;
-  EpiConv::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias,
-                     (const __half*)resid, act, slope, (__half*)tok, pe};
+  OPP_REQUIRE(!up || (out_h % 2 == 0 && out_w % 2 == 0 && out_h >= 4 && out_w >= 4),
+              "fused upsample-add needs even output dims >= 4 (got %d x %d)", out_h, out_w);
+  EpiConvParams ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias,
+                     (const __half*)resid, act, slope, (__half*)tok, pe, (const __half*)up,
+                     out_h / 2, out_w / 2,
+                     up ? (float)(out_h / 2 - 1) / (float)(out_h - 1) : 0.f,
+                     up ? (float)(out_w / 2 - 1) / (float)(out_w - 1) : 0.f};
+  if (up) return launch<A_CONV, EpiConvUp>(maps, s, ep, (cudaStream_t)stream);
   return launch<A_CONV, EpiConv>(maps, s, ep, (cudaStream_t)stream);
 }
 

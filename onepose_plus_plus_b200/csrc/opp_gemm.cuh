@@ -97,6 +97,7 @@ struct GemmShape {
   // A_ROWS
   int k_chunks_a0;  // chunks read through maps.a[0]; the rest through maps.a[1]
   int a0_lo, a1_lo; // element offsets of the lo planes of the two A arrays (= their K)
+  int a0_shared;    // the first A array is [1][rows][..]: one object shared by every batch element
   // A_CONV
   int conv_cchunks; // K chunks per filter tap
   int conv_c;       // padded input channels (multiple of 16); also the lo-plane offset
@@ -365,6 +366,7 @@ struct EpiLN {
     const float* beta;
     float eps;
     const __half* resid;  // same layout as out16 (ld, out_lo) or null
+    int resid_shared;     // resid is [1][rows][..], shared by every batch element
     __half* out16;        // or null
     long long ld;
     int out_lo;
@@ -372,7 +374,7 @@ struct EpiLN {
   };
   __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
     if (!p.resid || !c.valid) return;
-    const char* row = reinterpret_cast<const char*>(p.resid + c.grow * p.ld);
+    const char* row = reinterpret_cast<const char*>(p.resid + (p.resid_shared ? (long long)c.row : c.grow) * p.ld);
     for (int o = c.group * 128; o < c.ncols * 2; o += 256) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
       if (p.out_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * p.out_lo + o));
@@ -437,10 +439,13 @@ struct EpiLN {
       m2 = m2a + m2b + delta * delta * (na * nb / n);
     }
     const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
+    // a shared residual is indexed by the row inside the batch: rebase the pointer once per tile
+    const __half* resid = p.resid;
+    if (resid && p.resid_shared) resid -= (long long)c.b * s.rows * p.ld;
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #if OPP_LN_STAGED
       StagedRows pre;
-      if (p.resid) staged_load_issue(c, p.resid, p.ld, p.out_lo, c.n0 + col, c.ncols - col, pre);
+      if (resid) staged_load_issue(c, resid, p.ld, p.out_lo, c.n0 + col, c.ncols - col, pre);
 #endif
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -453,7 +458,7 @@ struct EpiLN {
       }
 #if OPP_LN_STAGED
       // every lane takes part in the warp-staged transposes; row validity is per staged row
-      if (p.resid) staged_load_add(c, p.out_lo, pre, v);
+      if (resid) staged_load_add(c, p.out_lo, pre, v);
       if (p.out32 && c.valid) {
         float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + col);
 #pragma unroll
@@ -463,8 +468,8 @@ struct EpiLN {
       if (p.out16) staged_store_h32(s, c, p.out16, p.ld, p.out_lo, c.n0 + col, v, c.ncols - col);
 #else
       if (!c.valid) return;
-      if (p.resid) {
-        const __half* rrow = p.resid + c.grow * p.ld;
+      if (resid) {
+        const __half* rrow = resid + c.grow * p.ld;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float r[8];
@@ -493,19 +498,26 @@ struct EpiLN {
 // Convolution epilogue: folded-BN bias, residual add, ReLU / LeakyReLU (resnet.py:36-45,112-124,
 // 141-147).  Optionally also emits the coarse tokens  x3_out + pe  in token-major order
 // (position_encoding.py:37-42 + OnePosePlusModel.py:137-142: NHWC *is* 'n (h w) c').
-struct EpiConv {
+struct EpiConvParams {
+  __half* out;          // NHWC, pixel stride ld (or null)
+  long long ld;
+  int out_lo;
+  const float* bias;    // [n_total]
+  const __half* resid;  // same layout as out, or null
+  int act;              // 0 none, 1 relu, 2 leaky relu
+  float slope;
+  __half* tok;          // [B*H*W] rows with the same (ld, out_lo) layout, or null
+  const float* pe;      // [H*W][n_total]
+  // FPN top-down path (resnet.py:149-157): out = conv(x) + bilinear_x2(up), align_corners=True.
+  // up is the coarser map [B][up_h][up_w] with the same (ld, out_lo) channel layout, or null.
+  const __half* up;
+  int up_h, up_w;
+  float up_sy, up_sx;   // (in - 1) / (out - 1)
+};
+template <bool kUp>
+struct EpiConvT {
   static constexpr int kGroups = OPP_CONV_GROUPS;
-  struct Params {
-    __half* out;          // NHWC, pixel stride ld (or null)
-    long long ld;
-    int out_lo;
-    const float* bias;    // [n_total]
-    const __half* resid;  // same layout as out, or null
-    int act;              // 0 none, 1 relu, 2 leaky relu
-    float slope;
-    __half* tok;          // [B*H*W] rows with the same (ld, out_lo) layout, or null
-    const float* pe;      // [H*W][n_total]
-  };
+  using Params = EpiConvParams;
   // Called before the accumulator wait: pull this row of the residual towards L2 while the MMAs
   // of the tile are still running (the conv2 of a BasicBlock was epilogue-bound on this read).
   __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
@@ -544,6 +556,43 @@ struct EpiConv {
     };
     if (has_res && c.col_first < c.ncols) issue(c.col_first);
 #endif
+    // Fused bilinear x2 upsample-add (torch semantics: src = dst * (in-1)/(out-1), i0 = floor(src),
+    // i1 = min(i0+1, in-1)).  A warp owns 2 output rows x 16 columns of the 8x16 tile; their
+    // neighbours lie in a 3 x 10 window of the coarse map (15 * 0.5 < 8 columns, 1 * 0.5 < 1 row),
+    // so per 32-channel chunk and plane the warp fetches those <= 30 pixels' 64-byte segments
+    // coalesced into its transpose buffer (slot = wy * 10 + wx) and every lane then reads its own
+    // four neighbours from shared memory.
+    const int lane_ = threadIdx.x & 31;
+    float uw00 = 0.f, uw01 = 0.f, uw10 = 0.f, uw11 = 0.f;
+    uint32_t us00 = 0, us01 = 0, us10 = 0, us11 = 0;   // shared addresses of the 4 neighbour slots
+    long long upix[4] = {0, 0, 0, 0};                  // source pixel (element offset) staged by this lane
+    if constexpr (kUp) {
+      const int rit = c.q * 32 + lane_;
+      const int ty = c.m_tile / s.tiles_x;
+      const int ly = rit / s.tile_w;
+      const int oy = min(ty * s.tile_h + ly, s.out_h - 1);
+      const int ox = min((c.m_tile - ty * s.tiles_x) * s.tile_w + (rit - ly * s.tile_w), s.out_w - 1);
+      const float fy = p.up_sy * (float)oy, fx = p.up_sx * (float)ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
+      const float wy = fy - (float)y0, wx = fx - (float)x0;
+      uw00 = (1.f - wy) * (1.f - wx);
+      uw01 = (1.f - wy) * wx;
+      uw10 = wy * (1.f - wx);
+      uw11 = wy * wx;
+      const int ymin = __shfl_sync(0xffffffffu, y0, 0), xmin = __shfl_sync(0xffffffffu, x0, 0);
+      us00 = c.wstage_s + ((y0 - ymin) * 10 + (x0 - xmin)) * kStageRowH;
+      us01 = c.wstage_s + ((y0 - ymin) * 10 + (x1 - xmin)) * kStageRowH;
+      us10 = c.wstage_s + ((y1 - ymin) * 10 + (x0 - xmin)) * kStageRowH;
+      us11 = c.wstage_s + ((y1 - ymin) * 10 + (x1 - xmin)) * kStageRowH;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int slot = min((lane_ >> 2) + 8 * i, 29);
+        const int sy_ = slot / 10, sx_ = slot - sy_ * 10;
+        upix[i] = (((long long)c.b * p.up_h + min(ymin + sy_, p.up_h - 1)) * p.up_w +
+                   min(xmin + sx_, p.up_w - 1)) * p.ld;
+      }
+    }
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
@@ -554,6 +603,40 @@ struct EpiConv {
         v[4 * g + 1] += __uint_as_float(bq.y);
         v[4 * g + 2] += __uint_as_float(bq.z);
         v[4 * g + 3] += __uint_as_float(bq.w);
+      }
+      if constexpr (kUp) {
+        const int seg = lane_ & 3;
+        const bool seg_ok = seg * 8 < nvalid;
+#pragma unroll
+        for (int plane = 0; plane < 2; ++plane) {
+          if (plane == 1 && p.out_lo == 0) break;
+          uint4 u[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            u[i] = seg_ok ? *reinterpret_cast<const uint4*>(p.up + upix[i] + plane * p.out_lo + g0 + seg * 8)
+                          : make_uint4(0, 0, 0, 0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts128(c.wstage_s + ((lane_ >> 2) + 8 * i) * kStageRowH + seg * 16, u[i]);
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 q00 = lds128(us00 + g * 16), q01 = lds128(us01 + g * 16);
+            const uint4 q10 = lds128(us10 + g * 16), q11 = lds128(us11 + g * 16);
+            const __half2* h00 = reinterpret_cast<const __half2*>(&q00);
+            const __half2* h01 = reinterpret_cast<const __half2*>(&q01);
+            const __half2* h10 = reinterpret_cast<const __half2*>(&q10);
+            const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 a = __half22float2(h00[j]), b = __half22float2(h01[j]);
+              const float2 cc = __half22float2(h10[j]), d = __half22float2(h11[j]);
+              v[8 * g + 2 * j] += (uw00 * a.x + uw01 * b.x) + (uw10 * cc.x + uw11 * d.x);
+              v[8 * g + 2 * j + 1] += (uw00 * a.y + uw01 * b.y) + (uw10 * cc.y + uw11 * d.y);
+            }
+          }
+          __syncwarp();
+        }
       }
 #if OPP_CONV_RESID_STAGED
       if (has_res) {
@@ -611,6 +694,9 @@ struct EpiConv {
     });
   }
 };
+
+using EpiConv = EpiConvT<false>;
+using EpiConvUp = EpiConvT<true>;   // + fused bilinear x2 upsample-add of the coarser FPN level
 
 // Dual-softmax statistics (coarse_matching.py:102-115): per row, over this tile's columns,
 // (max, sum exp) of sim = acc*scale.  Partials [grow][n_tile] are merged by a finalize kernel.
@@ -973,17 +1059,18 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
           const int kc = (first ? chunk : chunk - s.k_chunks_a0) * kBlockK;
           const CUtensorMap* am = first ? &maps.a[0] : &maps.a[1];
           const int lo = first ? s.a0_lo : s.a1_lo;
+          const int ba = (first && s.a0_shared) ? 0 : b;
           kb = chunk * kBlockK;
           if (elect_one()) {
             if (!pair || leader) mbar_expect_tx(&full[stage], tx_bytes);
             if (!skip_a) {
               if (pair) {
-                tma_load_3d_2sm(am, &full[stage], sa, kc, m_tile * kBlockM, b);
+                tma_load_3d_2sm(am, &full[stage], sa, kc, m_tile * kBlockM, ba);
                 if (s.split)
-                  tma_load_3d_2sm(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
+                  tma_load_3d_2sm(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, ba);
               } else {
-                tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, b);
-                if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, b);
+                tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, ba);
+                if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, ba);
               }
             }
           }

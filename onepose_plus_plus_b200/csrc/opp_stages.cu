@@ -298,6 +298,57 @@ __global__ void __launch_bounds__(256, 1) conv1_7x7_px4_kernel(const float* __re
 }
 
 // =============================================================================================
+// conv1 as a tensor-core GEMM (backbone/resnet.py:101-103,143): the 7x7 stride-2 pad-3 window of
+// every output pixel is written as one GEMM row  A[pixel][64] = (49 taps, 1.0, 0 x 14)  in fp16
+// planes; the weight matrix W[c][64] = (49 folded-BN taps, folded bias, 0 x 14) then gives
+// conv + bias as ONE 64-wide K chunk of the tcgen05 engine (opp_linear_act_f16 with ReLU), whose
+// row-major output [pixel][planes*C] IS the NHWC feature map.  This kernel is the im2col: pure
+// streaming (reads the image through a shared-memory patch, writes 128 B per pixel and plane,
+// fully coalesced).  IMG_U8: the image is uint8 and  x = u8 / 255  (data_io.py:34-68 does the
+// division on the host; folding it here lets callers upload 1 B instead of 4 B per pixel).
+// =============================================================================================
+template <bool IMG_U8>
+__global__ void __launch_bounds__(256) conv1_im2col_kernel(const void* __restrict__ img_v,
+                                                           __half* __restrict__ a_out, int H, int W,
+                                                           int lo_off) {
+  constexpr int P = 2 * kC1Tile + 5;   // 37 x 37 input patch of a 16 x 16 output tile
+  __shared__ float p_s[P * P];
+  const int b = blockIdx.z;
+  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
+  const int OH = H / 2, OW = W / 2;
+  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < P * P; i += 256) {
+    const int py = i / P, px = i - py * P;
+    const int y = iy0 + py, x = ix0 + px;
+    float v = 0.f;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const long long o = ((long long)b * H + y) * W + x;
+      if (IMG_U8) v = (float)reinterpret_cast<const uint8_t*>(img_v)[o] / 255.f;
+      else v = reinterpret_cast<const float*>(img_v)[o];
+    }
+    p_s[i] = v;
+  }
+  __syncthreads();
+  // thread -> (pixel, 8-column group): 8 consecutive lanes write one pixel's 128 B plane row
+  const int g = threadIdx.x & 7;
+  const int ld = lo_off ? 128 : 64;
+#pragma unroll 1
+  for (int pp = threadIdx.x >> 3; pp < kC1Tile * kC1Tile; pp += 32) {
+    const int ly = pp / kC1Tile, lx = pp - ly * kC1Tile;
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    if (oy >= OH || ox >= OW) continue;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = g * 8 + j;
+      const int ky = col / 7, kx = col - ky * 7;
+      v[j] = col < 49 ? p_s[(2 * ly + ky) * P + 2 * lx + kx] : (col == 49 ? 1.f : 0.f);
+    }
+    store_split8(a_out + (((long long)b * OH + oy) * OW + ox) * ld, g * 8, v, lo_off ? 64 : 0);
+  }
+}
+
+// =============================================================================================
 // out = a + bilinear_x2(b), align_corners=True   (backbone/resnet.py:151-152,155-156)
 // torch semantics: src = dst * (in-1)/(out-1); i0 = floor(src); i1 = min(i0+1, in-1)
 // =============================================================================================
@@ -986,7 +1037,7 @@ match_scatter_kernel(const float* pt_val, const int* pt_idx, const int* px_idx, 
                      const float* img_scale, long long rows, int l, int s, int wc, float thr,
                      int border, float cell, const int* block_offsets, long long* b_ids,
                      long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
-                     float* mkpts_c) {
+                     float* mkpts_c, int kpts_shared) {
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
@@ -1014,7 +1065,7 @@ match_scatter_kernel(const float* pt_val, const int* pt_idx, const int* px_idx, 
   i_ids[pos] = i;
   j_ids[pos] = j;
   mconf[pos] = pt_val[r];
-  const float* kp = kpts + (b * l + i) * 3;
+  const float* kp = kpts + ((kpts_shared ? 0 : b) * l + i) * 3;
   mkpts3d[pos * 3 + 0] = kp[0];
   mkpts3d[pos * 3 + 1] = kp[1];
   mkpts3d[pos * 3 + 2] = kp[2];
@@ -1033,7 +1084,7 @@ match_scatter_colmax_kernel(const float* pt_val, const int* pt_idx, const unsign
                      const float* img_scale, long long rows, int l, int s, int wc, float thr,
                      int border, float cell, const int* block_offsets, long long* b_ids,
                      long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
-                     float* mkpts_c) {
+                     float* mkpts_c, int kpts_shared) {
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag_colmax(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
@@ -1061,7 +1112,7 @@ match_scatter_colmax_kernel(const float* pt_val, const int* pt_idx, const unsign
   i_ids[pos] = i;
   j_ids[pos] = j;
   mconf[pos] = pt_val[r];
-  const float* kp = kpts + (b * l + i) * 3;
+  const float* kp = kpts + ((kpts_shared ? 0 : b) * l + i) * 3;
   mkpts3d[pos * 3 + 0] = kp[0];
   mkpts3d[pos * 3 + 1] = kp[1];
   mkpts3d[pos * 3 + 2] = kp[2];
@@ -1082,13 +1133,13 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const __half* __restrict__ fine, const float* __restrict__ desc3d,
     const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
     const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
-    int wf, int wc, int stride, int n, int lo_off) {
+    int wf, int wc, int stride, int n, int lo_off, int desc_shared) {
   const int m = blockIdx.x, c = threadIdx.x;
   const long long b = b_ids[m], i = i_ids[m], j = j_ids[m];
   const int jy = (int)(j / wc), jx = (int)(j - (long long)jy * wc);
   const long long row0 = (long long)m * 26;
   const int ld = lo_off ? 256 : 128;
-  const float d = desc3d[(b * 128 + c) * n + i];
+  const float d = desc3d[((desc_shared ? 0 : b) * 128 + c) * n + i];
   if (x32) x32[row0 * 128 + c] = d;
   store_split1(x16 + row0 * ld, c, d, lo_off);
   const __half* fb = fine + b * hf * wf * ld;
@@ -1384,6 +1435,19 @@ int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void*
   return OPP_OK;
 }
 
+int opp_conv1_im2col(const void* image, int image_u8, void* a_out, int batch, int h, int w, int split,
+                     opp_stream_t stream) {
+  OPP_REQUIRE(image && a_out, "null pointer");
+  OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && batch > 0, "bad conv1 shape");
+  dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
+  if (image_u8)
+    conv1_im2col_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
+  else
+    conv1_im2col_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
 #ifndef OPP_UPSAMPLE_ROWS_DEFAULT
 #define OPP_UPSAMPLE_ROWS_DEFAULT 0
 #endif
@@ -1573,7 +1637,7 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
                      const float* img_scale, int batch, int l, int hc, int wc, float thr,
                      int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
                      long long* j_ids, float* mconf, float* mkpts3d, float* mkpts_c,
-                     int* count_out, opp_stream_t stream) {
+                     int* count_out, int bank_shared, opp_stream_t stream) {
   OPP_REQUIRE(pt_val && pt_idx && px_idx && kpts && scratch && count_out, "null pointer");
   const long long rows = (long long)batch * l;
   const int nblocks = (int)((rows + 1023) / 1024);
@@ -1584,7 +1648,7 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
   match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
   match_scatter_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, kpts, img_scale, rows, l,
                                                  s, wc, thr, border, cell, scratch, b_ids, i_ids,
-                                                 j_ids, mconf, mkpts3d, mkpts_c);
+                                                 j_ids, mconf, mkpts3d, mkpts_c, bank_shared);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1593,7 +1657,8 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
                             const float* kpts, const float* img_scale, int batch, int l, int hc,
                             int wc, float thr, int border, float cell, int* scratch,
                             long long* b_ids, long long* i_ids, long long* j_ids, float* mconf,
-                            float* mkpts3d, float* mkpts_c, int* count_out, opp_stream_t stream) {
+                            float* mkpts3d, float* mkpts_c, int* count_out, int bank_shared,
+                            opp_stream_t stream) {
   OPP_REQUIRE(pt_val && pt_idx && colmax && kpts && scratch && count_out, "null pointer");
   const long long rows = (long long)batch * l;
   const int nblocks = (int)((rows + 1023) / 1024);
@@ -1604,19 +1669,20 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
   match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
   match_scatter_colmax_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, kpts, img_scale, rows,
                                                         l, s, wc, thr, border, cell, scratch, b_ids,
-                                                        i_ids, j_ids, mconf, mkpts3d, mkpts_c);
+                                                        i_ids, j_ids, mconf, mkpts3d, mkpts_c, bank_shared);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
-                    int hf, int wf, int wc, int stride, int n, int split, opp_stream_t stream) {
+                    int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
+                    opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x16, "null pointer");
   fine_gather_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)fine, desc3d, b_ids,
                                                           i_ids, j_ids, x32, (__half*)x16, hf, wf,
-                                                          wc, stride, n, split ? 128 : 0);
+                                                          wc, stride, n, split ? 128 : 0, bank_shared);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

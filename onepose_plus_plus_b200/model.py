@@ -270,14 +270,24 @@ class OnePosePlus_model(nn.Module):
                     p.requires_grad = False
         self._plan = None
         self._plan_sig = None
+        self._sig_tensors = None
+        self._apply_epoch = 0
         self._ws = {}
-        # experimental (not yet validated on a GPU, off by default): take the column maxima of
-        # conf from the first conf pass (warp butterfly + atomicMax) instead of a second GEMM pass
-        self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "0") == "1"
-        # same status: column log-sum-exp from the first lse pass (two warp butterflies per chunk)
-        self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "0") == "1"
-        # same status: K'/V rows of the coarse attention state stored as ONE fp16 plane (their
-        # consumer sums over thousands of tokens; oracle experiment: conf changes by 1e-4)
+        self._ws_epoch = 0
+        self._bank = None
+        self._graphs = {}
+        self._fwd_count = 0
+        # data["conf_matrix"]: "eager" = fp32 [B, N, S] written every forward (reference contract,
+        # coarse_matching.py:119; what the training loss reads); "lazy" = a LazyConfMatrix handle
+        # that materialises on demand (no inference consumer reads the matrix:
+        # inference_OnePosePlus_worker.py:20-31); "skip" = key not written.
+        self.conf_matrix_mode = os.environ.get("OPP_B200_CONF", "eager")
+        # one-pass dual softmax: column statistics of sim / conf from the row passes (warp
+        # butterflies in the epilogue) instead of two more sim GEMM passes
+        self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "1") == "1"
+        self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "1") == "1"
+        # K'/V rows of the coarse attention state stored as ONE fp16 plane (their consumer sums over
+        # thousands of tokens; oracle experiment: conf changes by 1e-4)
         self.kv_single_plane = os.environ.get("OPP_B200_KV1", "0") == "1"
 
     @property
@@ -287,13 +297,36 @@ class OnePosePlus_model(nn.Module):
     # pickling (Ray ships the module object): drop device-side caches
     def __getstate__(self):
         st = self.__dict__.copy()
-        st["_plan"], st["_plan_sig"], st["_ws"] = None, None, {}
+        st["_plan"], st["_plan_sig"], st["_ws"], st["_sig_tensors"] = None, None, {}, None
+        st["_bank"], st["_graphs"] = None, {}
         return st
 
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
+                     ("_graphs", {}), ("_fwd_count", 0)):
+            self.__dict__.setdefault(k, v)
+
     # ------------------------------------------------------------------ weight preparation
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() / .half(): parameters are replaced -> re-read the tensor list
+        self._sig_tensors = None
+        self._apply_epoch += 1
+        return super()._apply(fn, *args, **kwargs)
+
     def _signature(self):
-        return (self.precision,) + tuple((t.data_ptr(), t._version)
-                                         for t in self.state_dict(keep_vars=True).values())
+        """Cheap identity of the weights: the parameter / buffer tensors are listed once (the list
+        is rebuilt after _apply or load_state_dict(assign=True)); per forward only their in-place
+        version counters are read (load_state_dict, optimizer steps and .copy_() bump them)."""
+        ts = self._sig_tensors
+        if ts is None:
+            ts = self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+        return (self.precision, self._apply_epoch, sum(t._version for t in ts))
+
+    def load_state_dict(self, *args, **kwargs):
+        self._sig_tensors = None
+        self._apply_epoch += 1
+        return super().load_state_dict(*args, **kwargs)
 
     @torch.no_grad()
     def _prepare(self, device):
@@ -321,8 +354,13 @@ class OnePosePlus_model(nn.Module):
             bp[:co] = b
             P[name] = (ops.to_planes(wp.reshape(_pad16(co), -1), split), bp.contiguous())
 
+        # conv1 runs as ONE 64-wide K chunk of the tcgen05 engine: W[c] = (49 folded taps, folded
+        # bias, 14 zeros) against im2col rows (49 taps, 1.0, 14 zeros) — ops.conv1_gemm
         w, b = fold("backbone.conv1", "backbone.bn1")
-        P["conv1"] = (w.view(w.shape[0], 49).t().contiguous(), b.contiguous())
+        w64 = torch.zeros(w.shape[0], 64, device=device)
+        w64[:, :49] = w.view(w.shape[0], 49)
+        w64[:, 49] = b
+        P["conv1"] = ops.to_planes(w64, split)
         for li in (1, 2, 3):
             for bi in (0, 1):
                 p = f"layer{li}.{bi}"
@@ -373,17 +411,34 @@ class OnePosePlus_model(nn.Module):
         return self._plan["pe"][key]
 
     def _buf(self, name, shape, dtype, device):
-        """Workspace tensors are allocated once per (name, shape) and reused across calls."""
-        key = (name, tuple(shape), dtype)
-        t = self._ws.get(key)
-        if t is None or t.device != device:
-            t = torch.empty(shape, dtype=dtype, device=device)
-            self._ws[key] = t
-        return t
+        """Workspace tensor `name`: ONE backing allocation per name, grown to the largest size ever
+        requested (high-water mark) and viewed at the requested shape — memory stays bounded when
+        point counts / image sizes change from object to object (a long-running service), and the
+        steady state allocates nothing.  `_ws_epoch` counts (re)allocations: captured CUDA graphs
+        hold raw pointers and are dropped when it moves."""
+        nbytes = dtype.itemsize * math.prod(shape)
+        ent = self._ws.get(name)
+        if ent is None or ent[0].device != device or ent[0].numel() < nbytes:
+            ent = (torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device), {})
+            self._ws[name] = ent
+            self._ws_epoch += 1
+        key = (tuple(shape), dtype)
+        v = ent[1].get(key)
+        if v is None:
+            if len(ent[1]) >= 16:
+                ent[1].clear()
+            v = ent[0][:nbytes].view(dtype).view(tuple(shape))
+            ent[1][key] = v
+        return v
 
     def clear_workspace(self):
-        """Drop the cached per-shape workspace tensors (they are re-created on the next forward)."""
+        """Drop the cached workspace (re-created by the next forward) and captured graphs."""
         self._ws = {}
+        self._graphs = {}
+        self._ws_epoch += 1
+
+    def workspace_bytes(self):
+        return sum(e[0].numel() for e in self._ws.values())
 
     # ------------------------------------------------------------------ stages
     def _backbone(self, img):
@@ -402,8 +457,8 @@ class OnePosePlus_model(nn.Module):
             out = self._buf(out_name, (Bn, oh, ow, pl * w.shape[0]), f16, dev)
             return ops.conv2d_nhwc(x, w, b, out, ksize, stride, split, act, resid, **kw)
 
-        x0 = ops.conv1_7x7(img, *P["conv1"], self._buf("x0", (B, H // 2, W // 2, pl * 128), f16, dev),
-                           split)
+        x0 = ops.conv1_gemm(img, P["conv1"], self._buf("conv1_cols", (B * (H // 2) * (W // 2), pl * 64), f16, dev),
+                            self._buf("x0", (B, H // 2, W // 2, pl * 128), f16, dev), split)
 
         def block(prefix, x, tag, stride):
             t = cv(prefix + ".conv1", x, tag + "_t", 3, stride, act=1)
@@ -417,20 +472,20 @@ class OnePosePlus_model(nn.Module):
         S = hc * wc
         tok = self._buf("q2_0", (B, S, pl * 256), f16, dev)
         x3_out = cv("layer3_outconv", x3, "x3_out", 1, 1, tok=tok, pe=self._pe_tokens(hc, wc, dev))
-        x2_lat = cv("layer2_outconv", x2, "x2_lat", 1, 1)
-        ops.upsample2x_add(x2_lat, x3_out, x2_lat, split)
+        # FPN top-down merge fused into the lateral 1x1 conv epilogue (resnet.py:149-157)
+        x2_lat = cv("layer2_outconv", x2, "x2_lat", 1, 1, up=x3_out)
         t = cv("layer2_outconv2.0", x2_lat, "x2_h", 3, 1, act=2)
         x2_out = cv("layer2_outconv2.3", t, "x2_out", 3, 1)
-        x1_lat = cv("layer1_outconv", x1, "x1_lat", 1, 1)
-        ops.upsample2x_add(x1_lat, x2_out, x1_lat, split)
+        x1_lat = cv("layer1_outconv", x1, "x1_lat", 1, 1, up=x2_out)
         t = cv("layer1_outconv2.0", x1_lat, "x1_h", 3, 1, act=2)
         x1_out = cv("layer1_outconv2.3", t, "x1_out", 3, 1)
         return tok, x1_out, (hc, wc)
 
-    def _encoder_layer(self, L, tag, x, src, B, lx, ls, out):
-        """LoFTREncoderLayer.forward (transformer.py:65-94) with linear attention
-        (linear_attention.py:29-61) for d_model 256.  x, src, out: fp16 planes [B, len, pl*256]."""
-        dev = x.device
+    def _src_state(self, L, tag, src, B, ls):
+        """Source side of linear attention for one layer (linear_attention.py:46,55-57 +
+        transformer.py:78-79,85): K' = elu(Wk src)+1, V = Wv src, per-head KV / Ksum, with `merge`
+        folded in -> (Mt [B, 256, pl*256] fp16, Ksum [B, 256] fp32)."""
+        dev = src.device
         f16 = torch.float16
         split = self.split
         pl = 2 if split else 1
@@ -441,46 +496,151 @@ class OnePosePlus_model(nn.Module):
         mt = self._buf(tag + "mt", (B, 256, pl * 256), f16, dev)
         ksum = self._buf(tag + "ksum", (B, 256), torch.float32, dev)
         ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split, kv_split=kv_split)
-        qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
-        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split)
-        msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
-        ops.linear_ln(qz, None, mt, True, *L["n1"], B, lx, split, out16=msg)
-        h = self._buf(tag + "h", (B * lx, pl * 512), f16, dev)
-        ops.linear_act(x, msg, L["mlp0"], h, B * lx, 1, 512, split)
-        ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, B * lx, split, resid=x, out16=out)
+        return mt, ksum
 
-    def _coarse_transformer(self, q2, d3, B, S, N, d3_shared=None):
+    def _encoder_layer(self, L, tag, x, src, B, lx, ls, out, x_shared=False, state=None):
+        """LoFTREncoderLayer.forward (transformer.py:65-94) with linear attention
+        (linear_attention.py:29-61) for d_model 256.  x, src, out: fp16 planes [B, len, pl*256].
+        x_shared: x is [1, lx, ..] — one object's tokens, the same for every image of the batch.
+        state = (Mt [1, ...], Ksum [B, 256]): precomputed source state shared by the batch."""
+        dev = x.device
+        f16 = torch.float16
+        split = self.split
+        pl = 2 if split else 1
+        if state is None:
+            mt, ksum = self._src_state(L, tag, src, B, ls)
+            mt_batched = True
+        else:
+            mt, ksum = state
+            mt_batched = False
+        qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
+        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split, x_shared=x_shared)
+        msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
+        ops.linear_ln(qz, None, mt, mt_batched, *L["n1"], B, lx, split, out16=msg)
+        h = self._buf(tag + "h", (B * lx, pl * 512), f16, dev)
+        if x_shared:
+            ops.linear_act(x, msg, L["mlp0"], h, lx, 1, 512, split, batches=B, a0_shared=True)
+            ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], B, lx, split, resid=x, out16=out,
+                          resid_shared=True)
+        else:
+            ops.linear_act(x, msg, L["mlp0"], h, B * lx, 1, 512, split)
+            ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, B * lx, split, resid=x, out16=out)
+
+    # ------------------------------------------------------------------ descriptor bank
+    def _encode_bank(self, kpts, dcoarse, dfine, persistent):
+        """Image-independent part of the forward for one descriptor bank: keypoint
+        normalisation + encoding (normalize.py:16-26, position_encoding.py:54-60) and — when the
+        bank is ONE object ([1, N, .]) and the coarse transformer starts with (self, cross) — the
+        3D side of the first self layer plus the 3D-as-source attention state of the first cross
+        layer (transformer.py:148-159: both read only 3D tokens)."""
+        dev = kpts.device
+        f16 = torch.float16
+        pl = 2 if self.split else 1
+        Bb, N = kpts.shape[:2]
+        alloc = (lambda name, shape, dt: torch.empty(shape, dtype=dt, device=dev)) if persistent else \
+            (lambda name, shape, dt: self._buf("bank_" + name, shape, dt, dev))
+        st = {"Bb": Bb, "N": N, "kpts": kpts, "fine": dfine, "sig": self._plan_sig}
+        d3 = alloc("d3_in", (Bb, N, pl * 256), f16)
+        ops.kpt_encode(kpts, dcoarse, self._plan["kpt_mlp"], alloc("stats", (Bb, 4), torch.float32), d3,
+                       self.split)
+        st["d3_in"] = d3
+        names = self.loftr_coarse.layer_names
+        if Bb == 1 and len(names) >= 2 and names[0] == "self" and names[1] == "cross":
+            d3_l0 = alloc("d3_l0", (1, N, pl * 256), f16)
+            self._encoder_layer(self._plan["coarse"][0], "c3s_", d3, d3, 1, N, N, d3_l0)
+            mt, ksum = self._src_state(self._plan["coarse"][1], "c3s_", d3_l0, 1, N)
+            st["d3_l0"] = d3_l0
+            st["l1_mt"] = alloc("l1_mt", mt.shape, f16).copy_(mt)
+            st["l1_ksum"] = alloc("l1_ksum", ksum.shape, torch.float32).copy_(ksum)
+        return st
+
+    def set_bank(self, keypoints3d, descriptors3d_db, descriptors3d_coarse_db=None):
+        """Make one object's descriptor bank resident on the model's device (extension; the
+        reference re-uploads the bank with every frame: inference_OnePosePlus_worker.py:54-56, and
+        only `preload`s it in demo mode: OnePosePlus_inference_dataset.py:58-59).  Shapes as in the
+        reference data dict with a leading 1 (or none): keypoints3d [1, N, 3], descriptors3d_db
+        [1, 128, N], descriptors3d_coarse_db [1, 256, N].  Afterwards `forward(data)` uses this bank
+        whenever `data` carries no "keypoints3d"; the keypoint encoding, the 3D side of the first
+        self layer and the 3D source state of the first cross layer are computed once per object."""
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("set_bank: move the model to a CUDA device first (there is no CPU path)")
+
+        def prep(t, c):
+            t = torch.as_tensor(t)
+            if t.dim() == 2:
+                t = t[None]
+            if t.dim() != 3 or t.shape[0] != 1:
+                raise ValueError(f"set_bank expects ONE object ([1, ...] tensors), got {tuple(t.shape)}")
+            return t.to(device=dev, dtype=torch.float32).contiguous()
+
+        kp = prep(keypoints3d, 3)
+        fine = prep(descriptors3d_db, 128)
+        coarse = prep(descriptors3d_coarse_db, 256) if descriptors3d_coarse_db is not None else fine
+        N = kp.shape[1]
+        if kp.shape[2] != 3 or fine.shape[2] != N or coarse.shape[2] != N or coarse.shape[1] != 256:
+            raise ValueError("set_bank: expected keypoints3d [1,N,3], descriptors3d_db [1,128,N], "
+                             f"descriptors3d_coarse_db [1,256,N]; got {tuple(kp.shape)}, {tuple(fine.shape)}, "
+                             f"{tuple(coarse.shape)}")
+        self._bank = {"raw": (kp, coarse, fine), "state": None}
+        return self
+
+    def clear_bank(self):
+        self._bank = None
+
+    def _resident_bank_state(self):
+        b = self._bank
+        if b["state"] is None or b["state"]["sig"] != self._plan_sig:
+            b["state"] = self._encode_bank(*b["raw"], persistent=True)
+        return b["state"]
+
+    def _coarse_transformer(self, q2, bank, B, S, N):
         """LocalFeatureTransformer.forward (transformer.py:133-171): self layers update each
-        sequence from itself; cross layers update BOTH from the pre-update tensors.
-        `d3_shared` ([1, N, C]): every batch element carries the same bank, so the 3D side of a
-        leading self layer is image-independent — computed once and broadcast."""
+        sequence from itself; cross layers update BOTH from the pre-update tensors.  `bank` is the
+        state of _encode_bank; with one shared object the 3D work of the first (self, cross) pair
+        that does not depend on the image comes from it."""
         dev = q2.device
         f16 = torch.float16
         pl = 2 if self.split else 1
         names = self.loftr_coarse.layer_names
-        cur2, cur3 = q2, d3
-        for i, name in enumerate(names):
+        shared = bank["Bb"] == 1 and B > 1
+        cur2, cur3 = q2, bank["d3_in"]
+        first = 0
+        if shared and "d3_l0" in bank:
+            # layer 0 (self): 2D side only; layer 1 (cross): the 2D side reads the cached 3D source
+            # state, the 3D side reads the shared 3D tokens in place (no per-image copies)
+            L0, L1 = self._plan["coarse"][0], self._plan["coarse"][1]
+            o2 = self._buf("q2_1", (B, S, pl * 256), f16, dev)
+            self._encoder_layer(L0, "c2_", cur2, cur2, B, S, S, o2)
+            d3 = bank["d3_l0"]
+            ksum_b = self._buf("l1_ksum_b", (B, 256), torch.float32, dev)
+            ksum_b.copy_(bank["l1_ksum"].expand(B, -1))
+            o2b = self._buf("q2_0", (B, S, pl * 256), f16, dev)
+            o3 = self._buf("d3_0", (B, N, pl * 256), f16, dev)
+            self._encoder_layer(L1, "c2_", o2, None, B, S, N, o2b, state=(bank["l1_mt"], ksum_b))
+            self._encoder_layer(L1, "c3_", d3, o2, B, N, S, o3, x_shared=True)
+            cur2, cur3 = o2b, o3
+            first = 2
+        elif shared:
+            cur3 = self._buf("d3_0", (B, N, pl * 256), f16, dev)
+            cur3.copy_(bank["d3_in"].expand(B, -1, -1))
+        for i in range(first, len(names)):
             L = self._plan["coarse"][i]
             nxt = (i + 1) % 2
             o2 = self._buf(f"q2_{nxt}", (B, S, pl * 256), f16, dev)
             o3 = self._buf(f"d3_{nxt}", (B, N, pl * 256), f16, dev)
-            self_layer = name == "self"
+            self_layer = names[i] == "self"
             self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
                                 S if self_layer else N, o2)
-            if d3_shared is not None and self_layer and i == 0:
-                o3_1 = self._buf("d3_shared_out", (1, N, pl * 256), f16, dev)
-                self._encoder_layer(L, "c3s_", d3_shared, d3_shared, 1, N, N, o3_1)
-                o3.copy_(o3_1.expand(B, -1, -1))
-            else:
-                if d3_shared is not None and i == 0:
-                    cur3.copy_(d3_shared.expand(B, -1, -1))
-                self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
-                                    N if self_layer else S, o3)
+            self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
+                                N if self_layer else S, o3)
             cur2, cur3 = o2, o3
         return cur2, cur3
 
-    def _coarse_matching(self, q2, d3, data, B, N, hc, wc):
-        """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch."""
+    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out):
+        """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch.
+        Enqueues everything up to the ordered match lists (capacity B*min(N,S)) and the device-side
+        match count; nothing here synchronises.  Fills `out` with the full-capacity tensors."""
         dev = q2.device
         S = hc * wc
         f32, i32 = torch.float32, torch.int32
@@ -490,8 +650,6 @@ class OnePosePlus_model(nn.Module):
         ts, tl = ops.sim_tiles(S), ops.sim_tiles(N)
         pm_pt = self._buf("pm_pt", (B * N, ts), f32, dev)
         ps_pt = self._buf("ps_pt", (B * N, ts), f32, dev)
-        pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
-        ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
         lse_pt = self._buf("lse_pt", (B, N), f32, dev)
         lse_px = self._buf("lse_px", (B, S), f32, dev)
         if self.coarse_lse_cols:
@@ -500,16 +658,19 @@ class OnePosePlus_model(nn.Module):
             col_s = self._buf("lse_col_s", (B, groups, S), f32, dev)
             ops.sim_lse_cols(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, col_m, col_s, lse_px, split)
         else:
+            pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
+            ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
             ops.sim_lse(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, split)
             ops.sim_lse(q2, d3, B, S, N, 256, scale, pm_px, ps_px, lse_px, split)
-        conf = torch.empty((B, N, S), dtype=f32, device=dev)  # owned by the caller's dict
+        mode = self.conf_matrix_mode
+        conf = torch.empty((B, N, S), dtype=f32, device=dev) if mode == "eager" else None  # caller's
         pi_pt = self._buf("pi_pt", (B * N, ts), i32, dev)
-        pi_px = self._buf("pi_px", (B * S, tl), i32, dev)
         pt_val = self._buf("pt_val", (B, N), f32, dev)
         pt_idx = self._buf("pt_idx", (B, N), i32, dev)
-        px_val = self._buf("px_val", (B, S), f32, dev)
-        px_idx = self._buf("px_idx", (B, S), i32, dev)
-        cap = B * min(N, S)
+        # capacity: one match per 3D point and per query cell (mutual nearest neighbours); the
+        # value-based mutual test keeps every row of an exact tie (as the reference's mask does), so
+        # its capacity is one per 3D point
+        cap = B * N if self.coarse_colmax else B * min(N, S)
         scratch = self._buf("match_scratch", ((B * N + 1023) // 1024 + 2,), i32, dev)
         count = self._buf("match_count", (1,), i32, dev)
         b_ids = torch.empty(cap, dtype=torch.int64, device=dev)
@@ -518,61 +679,66 @@ class OnePosePlus_model(nn.Module):
         mconf = torch.empty(cap, dtype=f32, device=dev)
         mk3 = torch.empty((cap, 3), dtype=f32, device=dev)
         mkc = torch.empty((cap, 2), dtype=f32, device=dev)
-        img_scale = data.get("query_image_scale")
-        if img_scale is not None:
-            img_scale = img_scale.to(device=dev, dtype=f32).contiguous()
-        cell = float(data["q_hw_i"][0] / hc)
+        kshared = bank["Bb"] == 1
         if self.coarse_colmax:
             colmax = self._buf("colmax", (B, S), i32, dev)
             ops.sim_conf_colmax(d3, q2, lse_pt, lse_px, conf, B, N, S, 256, scale, pm_pt, pi_pt,
                                 pt_val, pt_idx, colmax, split)
-            ops.match_select_colmax(pt_val, pt_idx, colmax, data["keypoints3d"], img_scale, B, N, hc, wc,
+            ops.match_select_colmax(pt_val, pt_idx, colmax, bank["kpts"], img_scale, B, N, hc, wc,
                                     cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf,
-                                    mk3, mkc, count)
+                                    mk3, mkc, count, bank_shared=kshared)
         else:
+            pi_px = self._buf("pi_px", (B * S, tl), i32, dev)
+            pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
+            px_val = self._buf("px_val", (B, S), f32, dev)
+            px_idx = self._buf("px_idx", (B, S), i32, dev)
             ops.sim_conf(d3, q2, lse_pt, lse_px, True, conf, B, N, S, 256, scale, pm_pt, pi_pt,
                          pt_val, pt_idx, split)
             ops.sim_conf(q2, d3, lse_px, lse_pt, False, None, B, S, N, 256, scale, pm_px, pi_px,
                          px_val, px_idx, split)
-            ops.match_select(pt_val, pt_idx, px_idx, data["keypoints3d"], img_scale, B, N, hc, wc,
+            ops.match_select(pt_val, pt_idx, px_idx, bank["kpts"], img_scale, B, N, hc, wc,
                              cm.thr, cm.border_rm, cell, scratch, b_ids, i_ids, j_ids, mconf, mk3, mkc,
-                             count)
-        M = int(count.item())  # the one host sync of the forward (the reference syncs in torch.where)
-        data.update({
-            "conf_matrix": conf,
-            "b_ids": b_ids[:M], "i_ids": i_ids[:M], "j_ids": j_ids[:M],
-            "gt_mask": torch.zeros(M, dtype=torch.bool, device=dev),
-            "m_bids": b_ids[:M], "mkpts_3d_db": mk3[:M], "mkpts_query_c": mkc[:M], "mconf": mconf[:M],
-        })
-        return M, img_scale
+                             count, bank_shared=kshared)
+        if mode == "lazy":
+            conf = LazyConfMatrix(self, d3, q2, lse_pt, lse_px, B, N, S, scale)
+        out.update({"conf_matrix": conf, "b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids, "mconf": mconf,
+                    "mkpts_3d_db": mk3, "mkpts_query_c": mkc})
+        return count, cap
 
-    def _fine(self, data, fine_map, M, img_scale, wc):
+    def _materialize_conf(self, d3, q2, lse_pt, lse_px, B, N, S, scale):
+        """conf_matrix on demand (LazyConfMatrix): re-runs the conf pass with the fp32 store."""
+        dev = q2.device
+        ts = ops.sim_tiles(S)
+        conf = torch.empty((B, N, S), dtype=torch.float32, device=dev)
+        ops.sim_conf(d3, q2, lse_pt, lse_px, True, conf, B, N, S, 256, scale,
+                     self._buf("lz_pv", (B * N, ts), torch.float32, dev),
+                     self._buf("lz_pi", (B * N, ts), torch.int32, dev),
+                     self._buf("lz_bv", (B, N), torch.float32, dev),
+                     self._buf("lz_bi", (B, N), torch.int32, dev), self.split)
+        return conf
+
+    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, mcount=None):
         """FinePreprocess (fine_preprocess.py:32-55) -> loftr_fine -> FineMatching
-        (fine_matching.py:28-110)."""
+        (fine_matching.py:28-110) on the first M entries of the match lists."""
         dev = fine_map.device
         f16, f32 = torch.float16, torch.float32
         split = self.split
         pl = 2 if split else 1
-        data["W"] = self.fine_preprocess.W
-        if M == 0:
-            data.update({"expec_f": torch.empty(0, 3, device=dev),
-                         "mkpts_query_f": data["mkpts_query_c"]})
-            return
         B, hf, wf, _ = fine_map.shape
-        stride = data["q_hw_f"][0] // data["q_hw_c"][0]
+        stride = hf // hc
         rows = 26 * M
-        x = [torch.empty((rows, pl * 128), dtype=f16, device=dev) for _ in range(2)]
-        x32 = torch.empty((rows, 128), dtype=f32, device=dev)
-        desc = data["descriptors3d_db"]
+        x = [self._buf(f"fx{k}", (rows, pl * 128), f16, dev) for k in range(2)]
+        x32 = self._buf("fx32", (rows, 128), f32, dev)
         fine_layers = self.loftr_fine.layer_names if self.config["loftr_fine"]["enable"] else []
-        ops.fine_gather(fine_map, desc, data["b_ids"], data["i_ids"], data["j_ids"],
-                        None if fine_layers else x32, x[0], M, hf, wf, wc, stride, desc.shape[2], split)
+        b_ids, i_ids, j_ids, mkc = ids
+        ops.fine_gather(fine_map, bank["fine"], b_ids, i_ids, j_ids, None if fine_layers else x32, x[0], M,
+                        hf, wf, wc, stride, bank["N"], split, bank_shared=bank["Bb"] == 1)
         cur = 0
         if fine_layers:
-            qkv = torch.empty((rows, pl * 384), dtype=f16, device=dev)
-            att = torch.empty((rows, pl * 128), dtype=f16, device=dev)
-            msg = torch.empty((rows, pl * 128), dtype=f16, device=dev)
-            h = torch.empty((rows, pl * 256), dtype=f16, device=dev)
+            qkv = self._buf("f_qkv", (rows, pl * 384), f16, dev)
+            att = self._buf("f_att", (rows, pl * 128), f16, dev)
+            msg = self._buf("f_msg", (rows, pl * 128), f16, dev)
+            h = self._buf("f_h", (rows, pl * 256), f16, dev)
             for i, name in enumerate(fine_layers):
                 L = self._plan["fine"][i]
                 last = i == len(fine_layers) - 1
@@ -585,76 +751,150 @@ class OnePosePlus_model(nn.Module):
                 cur = 1 - cur
         expec_f = torch.empty((M, 3), dtype=f32, device=dev)
         mkpts_f = torch.empty((M, 2), dtype=f32, device=dev)
-        fine_scale = float(data["q_hw_i"][0] / data["q_hw_f"][0])
-        ops.fine_match(x32, data["mkpts_query_c"], data["b_ids"], img_scale, expec_f, mkpts_f, M,
-                       fine_scale)
-        data.update({"expec_f": expec_f, "mkpts_query_f": mkpts_f})
+        fine_scale = float(q_hw_i[0] / hf)
+        ops.fine_match(x32, mkc, b_ids, img_scale, expec_f, mkpts_f, M, fine_scale)
+        out.update({"expec_f": expec_f, "mkpts_query_f": mkpts_f})
+
+    # ------------------------------------------------------------------ input checks
+    def _check_inputs(self, data):
+        """Shape / dtype validation of the reference data dict (the kernels index raw pointers:
+        a wrong batch or point count would read out of bounds instead of raising like PyTorch)."""
+        img = data["query_image"]
+        if not torch.is_tensor(img) or not img.is_cuda:
+            raise RuntimeError("OnePosePlus_model (B200) has no CPU path: move the model and data to "
+                               "a CUDA device")
+        if img.dim() != 4 or img.shape[1] != 1:
+            raise ValueError(f"query_image must be [B, 1, H, W], got {tuple(img.shape)}")
+        if img.dtype != torch.uint8 and not img.is_floating_point():
+            raise TypeError(f"query_image must be floating point in [0, 1] or uint8, got {img.dtype}")
+        B, _, H, W = img.shape
+        if H % 8 or W % 8 or H < 16 or W < 16:
+            raise ValueError("query_image height/width must be multiples of 8 (>= 16)")
+        if self.dense_pos_encoding is not None:
+            mh, mw = self.dense_pos_encoding.pe.shape[2:]
+            if H // 8 > mh or W // 8 > mw:
+                raise ValueError(f"image {H}x{W} exceeds positional_encoding.pos_emb_shape {mh}x{mw} (x8)")
+        scale = data.get("query_image_scale")
+        if scale is not None and tuple(scale.shape) != (B, 2):
+            raise ValueError(f"query_image_scale must be [B, 2] = [{B}, 2], got {tuple(scale.shape)}")
+        if "keypoints3d" not in data:
+            if self._bank is None:
+                raise KeyError("data has no 'keypoints3d' and no bank is resident (set_bank)")
+            return img, scale, None
+        kp, dfine = data["keypoints3d"], data["descriptors3d_db"]
+        dco = data["descriptors3d_coarse_db"] if "descriptors3d_coarse_db" in data else dfine
+        if kp.dim() != 3 or kp.shape[2] != 3:
+            raise ValueError(f"keypoints3d must be [B, N, 3], got {tuple(kp.shape)}")
+        N = kp.shape[1]
+        if N < 1:
+            raise ValueError("keypoints3d is empty")
+        for name, t, c in (("descriptors3d_db", dfine, 128 if self.config["fine_matching"]["enable"] else None),
+                           ("descriptors3d_coarse_db", dco, 256)):
+            if t.dim() != 3 or t.shape[2] != N or (c is not None and t.shape[1] != c):
+                raise ValueError(f"{name} must be [B, {c}, N={N}], got {tuple(t.shape)}")
+        for name, t in (("keypoints3d", kp), ("descriptors3d_db", dfine), ("descriptors3d_coarse_db", dco)):
+            if t.shape[0] not in (1, B):
+                raise ValueError(f"{name} has batch {t.shape[0]}, query_image has batch {B}")
+            if not t.is_cuda or t.device != img.device:
+                raise RuntimeError(f"{name} must be on the same CUDA device as query_image")
+        if len({kp.shape[0], dfine.shape[0], dco.shape[0]}) != 1:
+            raise ValueError("keypoints3d / descriptors3d_db / descriptors3d_coarse_db disagree on the batch size")
+        return img, scale, (kp, dco, dfine)
 
     # ------------------------------------------------------------------ forward
     def forward(self, data):
         """Same contract as the reference (OnePosePlusModel.py:96-201): reads query_image,
         keypoints3d, descriptors3d_db, descriptors3d_coarse_db (optional), query_image_scale
         (optional); writes bs, q_hw_i, q_hw_c, q_hw_f, conf_matrix, b_ids, i_ids, j_ids, gt_mask,
-        m_bids, mkpts_3d_db, mkpts_query_c, mconf, W, expec_f, mkpts_query_f; returns None."""
+        m_bids, mkpts_3d_db, mkpts_query_c, mconf, W, expec_f, mkpts_query_f; returns None.
+        Extensions: query_image may be uint8 (x/255 folded into conv1); the bank keys may be
+        absent after set_bank(); a bank given as [1, N, .] tensors or stride-0 expanded views is
+        encoded once for the whole batch."""
         if self.training:
             raise NotImplementedError(
-                "onepose_plus_plus_b200 round 1 builds the inference path only: call .eval() "
+                "onepose_plus_plus_b200 builds the inference path only: call .eval() "
                 "(training/autograd is listed under 'next' in DESIGN.md)")
-        if "query_image_mask" in data:
+        if data.get("query_image_mask") is not None:
             raise NotImplementedError("query_image_mask (cold path, img_pad=False in every shipped "
                                       "config) is not built")
-        img = data["query_image"]
-        if not img.is_cuda:
-            raise RuntimeError("OnePosePlus_model (B200) has no CPU path: move the model and data to "
-                               "a CUDA device")
+        img, img_scale, bank_raw = self._check_inputs(data)
+        self._fwd_count += 1
         # kernels are enqueued on the current stream of the tensors' device
         with torch.no_grad(), torch.cuda.device(img.device):
             dev = img.device
             sig = self._signature()
-            if self._plan is None or self._plan_sig != sig:
+            if self._plan is None or self._plan_sig != sig or self._plan["device"] != dev:
                 self._plan = self._prepare(dev)
+                self._plan["device"] = dev
                 self._plan_sig = sig
-            img = img.contiguous().float()
+            if img.dtype != torch.uint8 and img.dtype != torch.float32:
+                img = img.float()
+            img = img.contiguous()
             B, _, H, W = img.shape
-            if H % 8 or W % 8:
-                raise ValueError("query_image height/width must be multiples of 8")
             data.update({"bs": B, "q_hw_i": img.shape[2:]})
             q2, fine_map, (hc, wc) = self._backbone(img)
             data.update({"q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3])})
-            kraw = data["keypoints3d"]
-            draw = data["descriptors3d_coarse_db"] if "descriptors3d_coarse_db" in data \
-                else data["descriptors3d_db"]
-            N = kraw.shape[1]
-            if draw.shape[1] != 256:
-                raise ValueError("coarse descriptors must be 256-d")
-            pl = 2 if self.split else 1
-            # one bank shared by the whole batch (expanded view, stride 0): encode it once
-            shared = B > 1 and kraw.stride(0) == 0 and draw.stride(0) == 0
-            kpts = kraw.contiguous().float()
-            d3 = self._buf("d3_0", (B, N, pl * 256), torch.float16, dev)
-            d3_shared = None
-            if shared:
-                d3_shared = self._buf("d3_shared_in", (1, N, pl * 256), torch.float16, dev)
-                ops.kpt_encode(kpts[:1].contiguous(), draw[:1].contiguous().float(), self._plan["kpt_mlp"],
-                               self._buf("kpt_stats", (1, 4), torch.float32, dev), d3_shared, self.split)
+            if bank_raw is None:
+                bank = self._resident_bank_state()
             else:
-                ops.kpt_encode(kpts, draw.contiguous().float(), self._plan["kpt_mlp"],
-                               self._buf("kpt_stats", (B, 4), torch.float32, dev), d3, self.split)
-            q2, d3 = self._coarse_transformer(q2, d3, B, hc * wc, N, d3_shared)
-            local = dict(data)
-            local["keypoints3d"] = kpts
-            M, img_scale = self._coarse_matching(q2, d3, local, B, N, hc, wc)
-            for k in ("conf_matrix", "b_ids", "i_ids", "j_ids", "gt_mask", "m_bids", "mkpts_3d_db",
-                      "mkpts_query_c", "mconf"):
-                data[k] = local[k]
-            if not self.config["fine_matching"]["enable"]:
-                data.update({"mkpts_query_f": data["mkpts_query_c"]})
-                return
-            fine_desc = data["descriptors3d_db"]
-            if fine_desc.shape[1] != 128:
-                raise ValueError("fine descriptors (descriptors3d_db) must be 128-d")
-            local = dict(data)
-            local["descriptors3d_db"] = fine_desc.contiguous().float()
-            self._fine(local, fine_map, M, img_scale, wc)
-            for k in ("W", "expec_f", "mkpts_query_f"):
-                data[k] = local[k]
+                kp, dco, dfine = bank_raw
+                # one object for the whole batch ([1, N, .] tensors or stride-0 expanded views)
+                one = kp.shape[0] == 1 or (B > 1 and kp.stride(0) == 0 and dco.stride(0) == 0
+                                           and dfine.stride(0) == 0)
+                if one:
+                    kp, dco, dfine = kp[:1], dco[:1], dfine[:1]
+                bank = self._encode_bank(kp.float().contiguous(), dco.float().contiguous(),
+                                         dfine.float().contiguous(), persistent=False)
+            N = bank["N"]
+            if img_scale is not None:
+                img_scale = img_scale.to(device=dev, dtype=torch.float32).contiguous()
+            q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N)
+            out = {}
+            count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out)
+            M = int(count.item())  # the one host sync of the forward (the reference syncs in torch.where)
+            fine_on = self.config["fine_matching"]["enable"]
+            if fine_on:
+                data["W"] = self.fine_preprocess.W   # fine_preprocess.py:33 (not reached when disabled)
+            if fine_on and M > 0:
+                self._fine(fine_map, bank, (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"]),
+                           M, img_scale, hc, wc, data["q_hw_i"], out)
+            self._publish(data, out, M, dev, fine_on)
+
+    def _publish(self, data, out, M, dev, fine_on):
+        """Write the reference's output keys (coarse_matching.py:231-241, fine_matching.py:46-55,107-110)."""
+        if out["conf_matrix"] is not None:
+            data["conf_matrix"] = out["conf_matrix"]
+        b_ids = out["b_ids"][:M]
+        data.update({
+            "b_ids": b_ids, "i_ids": out["i_ids"][:M], "j_ids": out["j_ids"][:M],
+            "gt_mask": torch.zeros(M, dtype=torch.bool, device=dev),
+            "m_bids": b_ids, "mkpts_3d_db": out["mkpts_3d_db"][:M], "mkpts_query_c": out["mkpts_query_c"][:M],
+            "mconf": out["mconf"][:M],
+        })
+        if not fine_on:
+            data["mkpts_query_f"] = data["mkpts_query_c"]
+        elif M == 0:
+            data.update({"expec_f": torch.empty(0, 3, device=dev), "mkpts_query_f": data["mkpts_query_c"]})
+        else:
+            data.update({"expec_f": out["expec_f"][:M], "mkpts_query_f": out["mkpts_query_f"][:M]})
+
+
+class LazyConfMatrix:
+    """Handle stored in data["conf_matrix"] when `model.conf_matrix_mode == "lazy"`: the dual-softmax
+    statistics of the forward are kept, the 4 B x N x S bytes of the matrix are only written when
+    somebody asks (`.materialize()` / `torch.as_tensor(handle.materialize())`).  Valid until the
+    model's next forward (it reads the model's workspace)."""
+
+    def __init__(self, model, d3, q2, lse_pt, lse_px, B, N, S, scale):
+        self._model, self._args = model, (d3, q2, lse_pt, lse_px, B, N, S, scale)
+        self._epoch = model._fwd_count
+        self.shape = torch.Size((B, N, S))
+        self._value = None
+
+    def materialize(self):
+        if self._value is None:
+            if self._model._fwd_count != self._epoch:
+                raise RuntimeError("LazyConfMatrix is stale: the model ran another forward since")
+            with torch.no_grad(), torch.cuda.device(self._args[1].device):
+                self._value = self._model._materialize_conf(*self._args)
+        return self._value

@@ -36,6 +36,20 @@ def _chk(t, dtype, name):
         raise ValueError(f"{name} must be contiguous")
 
 
+def conv1_gemm(image, w64, a_buf, out, split):
+    """conv1 7x7/2 + folded BN + ReLU as im2col + ONE 64-wide tcgen05 K chunk (bias rides in K column
+    49).  image fp32 or uint8 [B,1,H,W]; w64 fp16 [C, planes*64]; a_buf fp16 [B*H/2*W/2, planes*64]."""
+    B, _, H, W = image.shape
+    if image.dtype not in (torch.float32, torch.uint8):
+        raise TypeError(f"image: expected float32 or uint8, got {image.dtype}")
+    call("opp_conv1_im2col", ptr(image), int(image.dtype == torch.uint8), ptr(a_buf), B, H, W, int(split),
+         stream())
+    rows = B * (H // 2) * (W // 2)
+    call("opp_linear_act_f16", ptr(a_buf), 64, None, 0, ptr(w64), ptr(out), rows, w64.shape[0], 1,
+         (w64.shape[0] + 31) // 32 * 32, int(split), stream())
+    return out
+
+
 def conv1_7x7(image, w_t, bias, out, split):
     B, _, H, W = image.shape
     _chk(image, torch.float32, "image")
@@ -45,16 +59,16 @@ def conv1_7x7(image, w_t, bias, out, split):
 
 
 def conv2d_nhwc(x, w, bias, out, ksize, stride, split, act=0, resid=None, slope=0.01, tok=None,
-                pe=None):
+                pe=None, up=None):
     """x NHWC fp16 [B,H,W,planes*Cin_pad]; w fp16 [Cout_pad, planes*k*k*Cin_pad];
-    act 0 none / 1 relu / 2 leaky."""
+    act 0 none / 1 relu / 2 leaky; up: coarser NHWC map added as bilinear x2 (align_corners)."""
     _chk(x, torch.float16, "x")
     _chk(w, torch.float16, "w")
     _chk(resid, torch.float16, "resid")
     B, H, W, C = x.shape
     planes = 2 if split else 1
     call("opp_conv2d_nhwc", ptr(x), ptr(w), ptr(bias), ptr(resid), ptr(out), B, H, W, C // planes,
-         w.shape[0], ksize, stride, act, float(slope), ptr(tok), ptr(pe), int(split), stream())
+         w.shape[0], ksize, stride, act, float(slope), ptr(tok), ptr(pe), ptr(up), int(split), stream())
     return out
 
 
@@ -77,9 +91,10 @@ def kpt_encode(kpts, desc, mlp, stats, tok, split):
          ptr(w3), ptr(b3), ptr(w4), ptr(b4), ptr(tok), B, N, int(split), stream())
 
 
-def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None):
+def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None, batches=1, a0_shared=False):
     """a_i fp16 [rows, planes*k_i]; w fp16 [n, planes*(k0+k1)]; out fp16 [rows, planes*n]
-    (out_split=False with split=True: split operands, single-plane output [rows, n])."""
+    (out_split=False with split=True: split operands, single-plane output [rows, n]).
+    batches > 1: rows is per batch; a0_shared: a0 is [1, rows, ..] shared by every batch."""
     _chk(a0, torch.float16, "a0")
     _chk(a1, torch.float16, "a1")
     _chk(w, torch.float16, "w")
@@ -90,19 +105,23 @@ def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None):
         call("opp_linear_act_f16_out1", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
              act_cols, stream())
         return out
+    if batches > 1 or a0_shared:
+        call("opp_linear_act_f16_b", ptr(a0), k0, int(a0_shared), ptr(a1), k1, ptr(w), ptr(out), batches, rows,
+             w.shape[0], act, act_cols, int(split), stream())
+        return out
     call("opp_linear_act_f16", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
          act_cols, int(split), stream())
     return out
 
 
-def linear_q(x16, wq, ksum, out, batches, rows, v_len, split, eps=1e-6):
+def linear_q(x16, wq, ksum, out, batches, rows, v_len, split, eps=1e-6, x_shared=False):
     call("opp_linear_q_f16", ptr(x16), ptr(wq), ptr(ksum), ptr(out), batches, rows, wq.shape[0],
-         float(v_len), float(eps), int(split), stream())
+         float(v_len), float(eps), int(split), int(x_shared), stream())
     return out
 
 
 def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=None, out16=None,
-              out32=None, eps=1e-5):
+              out32=None, eps=1e-5, resid_shared=False):
     _chk(a0, torch.float16, "a0")
     _chk(w, torch.float16, "w")
     _chk(resid, torch.float16, "resid")
@@ -111,7 +130,8 @@ def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=Non
     k1 = a1.shape[-1] // planes if a1 is not None else 0
     n = w.shape[-2]
     call("opp_linear_ln", ptr(a0), k0, ptr(a1), k1, ptr(w), int(w_batched), ptr(gamma), ptr(beta),
-         float(eps), ptr(resid), ptr(out16), ptr(out32), batches, rows, n, int(split), stream())
+         float(eps), ptr(resid), int(resid_shared), ptr(out16), ptr(out32), batches, rows, n, int(split),
+         stream())
 
 
 def kv_chunks(s):
@@ -168,23 +188,24 @@ def sim_conf_colmax(a, b, lse_own, lse_other, conf, batches, rows, cols, k, scal
 
 
 def match_select_colmax(pt_val, pt_idx, colmax, kpts, img_scale, batch, l, hc, wc, thr, border, cell,
-                        scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count):
+                        scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count, bank_shared=False):
     call("opp_match_select_colmax", ptr(pt_val), ptr(pt_idx), ptr(colmax), ptr(kpts), ptr(img_scale),
          batch, l, hc, wc, float(thr), int(border), float(cell), ptr(scratch), ptr(b_ids),
-         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), stream())
+         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), int(bank_shared), stream())
 
 
 def match_select(pt_val, pt_idx, px_idx, kpts, img_scale, batch, l, hc, wc, thr, border, cell,
-                 scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count):
+                 scratch, b_ids, i_ids, j_ids, mconf, mkpts3d, mkpts_c, count, bank_shared=False):
     call("opp_match_select", ptr(pt_val), ptr(pt_idx), ptr(px_idx), ptr(kpts), ptr(img_scale),
          batch, l, hc, wc, float(thr), int(border), float(cell), ptr(scratch), ptr(b_ids),
-         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), stream())
+         ptr(i_ids), ptr(j_ids), ptr(mconf), ptr(mkpts3d), ptr(mkpts_c), ptr(count), int(bank_shared), stream())
 
 
-def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stride, n, split):
+def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stride, n, split,
+                bank_shared=False):
     _chk(desc3d, torch.float32, "descriptors3d_db")
     call("opp_fine_gather", ptr(fine), ptr(desc3d), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x32),
-         ptr(x16), m, hf, wf, wc, stride, n, int(split), stream())
+         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), stream())
 
 
 def fine_attention(qkv, msg, m, cross, split, eps=1e-6):

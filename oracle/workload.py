@@ -151,6 +151,34 @@ def planted_workload(sd, h=512, w=512, n_points=5000, n_planted=3000, batch=1, a
     return data, meta
 
 
+@torch.no_grad()
+def hetero_workload(sd, h=256, w=320, n_points=1500, n_planted=700, batch=3, seed=5):
+    """Batch whose elements are DIFFERENT objects: every batch element has its own image, its own
+    keypoint cloud (different extents and offsets), its own planted descriptor banks and its own
+    query_image_scale — exercises the per-batch indexing (desc[b], kpts[b], img_scale[b]) and the
+    reference quirk of per-batch mean with batch-0 extents (normalize.py:16-26), which a shared bank
+    cannot see.  Each element is planted on its own image with the keypoint encoding it receives
+    INSIDE the batch."""
+    parts = [planted_workload(sd, h, w, n_points, n_planted, batch=1, seed=seed + 10 * b)[0] for b in range(batch)]
+    g = torch.Generator().manual_seed(seed + 999)
+    kpts = torch.cat([p["keypoints3d"] * (1.0 + 0.35 * b) + 0.2 * b for b, p in enumerate(parts)], 0)
+    # re-plant the coarse descriptors with the encoding each element gets inside the batch
+    kenc_batch = oracle.keypoint_encoding(sd, oracle.normalize_3d_keypoints(kpts), torch.zeros(batch, 256, n_points))
+    dcs = []
+    for b, p in enumerate(parts):
+        kenc_alone = oracle.keypoint_encoding(sd, oracle.normalize_3d_keypoints(p["keypoints3d"]),
+                                              torch.zeros(1, 256, n_points))
+        dcs.append(p["descriptors3d_coarse_db"] + kenc_alone - kenc_batch[b:b + 1])
+    scales = 0.7 + 0.8 * torch.rand(batch, 2, generator=g)
+    return {
+        "query_image": torch.cat([p["query_image"] for p in parts], 0),
+        "keypoints3d": kpts.contiguous(),
+        "descriptors3d_db": torch.cat([p["descriptors3d_db"] for p in parts], 0),
+        "descriptors3d_coarse_db": torch.cat(dcs, 0),
+        "query_image_scale": scales,
+    }
+
+
 def random_workload(h=512, w=512, n_points=5000, batch=1, seed=1):
     """BASELINE.json config 1 taken literally: random image, random descriptors (yields M = 0)."""
     g = torch.Generator().manual_seed(seed)

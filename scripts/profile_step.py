@@ -18,6 +18,8 @@ m.load_state_dict(sd)
 m = m.eval().cuda()
 data, _ = workload.planted_workload(sd, 512, 512, 5000, 3000, batch=B)
 d = {k: v.cuda() for k, v in data.items()}
+for k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db"):   # one object shared by the batch
+    d[k] = d[k][:1].contiguous()
 for _ in range(2):
     m(dict(d))
 torch.cuda.synchronize()

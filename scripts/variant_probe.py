@@ -42,6 +42,8 @@ def golden(label):
     for case in golden_io.cases():
         data, z = golden_io.load(case)
         got = parity.run_cuda(data)
+        if not torch.is_tensor(got.get("conf_matrix")):
+            got["conf_matrix"] = got["conf_matrix"].materialize()
         res["golden"][f"{case}[{label}]"] = parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
 
 
@@ -106,17 +108,18 @@ def timing(label):
 # options: C-ABI switches (opp_set_option) except "colmax" / "lse_cols", host-flow switches of the
 # model (column maxima of conf / column log-sum-exp from the first pass instead of a second GEMM).  Every config
 # starts from the defaults; its label lists the options it turns on.
-EXPERIMENTAL_CHECK = {"upsample_rows": "upsample_rows", "conv1_px4": "conv1_px4", "colmax": "sim_colmax",
-                      "lse_cols": "sim_lse_cols", "fine_attn_vec": "fine_attn_vec", "kv1": "kv_single_plane"}
-DEFAULTS = {"upsample_rows": 0, "conv1_px4": 0, "colmax": 0, "lse_cols": 0, "fine_attn_vec": 0, "kv1": 0}
-MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols", "kv1": "kv_single_plane"}
+EXPERIMENTAL_CHECK = {"fine_attn_vec": "fine_attn_vec", "kv1": "kv_single_plane"}
+DEFAULTS = {"colmax": 1, "lse_cols": 1, "fine_attn_vec": 0, "kv1": 0, "lazy": 0}
+MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols", "kv1": "kv_single_plane",
+              "lazy": "conf_matrix_mode"}
+ATTR_VALUE = {"lazy": {0: "eager", 1: "lazy"}}
 
 
 def apply(cfg):
     for k, v in {**DEFAULTS, **cfg}.items():
         if k in MODEL_ATTR:
             try:
-                setattr(parity.cuda_model(), MODEL_ATTR[k], bool(v))
+                setattr(parity.cuda_model(), MODEL_ATTR[k], ATTR_VALUE[k][v] if k in ATTR_VALUE else bool(v))
             except RuntimeError:   # no CUDA device (dry run of the script logic)
                 pass
         else:
@@ -125,12 +128,12 @@ def apply(cfg):
 
 first = True
 for cfg in configs:
-    label = ",".join(f"{k}={v}" for k, v in cfg.items() if v) or "default"
+    label = ",".join(f"{k}={v}" for k, v in cfg.items()) or "default"
     if first:   # the tcgen05 epilogues do not depend on the runtime options
         apply({})
         for name in ("linear_ln", "conv", "linear_act", "linear_q", "sim"):
             guarded(name, kernel_checks.CHECKS[name])
-        guarded("conv1_ragged", kernel_checks.EXPERIMENTAL["conv1_ragged"])
+        guarded("conv1_gemm", kernel_checks.CHECKS["conv1_gemm"])
         guarded("c5_shape", c5_shape)
         first = False
     for k, v in cfg.items():
@@ -138,8 +141,6 @@ for cfg in configs:
             guarded(f"{EXPERIMENTAL_CHECK[k]}[{label}]", kernel_checks.EXPERIMENTAL[EXPERIMENTAL_CHECK[k]])
     apply(cfg)
     guarded(f"kv_state[{label}]", kernel_checks.check_kv_state)
-    guarded(f"conv1[{label}]", kernel_checks.CHECKS["conv1"])
-    guarded(f"upsample[{label}]", kernel_checks.CHECKS["upsample"])
     guarded(f"golden[{label}]", lambda label=label: golden(label))
     guarded(f"timing[{label}]", lambda label=label: timing(label))
 apply({})

