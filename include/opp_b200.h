@@ -33,32 +33,20 @@ int opp_version(void);
 const char* opp_last_error(void);
 int opp_num_sms(void);
 
-/* Process-wide kernel selection switches (no reference counterpart: the reference picks its
- * kernels inside PyTorch).
- *   "kv_mma":       1 = opp_kv_partial runs the mma.sync tensor-core stream, 0 = the SIMT fp32
- *                   kernel (initial value: $OPP_KV_MMA, else the build default)
- *   "conv1_staged": 1 = opp_conv1_7x7 writes its output through a per-warp transpose buffer
- *                   (8 pixels x 64 B per store instruction), 0 = one 16 B store per pixel
- *                   (initial value: $OPP_CONV1_STAGED, else the build default)
- *   "conv1_px4":    1 = opp_conv1_7x7 computes 4 adjacent output pixels per thread (one pair of
- *                   weight loads per 32 FMAs); takes precedence over "conv1_staged"
- *                   (initial value: $OPP_CONV1_PX4, else 0 — not yet validated on a GPU)
- *   "fine_attn_vec": 1 = opp_fine_attention moves its rows with 16-byte accesses
- *                   (initial value: $OPP_FINE_ATTN_VEC, else 0 — not yet validated on a GPU)
- *   "upsample_rows": 1 = opp_upsample2x_add uses the division-free row-mapped kernel
- *                   (initial value: $OPP_UPSAMPLE_ROWS, else 0 — not yet validated on a GPU)
+/* Process-wide integer switches (no reference counterpart: the reference picks its kernels inside
+ * PyTorch): selection between alternative kernels behind one entry point while a new variant is
+ * validated.  Current names:
+ *   "gemm_w_resident": 1 = token GEMMs whose W tile fits keep it in shared memory across M tiles
+ *                      (initial value: $OPP_GEMM_W_RESIDENT, else 0)
  * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */
 int opp_set_option(const char* name, int value);
 int opp_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------
- * Backbone — ResNetFPN_8_2.forward (backbone/resnet.py:141-164), BatchNorm folded on the host
+ * Backbone — ResNetFPN_8_2.forward (backbone/resnet.py:141-164), BatchNorm folded on the host;
+ * every convolution runs on the tcgen05 engine, the two bilinear x2 upsample-adds of the FPN are
+ * epilogues of the lateral 1x1 convolutions
  * ---------------------------------------------------------------------------------------- */
-
-/* conv1 7x7 stride 2 pad 3, 1 -> c_out channels, + folded bn1 + ReLU (resnet.py:101-103,143).
- * image fp32 [B][1][H][W]; w_t fp32 [49][c_out] (tap-major); out NHWC fp16 [B][H/2][W/2][c_out] */
-int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
-                  int h, int w, int c_out, int split, opp_stream_t stream);
 
 /* conv1 on the tensor-core engine: im2col of the 7x7 stride-2 pad-3 windows (resnet.py:101-103).
  * a_out fp16 [B*H/2*W/2][planes*64]: row = (49 taps, 1.0, 14 zeros) of one output pixel, so that
@@ -88,11 +76,6 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
                     void* out, int batch, int in_h, int in_w, int c_in_pad, int c_out_pad,
                     int ksize, int stride, int act, float slope, void* tok, const float* pe,
                     const void* up, int split, opp_stream_t stream);
-
-/* out = a + bilinear_x2(b), align_corners=True (resnet.py:151-152,155-156).
- * a, out NHWC fp16 [B][2h][2w][c]; b NHWC fp16 [B][h][w][c]. out may alias a. */
-int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
-                       int split, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * 3D keypoint encoding — normalize_3d_keypoints (utils/normalize.py:16-26) +
@@ -125,24 +108,38 @@ int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const voi
 
 /* Batched form: a0 / a1 / out are [batches][rows][..]; with a0_shared != 0 the first operand is
  * [1][rows][k0] — one object's tokens shared by every image of the batch (the 3D side of the
- * first cross layer, whose x is image-independent: transformer.py:148-159) — and is read once. */
+ * first cross layer, whose x is image-independent: transformer.py:148-159) — and is read once.
+ * row_mask (uint8 [batches*rows], or NULL): rows whose mask is 0 are written as zeros — padded
+ * source positions of query_image_mask (linear_attention.py:51-53: K and V are multiplied by kv_mask). */
 int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, int k1, const void* w,
                          void* out, int batches, long long rows, int n, int act, int act_cols,
-                         int split, opp_stream_t stream);
+                         int split, const unsigned char* row_mask, opp_stream_t stream);
 
 /* Same GEMM with split (hi|lo) operands but a single-plane fp16 output [rows][n]: for the K'/V rows
  * of the linear-attention state, whose consumer sums over thousands of rows (built for the next
  * GPU session; selected by $OPP_B200_KV1). */
 int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
-                            long long rows, int n, int act, int act_cols, opp_stream_t stream);
+                            long long rows, int n, int act, int act_cols, const unsigned char* row_mask,
+                            opp_stream_t stream);
+
+/* opp_linear_act_f16 / opp_linear_ln with a device-side row count: rows = *count * rows_per_count
+ * (clamped to cap_rows, the size the operands were allocated for). */
+int opp_linear_act_f16_dyn(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
+                           long long cap_rows, const int* count, int rows_per_count, int n, int act,
+                           int act_cols, int split, opp_stream_t stream);
+int opp_linear_ln_dyn(const void* a0, int k0, const void* a1, int k1, const void* w, const float* gamma,
+                      const float* beta, float eps, const void* resid, void* out16, float* out32,
+                      long long cap_rows, const int* count, int rows_per_count, int n, int split,
+                      opp_stream_t stream);
 
 /* q_proj + feature map + normaliser (transformer.py:77, linear_attention.py:45,58):
  * out = Q * v_len / (Q . ksum_head + eps), Q = elu(x @ wq^T) + 1, heads of 32 channels.
  * x fp16 [B][rows][256] (or [1][rows][256] with x_shared != 0); ksum fp32 [B][256];
- * out fp16 [B][rows][256] */
+ * out fp16 [B][rows][256]; row_mask uint8 [B*rows] or NULL: Q = 0 on padded query positions
+ * (linear_attention.py:49-50) */
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
                      int rows, int d_model, float v_len, float eps, int split, int x_shared,
-                     opp_stream_t stream);
+                     const unsigned char* row_mask, opp_stream_t stream);
 
 /* y = LayerNorm(concat_K(a0,a1) @ w^T) [+ resid]  (transformer.py:85-94).
  * w fp16 [n][planes*k] or, when w_batched, [B][n][planes*k] (the per-image
@@ -192,12 +189,15 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
 
 /* opp_sim_lse for rows = 3D points that also produces the COLUMN statistics (saves the second lse
  * pass): col_m/col_s fp32 [B][ceil(rows/32)][cols] = per 32-row group (max, sum exp(x - max)) of
- * every column; opp_lse_col_finalize merges the groups into lse[b][s] = logsumexp_l sim[b, l, s]. */
+ * every column; opp_lse_col_finalize merges the groups into lse[b][s] = logsumexp_l sim[b, l, s].
+ * col_mask (uint8 [B][cols] or NULL) = query_image_mask at coarse resolution: masked columns get
+ * sim - 1e9 (coarse_matching.py:108-114), i.e. they drop out of every row's softmax, and
+ * opp_lse_col_finalize writes lse = +inf for them so that conf is exactly 0 there. */
 int opp_sim_lse_cols(const void* a, const void* b, float* part_m, float* part_s, float* col_m,
                      float* col_s, int batches, int rows, int cols, int k, float scale, int split,
-                     opp_stream_t stream);
+                     const unsigned char* col_mask, opp_stream_t stream);
 int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
-                         int cols, opp_stream_t stream);
+                         int cols, const unsigned char* col_mask, opp_stream_t stream);
 
 /* opp_sim_conf for rows = 3D points with the column maxima folded in (saves the second conf pass):
  * colmax uint32 [B][cols] receives the float bits of max_l conf[b, l, s] (zeroed inside, then
@@ -239,6 +239,12 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
  * FineMatching (utils/fine_matching.py:28-110)
  * ---------------------------------------------------------------------------------------- */
 
+/* Every fine-level entry point takes `count_dev`: NULL = `m` is the exact number of matches (known
+ * on the host); otherwise `m` is the CAPACITY the buffers were sized for and the kernels read the
+ * real match count from *count_dev (int32, device; written by opp_match_select*), so the whole
+ * forward can be enqueued / captured in a CUDA graph without the host learning M first (the
+ * reference synchronises in torch.where: coarse_matching.py:170). */
+
 /* For match m: row 26m = descriptors3d_db[b, :, i]; rows 26m+1+ww = the 5x5 window (ww = ky*5+kx)
  * of the fine map centred on fine pixel (stride*jy, stride*jx), zero outside the map.
  * fine NHWC fp16 [B][hf][wf][planes*128]; desc3d fp32 [B][128][n];
@@ -247,21 +253,41 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
                     int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
-                    opp_stream_t stream);
+                    const int* count_dev, opp_stream_t stream);
 
 /* Linear attention for the 1 + 25 tokens of each match (linear_attention.py:29-61 with
  * L,S in {1,25}).  qkv fp16 [26 M][planes*384] = (elu(q)+1 | elu(k)+1 | v), 8 heads of 16.
  * cross = 0: self layer (each sequence attends to itself); 1: cross layer, both directions from
  * the pre-update tensors (transformer.py:154-159).  msg fp16 [26 M][planes*128] */
 int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, int split,
-                       opp_stream_t stream);
+                       const int* count_dev, opp_stream_t stream);
 
 /* Correlation softmax + expectation + std (fine_matching.py:78-94) and sub-pixel coordinates
  * (fine_matching.py:96-110).  x32 fp32 [26 M][128]; img_scale fp32 [B][2] or NULL;
  * expec_f fp32 [M][3]; mkpts_f fp32 [M][2] */
 int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_ids,
                    const float* img_scale, float* expec_f, float* mkpts_f, int m, float fine_scale,
-                   opp_stream_t stream);
+                   const int* count_dev, opp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pose from the matches — ransac_PnP (src/utils/metric_utils.py:121-204: cv2.solvePnPRansac with
+ * EPnP, iterationsCount 10000, reprojectionError `pnp_reprojection_error`, per frame on the CPU
+ * after a D2H copy; callers: compute_query_pose_errors metric_utils.py:207-292, demo.py:132)
+ * ---------------------------------------------------------------------------------------- */
+
+/* Batched RANSAC-PnP, one CTA per image, consuming the matcher's output lists in place.
+ *   pts3d fp32 [m][3] (mkpts_3d_db), pts2d fp32 [m][2] (mkpts_query_f), m_bids int64 [m] ascending
+ *   (the matches of image b are the run m_bids == b); intrinsics fp32 [batch][3][3];
+ *   scale: point-cloud rescale (3D points are multiplied by it, t is divided by it: metric_utils.py:179,193)
+ *   reproj_thr: inlier threshold in pixels; hypotheses: P3P minimal samples per image;
+ *   seed: RNG seed (counter based: results are reproducible and independent of scheduling);
+ *   refine_rounds: local-optimisation rounds (Gauss-Newton on the inliers + inlier re-selection)
+ * Outputs: poses fp32 [batch][3][4] = [R | t] (identity when the image fails), n_inliers int32
+ * [batch], inlier_mask uint8 [m], status int32 [batch] (1 = pose found from >= 4 inliers). */
+int opp_pnp_ransac(const float* pts3d, const float* pts2d, const long long* m_bids, int m,
+                   const float* intrinsics, int batch, float scale, float reproj_thr, int hypotheses,
+                   unsigned seed, int refine_rounds, float* poses, int* n_inliers,
+                   unsigned char* inlier_mask, int* status, opp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@
 (src/models/OnePosePlus/OnePosePlusModel.py) and runs on hand-written CUDA kernels through the
 C ABI in ``include/opp_b200.h``.
 """
-from .model import OnePosePlus_model, build_backbone  # noqa: F401
+from .model import LazyConfMatrix, OnePosePlus_model, build_backbone  # noqa: F401
+from . import pnp  # noqa: F401  (device-side RANSAC-PnP front end: metric_utils.ransac_PnP)
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"

@@ -24,31 +24,32 @@ P, I, L, F = c_void_p, c_int, c_longlong, c_float
 
 # name -> argtypes; must mirror include/opp_b200.h exactly (tests check every symbol resolves)
 SIGNATURES = {
-    "opp_conv1_7x7": [P, P, P, P, I, I, I, I, I, P],
     "opp_conv2d_nhwc": [P, P, P, P, P, I, I, I, I, I, I, I, I, F, P, P, P, I, P],
     "opp_conv1_im2col": [P, I, P, I, I, I, I, P],
-    "opp_upsample2x_add": [P, P, P, I, I, I, I, I, P],
     "opp_kpt_stats": [P, P, I, I, P],
     "opp_kpt_encode": [P] * 12 + [I, I, I, P],
     "opp_linear_act_f16": [P, I, P, I, P, P, L, I, I, I, I, P],
-    "opp_linear_act_f16_out1": [P, I, P, I, P, P, L, I, I, I, P],
-    "opp_linear_act_f16_b": [P, I, I, P, I, P, P, I, L, I, I, I, I, P],
-    "opp_linear_q_f16": [P, P, P, P, I, I, I, F, F, I, I, P],
+    "opp_linear_act_f16_out1": [P, I, P, I, P, P, L, I, I, I, P, P],
+    "opp_linear_act_f16_b": [P, I, I, P, I, P, P, I, L, I, I, I, I, P, P],
+    "opp_linear_q_f16": [P, P, P, P, I, I, I, F, F, I, I, P, P],
     "opp_linear_ln": [P, I, P, I, P, I, P, P, F, P, I, P, P, I, L, I, I, P],
     "opp_kv_partial": [P, P, I, I, I, I, P],
     "opp_kv_finalize": [P, P, P, P, I, I, I, F, I, P],
     "opp_sim_lse": [P, P, P, P, I, I, I, I, F, I, P],
     "opp_lse_finalize": [P, P, P, L, I, P],
     "opp_sim_conf": [P, P, P, P, I, P, P, P, I, I, I, I, F, I, P],
-    "opp_sim_lse_cols": [P, P, P, P, P, P, I, I, I, I, F, I, P],
-    "opp_lse_col_finalize": [P, P, P, I, I, I, P],
+    "opp_sim_lse_cols": [P, P, P, P, P, P, I, I, I, I, F, I, P, P],
+    "opp_lse_col_finalize": [P, P, P, I, I, I, P, P],
     "opp_sim_conf_colmax": [P, P, P, P, P, P, P, P, I, I, I, I, F, I, P],
     "opp_best_finalize": [P, P, P, P, L, I, P],
     "opp_match_select": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, I, P],
     "opp_match_select_colmax": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, I, P],
-    "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P],
-    "opp_fine_attention": [P, P, I, I, F, I, P],
-    "opp_fine_match": [P, P, P, P, P, P, I, F, P],
+    "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P],
+    "opp_fine_attention": [P, P, I, I, F, I, P, P],
+    "opp_fine_match": [P, P, P, P, P, P, I, F, P, P],
+    "opp_linear_act_f16_dyn": [P, I, P, I, P, P, L, P, I, I, I, I, I, P],
+    "opp_linear_ln_dyn": [P, I, P, I, P, P, P, F, P, P, P, L, P, I, I, I, P],
+    "opp_pnp_ransac": [P, P, P, I, P, I, F, F, I, ctypes.c_uint, I, P, P, P, P, P],
 }
 PLAIN = {"opp_version": ([], c_int), "opp_num_sms": ([], c_int), "opp_sim_tiles": ([I], c_int),
          "opp_kv_chunks": ([I], c_int),

@@ -98,7 +98,7 @@ static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long ro
   return make_map(map, ptr, 3, dims, str, box);
 }
 
-template <int A_MODE, class Epi>
+template <int A_MODE, class Epi, bool DYN = false>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream) {
   s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair);
@@ -117,7 +117,7 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
     if (cap > 1 && s.stages > cap) s.stages = cap;
   }
   const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair);
-  auto kern = gemm_kernel<A_MODE, Epi>;
+  auto kern = gemm_kernel<A_MODE, Epi, DYN>;
   // function attributes are per device: set once per (template instantiation, device)
   static unsigned long long attr_done = 0;
   int dev = 0;
@@ -257,12 +257,12 @@ const char* opp_last_error(void) { return opp::last_error(); }
 int opp_linear_act_f16(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
                        long long rows, int n, int act, int act_cols, int split,
                        opp_stream_t stream) {
-  return opp_linear_act_f16_b(a0, k0, 0, a1, k1, w, out, 1, rows, n, act, act_cols, split, stream);
+  return opp_linear_act_f16_b(a0, k0, 0, a1, k1, w, out, 1, rows, n, act, act_cols, split, nullptr, stream);
 }
 
 int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, int k1, const void* w,
                          void* out, int batches, long long rows, int n, int act, int act_cols,
-                         int split, opp_stream_t stream) {
+                         int split, const unsigned char* row_mask, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, batches, rows, n, split, 16, a0_shared);
@@ -270,7 +270,7 @@ int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, 
   OPP_REQUIRE(out, "null output");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
   EpiStoreF16::Params ep{(__half*)out, (long long)n * (split ? 2 : 1), split ? n : 0, act,
-                         act_cols};
+                         act_cols, row_mask};
   return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
 }
 
@@ -279,20 +279,57 @@ int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, 
 // the 2^-12 output rounding is harmless while the row is half as long in HBM.  Same kernel as
 // opp_linear_act_f16 (EpiStoreF16 with out_lo = 0).
 int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
-                            long long rows, int n, int act, int act_cols, opp_stream_t stream) {
+                            long long rows, int n, int act, int act_cols, const unsigned char* row_mask,
+                            opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, 1);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
-  EpiStoreF16::Params ep{(__half*)out, (long long)n, 0, act, act_cols};
+  EpiStoreF16::Params ep{(__half*)out, (long long)n, 0, act, act_cols, row_mask};
   return launch<A_ROWS, EpiStoreF16>(maps, s, ep, (cudaStream_t)stream);
+}
+
+// Same GEMMs with a device-side row count: rows = *count * rows_per_count (<= cap_rows, the size
+// the buffers were allocated for).  Used by the fine stage, whose row count is the number of coarse
+// matches found on the device.
+int opp_linear_act_f16_dyn(const void* a0, int k0, const void* a1, int k1, const void* w, void* out,
+                           long long cap_rows, const int* count, int rows_per_count, int n, int act,
+                           int act_cols, int split, opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, cap_rows, n, split);
+  if (rc) return rc;
+  OPP_REQUIRE(out && count && rows_per_count > 0, "bad dynamic-row arguments");
+  OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
+  s.rows_dev = count;
+  s.rows_mult = rows_per_count;
+  EpiStoreF16::Params ep{(__half*)out, (long long)n * (split ? 2 : 1), split ? n : 0, act, act_cols, nullptr};
+  return launch<A_ROWS, EpiStoreF16, true>(maps, s, ep, (cudaStream_t)stream);
+}
+
+int opp_linear_ln_dyn(const void* a0, int k0, const void* a1, int k1, const void* w, const float* gamma,
+                      const float* beta, float eps, const void* resid, void* out16, float* out32,
+                      long long cap_rows, const int* count, int rows_per_count, int n, int split,
+                      opp_stream_t stream) {
+  TensorMaps maps;
+  GemmShape s;
+  OPP_REQUIRE(n == 128 || n == 256, "LayerNorm epilogue needs N in {128,256}, got %d", n);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, cap_rows, n, split);
+  if (rc) return rc;
+  OPP_REQUIRE(gamma && beta && count && rows_per_count > 0, "bad dynamic-row arguments");
+  OPP_REQUIRE(out16 || out32, "no output requested");
+  s.rows_dev = count;
+  s.rows_mult = rows_per_count;
+  EpiLN::Params ep{gamma, beta, eps, (const __half*)resid, 0, (__half*)out16,
+                   (long long)n * (split ? 2 : 1), split ? n : 0, out32};
+  return launch<A_ROWS, EpiLN, true>(maps, s, ep, (cudaStream_t)stream);
 }
 
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
                      int rows, int d_model, float v_len, float eps, int split, int x_shared,
-                     opp_stream_t stream) {
+                     const unsigned char* row_mask, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(d_model == 256, "opp_linear_q_f16 supports d_model 256 (8 heads x 32), got %d",
@@ -301,7 +338,7 @@ int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out
   if (rc) return rc;
   OPP_REQUIRE(ksum && out, "null pointer");
   EpiQ::Params ep{(__half*)out, (long long)d_model * (split ? 2 : 1), split ? d_model : 0, ksum,
-                  v_len, eps};
+                  v_len, eps, row_mask};
   return launch<A_ROWS, EpiQ>(maps, s, ep, (cudaStream_t)stream);
 }
 
@@ -422,13 +459,13 @@ int opp_sim_conf(const void* a, const void* b, const float* lse_own, const float
 
 int opp_sim_lse_cols(const void* a, const void* b, float* part_m, float* part_s, float* col_m,
                      float* col_s, int batches, int rows, int cols, int k, float scale, int split,
-                     opp_stream_t stream) {
+                     const unsigned char* col_mask, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
   int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
   if (rc) return rc;
   OPP_REQUIRE(part_m && part_s && col_m && col_s, "null pointer");
-  EpiLseCol::Params ep{part_m, part_s, scale, col_m, col_s, (rows + 31) / 32};
+  EpiLseCol::Params ep{part_m, part_s, scale, col_m, col_s, (rows + 31) / 32, col_mask};
   return launch<A_ROWS, EpiLseCol>(maps, s, ep, (cudaStream_t)stream);
 }
 

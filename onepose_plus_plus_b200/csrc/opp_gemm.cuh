@@ -98,6 +98,10 @@ struct GemmShape {
   int k_chunks_a0;  // chunks read through maps.a[0]; the rest through maps.a[1]
   int a0_lo, a1_lo; // element offsets of the lo planes of the two A arrays (= their K)
   int a0_shared;    // the first A array is [1][rows][..]: one object shared by every batch element
+  // device-side row count (DYN kernels): rows = *rows_dev * rows_mult, read when the kernel starts;
+  // the host-side `rows` / `m_tiles` then only describe the CAPACITY the tensor maps were built for
+  const int* rows_dev;
+  int rows_mult;
   // A_CONV
   int conv_cchunks; // K chunks per filter tap
   int conv_c;       // padded input channels (multiple of 16); also the lo-plane offset
@@ -298,9 +302,13 @@ struct EpiStoreF16 {
     int out_lo;     // 0 or n_total
     int act;
     int act_cols;   // multiple of 32
+    // padded positions (query_image_mask, linear_attention.py:49-53): rows with row_mask[grow] == 0
+    // are written as zeros (K' and V of a masked source token), or null
+    const unsigned char* row_mask;
   };
   __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    const bool masked = p.row_mask && c.valid && p.row_mask[c.grow] == 0;
     tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int act = g0 < p.act_cols ? p.act : 0;
@@ -310,6 +318,10 @@ struct EpiStoreF16 {
       } else if (act == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = elu_plus_one_fast(v[j]);
+      }
+      if (masked) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
       }
       staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, c.ncols - col);
     });
@@ -329,6 +341,7 @@ struct EpiQ {
     const float* ksum;  // [batches][n_total]
     float v_len;
     float eps;
+    const unsigned char* row_mask;   // Q = 0 on padded query positions (linear_attention.py:49-50), or null
   };
   __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
@@ -336,6 +349,7 @@ struct EpiQ {
     for (int i = c.etid; i < c.ncols; i += 128)
       sts32f(c.smem_s + 4 * i, p.ksum[(long long)c.b * s.n_total + c.n0 + i]);
     epi_sync(c);
+    const bool qmasked = p.row_mask && c.valid && p.row_mask[c.grow] == 0;
     tmem_foreach32(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       float dot = 0.f;
 #pragma unroll
@@ -349,7 +363,7 @@ struct EpiQ {
           dot = fmaf(v[4 * g + j], kk[j], dot);
         }
       }
-      const float z = p.v_len / (dot + p.eps);
+      const float z = qmasked ? 0.f : p.v_len / (dot + p.eps);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] *= z;
       staged_store_h32(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, 32);
@@ -808,6 +822,8 @@ struct EpiLseCol {
     float* col_m;   // [batches][row_groups][n_total]
     float* col_s;
     int row_groups; // ceil(rows / 32)
+    // query_image_mask: columns with col_mask[b][col] == 0 get sim + (-1e9) (coarse_matching.py:108-114), or null
+    const unsigned char* col_mask;
   };
   __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
@@ -815,12 +831,19 @@ struct EpiLseCol {
     const int rg = c.m_tile * 4 + c.q;   // 32-row group of this warp inside the batch
     const bool rg_ok = rg < p.row_groups;
     const long long cbase = ((long long)c.b * p.row_groups + rg) * s.n_total + c.n0;
+    if (p.col_mask) {   // additive column bias (0 / -1e9) of this tile, shared by the epilogue group
+      epi_sync(c);
+      for (int i = c.etid; i < c.ncols; i += 128)
+        sts32f(c.smem_s + 4 * i, p.col_mask[(long long)c.b * s.n_total + c.n0 + i] ? 0.f : -1e9f);
+      epi_sync(c);
+    }
     float m = -INFINITY;
     tmem_foreach32_lean(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] = (c.valid && col + j < c.ncols) ? v[j] * p.scale : -INFINITY;
+        const float cb_ = p.col_mask ? lds32f(c.smem_s + 4 * ((col + j) & 255)) : 0.f;
+        v[j] = (c.valid && col + j < c.ncols) ? v[j] * p.scale + cb_ : -INFINITY;
         m = fmaxf(m, v[j]);
         t[j] = v[j];
       }
@@ -859,7 +882,10 @@ struct EpiLseCol {
     tmem_foreach32_lean(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col + j < c.ncols) sum += fast_exp(v[j] * p.scale - m);
+        if (col + j < c.ncols) {
+          const float cb_ = p.col_mask ? lds32f(c.smem_s + 4 * ((col + j) & 255)) : 0.f;
+          sum += fast_exp((v[j] * p.scale + cb_) - m);
+        }
     });
     if (c.valid) {
       p.part_m[c.grow * (kGroups * s.n_tiles) + kGroups * c.n_tile + c.group] = m;
@@ -944,10 +970,21 @@ struct EpiConfCol {
 // =============================================================================================
 // The kernel
 // =============================================================================================
-template <int A_MODE, class Epi>
+template <int A_MODE, class Epi, bool DYN = false>
 __global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
-gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s,
+gemm_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmShape s_in,
             const typename Epi::Params ep) {
+  // DYN: the number of valid rows lives in device memory (the match count of the coarse stage), so
+  // a whole forward can be enqueued — or captured in a CUDA graph — without a host round trip
+  GemmShape s_dyn;
+  if constexpr (DYN) {
+    s_dyn = s_in;
+    const int r = *s_in.rows_dev * s_in.rows_mult;
+    s_dyn.rows = r < s_in.rows ? r : s_in.rows;
+    s_dyn.m_tiles = (s_dyn.rows + kBlockM - 1) / kBlockM;
+    s_dyn.msup = (s_dyn.m_tiles + s_in.cluster - 1) / s_in.cluster;
+  }
+  const GemmShape& s = DYN ? s_dyn : s_in;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));

@@ -39,15 +39,15 @@ __device__ __forceinline__ uint32_t pnp_hash(uint32_t x) {
   return x;
 }
 
-__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+__host__ __device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
   c[0] = a[1] * b[2] - a[2] * b[1];
   c[1] = a[2] * b[0] - a[0] * b[2];
   c[2] = a[0] * b[1] - a[1] * b[0];
 }
-__device__ __forceinline__ double dot3(const double* a, const double* b) {
+__host__ __device__ __forceinline__ double dot3(const double* a, const double* b) {
   return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
 }
-__device__ __forceinline__ bool normalize3(double* a) {
+__host__ __device__ __forceinline__ bool normalize3(double* a) {
   const double n = sqrt(dot3(a, a));
   if (!(n > 1e-300)) return false;
   a[0] /= n;
@@ -57,7 +57,7 @@ __device__ __forceinline__ bool normalize3(double* a) {
 }
 
 // largest real root of x^3 + a2 x^2 + a1 x + a0
-__device__ double cubic_largest_real(double a2, double a1, double a0) {
+__host__ __device__ double cubic_largest_real(double a2, double a1, double a0) {
   const double p = a1 - a2 * a2 / 3.0;
   const double q = 2.0 * a2 * a2 * a2 / 27.0 - a2 * a1 / 3.0 + a0;
   const double disc = q * q / 4.0 + p * p * p / 27.0;
@@ -77,7 +77,7 @@ __device__ double cubic_largest_real(double a2, double a1, double a0) {
 }
 
 // real roots of A4 x^4 + ... + A0 (Ferrari), each polished with Newton steps; returns the count
-__device__ int solve_quartic(double A4, double A3, double A2, double A1, double A0, double* roots) {
+__host__ __device__ int solve_quartic(double A4, double A3, double A2, double A1, double A0, double* roots) {
   if (!(fabs(A4) > 1e-14)) return 0;
   const double b = A3 / A4, c = A2 / A4, d = A1 / A4, e = A0 / A4;
   const double p = c - 3.0 * b * b / 8.0;
@@ -130,7 +130,7 @@ __device__ int solve_quartic(double A4, double A3, double A2, double A1, double 
 }
 
 // orthonormal frame of a triangle: columns e1 = (Q1-Q0)^, e3 = (e1 x (Q2-Q0))^, e2 = e3 x e1
-__device__ bool tri_frame(const double* Q0, const double* Q1, const double* Q2, double* F) {
+__host__ __device__ bool tri_frame(const double* Q0, const double* Q1, const double* Q2, double* F) {
   double e1[3] = {Q1[0] - Q0[0], Q1[1] - Q0[1], Q1[2] - Q0[2]};
   double w[3] = {Q2[0] - Q0[0], Q2[1] - Q0[1], Q2[2] - Q0[2]};
   double e3[3], e2[3];
@@ -150,7 +150,7 @@ __device__ bool tri_frame(const double* Q0, const double* Q1, const double* Q2, 
 // P3P (Grunert 1841 as restated by Haralick et al. 1994): world points P[3], unit bearings f[3].
 // Calls `visit(pose)` for every admissible solution.
 template <class V>
-__device__ void p3p_grunert(const double (*P)[3], const double (*f)[3], V&& visit) {
+__host__ __device__ void p3p_grunert(const double (*P)[3], const double (*f)[3], V&& visit) {
   double d12[3], d02[3], d01[3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) {

@@ -13,289 +13,7 @@
 namespace opp {
 int num_sms();
 
-// =============================================================================================
-// conv1: 7x7 stride 2 pad 3, 1 -> C channels, folded BN + ReLU   (backbone/resnet.py:101-103,143)
-// One thread per output pixel, all C channels; the 49-tap patch lives in registers, the
-// tap-major weights in shared memory (broadcast reads), output NHWC fp16.
-// =============================================================================================
-constexpr int kC1Tile = 16;  // 16x16 output pixels per CTA
-
-__global__ void __launch_bounds__(256) conv1_7x7_kernel(const float* __restrict__ img,
-                                                        const float* __restrict__ w_t,
-                                                        const float* __restrict__ bias,
-                                                        __half* __restrict__ out, int H, int W,
-                                                        int C, int lo_off) {
-  extern __shared__ float sm[];
-  float* w_s = sm;                 // [49][C]
-  float* b_s = w_s + 49 * C;       // [C]
-  float* p_s = b_s + C;            // [37][37] input patch
-  constexpr int P = 2 * kC1Tile + 5;
-  const int b = blockIdx.z;
-  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
-  const int OH = H / 2, OW = W / 2;
-  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
-  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
-  const float* im = img + (long long)b * H * W;
-  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-  for (int i = threadIdx.x; i < P * P; i += 256) {
-    const int py = i / P, px = i - py * P;
-    const int y = iy0 + py, x = ix0 + px;
-    p_s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
-  }
-  __syncthreads();
-  const int ly = threadIdx.x / kC1Tile, lx = threadIdx.x % kC1Tile;
-  const int oy = oy0 + ly, ox = ox0 + lx;
-  float x[49];
-#pragma unroll
-  for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 7; ++kx) x[ky * 7 + kx] = p_s[(2 * ly + ky) * P + 2 * lx + kx];
-  if (oy >= OH || ox >= OW) return;
-  __half* dst = out + (((long long)b * OH + oy) * OW + ox) * (lo_off ? 2 * C : C);
-  for (int c0 = 0; c0 < C; c0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = b_s[c0 + j];
-#pragma unroll
-    for (int t = 0; t < 49; ++t) {
-      const float4 wa = *reinterpret_cast<const float4*>(w_s + t * C + c0);
-      const float4 wb = *reinterpret_cast<const float4*>(w_s + t * C + c0 + 4);
-      acc[0] = fmaf(x[t], wa.x, acc[0]);
-      acc[1] = fmaf(x[t], wa.y, acc[1]);
-      acc[2] = fmaf(x[t], wa.z, acc[2]);
-      acc[3] = fmaf(x[t], wa.w, acc[3]);
-      acc[4] = fmaf(x[t], wb.x, acc[4]);
-      acc[5] = fmaf(x[t], wb.y, acc[5]);
-      acc[6] = fmaf(x[t], wb.z, acc[6]);
-      acc[7] = fmaf(x[t], wb.w, acc[7]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = fmaxf(acc[j], 0.f);
-    store_split8(dst, c0, acc, lo_off);
-  }
-}
-
-// Same convolution with warp-staged output stores (selected by opp_set_option("conv1_staged") /
-// $OPP_CONV1_STAGED).  In the kernel above every 16 B store instruction of a warp touches 32
-// different pixels = 32 L1 wavefronts, 32 such instructions per thread: the store stream, not the
-// FMAs, bounds it.  Here a warp collects 32 channels (4 groups of 8) of its 32 pixels in a
-// shared-memory transpose buffer and writes them as 8 pixels x 64 B per instruction (4x fewer
-// wavefronts).  Requires C % 32 == 0.
-constexpr int kC1StageRow = 80;   // 32 fp16 (64 B) + 16 B pad per pixel row of the transpose buffer
-
-__global__ void __launch_bounds__(256, 3) conv1_7x7_staged_kernel(const float* __restrict__ img,
-                                                               const float* __restrict__ w_t,
-                                                               const float* __restrict__ bias,
-                                                               __half* __restrict__ out, int H, int W,
-                                                               int C, int lo_off) {
-  extern __shared__ float sm[];
-  float* w_s = sm;                 // [49][C]
-  float* b_s = w_s + 49 * C;       // [C]
-  float* p_s = b_s + C;            // [37][37] input patch
-  constexpr int P = 2 * kC1Tile + 5;
-  uint8_t* stage = reinterpret_cast<uint8_t*>(p_s + ((P * P + 3) & ~3));   // [8 warps][2 planes][32][80 B]
-  const int b = blockIdx.z;
-  const int oy0 = blockIdx.y * kC1Tile, ox0 = blockIdx.x * kC1Tile;
-  const int OH = H / 2, OW = W / 2;
-  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
-  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
-  const float* im = img + (long long)b * H * W;
-  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-  for (int i = threadIdx.x; i < P * P; i += 256) {
-    const int py = i / P, px = i - py * P;
-    const int y = iy0 + py, x = ix0 + px;
-    p_s[i] = (y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
-  }
-  __syncthreads();
-  const int ly = threadIdx.x / kC1Tile, lx = threadIdx.x % kC1Tile;
-  float x[49];
-#pragma unroll
-  for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 7; ++kx) x[ky * 7 + kx] = p_s[(2 * ly + ky) * P + 2 * lx + kx];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t st_hi = smem_u32(stage) + warp * (2 * 32 * kC1StageRow);
-  const uint32_t st_lo = st_hi + 32 * kC1StageRow;
-  const int ld = lo_off ? 2 * C : C;
-  // the four pixels this lane writes back: local index rr = (lane >> 2) + 8 i of the warp's 32
-  // pixels (warp w = tile rows 2w, 2w+1; pixel rr -> row 2w + rr / 16, column rr % 16)
-  long long pix_off[4];
-  unsigned pix_ok = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = (lane >> 2) + 8 * i;
-    const int oy = oy0 + 2 * warp + rr / kC1Tile, ox = ox0 + rr % kC1Tile;
-    if (oy < OH && ox < OW) pix_ok |= 1u << i;
-    pix_off[i] = (((long long)b * OH + oy) * OW + ox) * ld;
-  }
-  const int seg = lane & 3;
-  for (int cq = 0; cq < C; cq += 32) {
-#pragma unroll 1
-    for (int cg = 0; cg < 4; ++cg) {
-      const int c0 = cq + cg * 8;
-      float acc[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = b_s[c0 + j];
-#pragma unroll
-      for (int t = 0; t < 49; ++t) {
-        const float4 wa = *reinterpret_cast<const float4*>(w_s + t * C + c0);
-        const float4 wb = *reinterpret_cast<const float4*>(w_s + t * C + c0 + 4);
-        acc[0] = fmaf(x[t], wa.x, acc[0]);
-        acc[1] = fmaf(x[t], wa.y, acc[1]);
-        acc[2] = fmaf(x[t], wa.z, acc[2]);
-        acc[3] = fmaf(x[t], wa.w, acc[3]);
-        acc[4] = fmaf(x[t], wb.x, acc[4]);
-        acc[5] = fmaf(x[t], wb.y, acc[5]);
-        acc[6] = fmaf(x[t], wb.z, acc[6]);
-        acc[7] = fmaf(x[t], wb.w, acc[7]);
-      }
-      float lo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = fmaxf(acc[j], 0.f);
-        lo[j] = acc[j] - __half2float(__float2half_rn(acc[j]));
-      }
-      sts128(st_hi + lane * kC1StageRow + cg * 16,
-             make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]),
-                        pack_half2(acc[4], acc[5]), pack_half2(acc[6], acc[7])));
-      if (lo_off)
-        sts128(st_lo + lane * kC1StageRow + cg * 16,
-               make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]), pack_half2(lo[4], lo[5]),
-                          pack_half2(lo[6], lo[7])));
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = (lane >> 2) + 8 * i;
-      if ((pix_ok >> i) & 1u) {
-        __half* dst = out + pix_off[i] + cq + seg * 8;
-        *reinterpret_cast<uint4*>(dst) = lds128(st_hi + rr * kC1StageRow + seg * 16);
-        if (lo_off) *reinterpret_cast<uint4*>(dst + lo_off) = lds128(st_lo + rr * kC1StageRow + seg * 16);
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// Register-tiled variant (opp_set_option("conv1_px4") / $OPP_CONV1_PX4; not yet validated on a
-// GPU).  ncu of the kernels above: L1 LSU wavefronts 85 %, FMA pipe 36 % — every 8 FMAs of a lane
-// need two 16-byte broadcast loads of the weights from shared memory, so the load/store unit, not
-// the FMA pipe, is the limiter.  Here a thread computes 4 horizontally adjacent output pixels
-// (7 x 13 input values in registers), so one pair of weight loads feeds 32 FMAs.  CTA tile:
-// 64 x 16 output pixels; output through per-warp transpose buffers as in the staged kernel.
-constexpr int kC4TileX = 64, kC4TileY = 16;
-constexpr int kC4PatchW = 2 * kC4TileX + 5;          // 133 input columns
-constexpr int kC4PatchS = 136;                        // padded row stride (floats)
-constexpr int kC4PatchH = 2 * kC4TileY + 5;          // 37 input rows
-
-__global__ void __launch_bounds__(256, 1) conv1_7x7_px4_kernel(const float* __restrict__ img,
-                                                               const float* __restrict__ w_t,
-                                                               const float* __restrict__ bias,
-                                                               __half* __restrict__ out, int H, int W,
-                                                               int C, int lo_off) {
-  extern __shared__ float sm[];
-  float* w_s = sm;                 // [49][C]
-  float* b_s = w_s + 49 * C;       // [C]
-  float* p_s = b_s + C;            // [37][136] input patch
-  uint8_t* stage = reinterpret_cast<uint8_t*>(p_s + kC4PatchH * kC4PatchS);   // [8 warps][4 px][2 planes][32][80 B]
-  const int b = blockIdx.z;
-  const int oy0 = blockIdx.y * kC4TileY, ox0 = blockIdx.x * kC4TileX;
-  const int OH = H / 2, OW = W / 2;
-  for (int i = threadIdx.x; i < 49 * C; i += 256) w_s[i] = w_t[i];
-  for (int i = threadIdx.x; i < C; i += 256) b_s[i] = bias[i];
-  const float* im = img + (long long)b * H * W;
-  const int iy0 = oy0 * 2 - 3, ix0 = ox0 * 2 - 3;
-  for (int i = threadIdx.x; i < kC4PatchH * kC4PatchS; i += 256) {
-    const int py = i / kC4PatchS, px = i - py * kC4PatchS;
-    const int y = iy0 + py, x = ix0 + px;
-    p_s[i] = (px < kC4PatchW && y >= 0 && y < H && x >= 0 && x < W) ? im[(long long)y * W + x] : 0.f;
-  }
-  __syncthreads();
-  const int ly = threadIdx.x >> 4, lx4 = threadIdx.x & 15;   // pixels (oy0 + ly, ox0 + 4 lx4 + p)
-  float x[7][13];
-#pragma unroll
-  for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-    for (int j = 0; j < 13; ++j) x[ky][j] = p_s[(2 * ly + ky) * kC4PatchS + 8 * lx4 + j];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kPlane = 32 * kC1StageRow;                    // one [32 pixels][80 B] buffer
-  const uint32_t st0 = smem_u32(stage) + warp * (4 * 2 * kPlane);   // + p * 2 kPlane (+ kPlane for lo)
-  const int ld = lo_off ? 2 * C : C;
-  // write-back: lane -> pixels rr = (lane >> 2) + 8 i of the warp's 32 lanes, 16 B segment seg;
-  // lane rr owns row 2 warp + rr / 16 and columns 4 (rr % 16) + p
-  long long pix_off[4];
-  int pix_x[4];
-  unsigned row_ok = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = (lane >> 2) + 8 * i;
-    const int oy = oy0 + 2 * warp + (rr >> 4);
-    pix_x[i] = ox0 + 4 * (rr & 15);
-    if (oy < OH) row_ok |= 1u << i;
-    pix_off[i] = (((long long)b * OH + oy) * OW + pix_x[i]) * ld;
-  }
-  const int seg = lane & 3;
-  for (int cq = 0; cq < C; cq += 32) {
-#pragma unroll 1
-    for (int cg = 0; cg < 4; ++cg) {
-      const int c0 = cq + cg * 8;
-      float acc[4][8];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[p][j] = b_s[c0 + j];
-#pragma unroll
-      for (int ky = 0; ky < 7; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const float4 wa = *reinterpret_cast<const float4*>(w_s + (ky * 7 + kx) * C + c0);
-          const float4 wb = *reinterpret_cast<const float4*>(w_s + (ky * 7 + kx) * C + c0 + 4);
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const float xv = x[ky][2 * p + kx];
-            acc[p][0] = fmaf(xv, wa.x, acc[p][0]);
-            acc[p][1] = fmaf(xv, wa.y, acc[p][1]);
-            acc[p][2] = fmaf(xv, wa.z, acc[p][2]);
-            acc[p][3] = fmaf(xv, wa.w, acc[p][3]);
-            acc[p][4] = fmaf(xv, wb.x, acc[p][4]);
-            acc[p][5] = fmaf(xv, wb.y, acc[p][5]);
-            acc[p][6] = fmaf(xv, wb.z, acc[p][6]);
-            acc[p][7] = fmaf(xv, wb.w, acc[p][7]);
-          }
-        }
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        float lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          acc[p][j] = fmaxf(acc[p][j], 0.f);
-          lo[j] = acc[p][j] - __half2float(__float2half_rn(acc[p][j]));
-        }
-        const uint32_t sp = st0 + p * (2 * kPlane) + lane * kC1StageRow + cg * 16;
-        sts128(sp, make_uint4(pack_half2(acc[p][0], acc[p][1]), pack_half2(acc[p][2], acc[p][3]),
-                              pack_half2(acc[p][4], acc[p][5]), pack_half2(acc[p][6], acc[p][7])));
-        if (lo_off)
-          sts128(sp + kPlane, make_uint4(pack_half2(lo[0], lo[1]), pack_half2(lo[2], lo[3]),
-                                         pack_half2(lo[4], lo[5]), pack_half2(lo[6], lo[7])));
-      }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int rr = (lane >> 2) + 8 * i;
-        if (((row_ok >> i) & 1u) && pix_x[i] + p < OW) {
-          __half* dst = out + pix_off[i] + (long long)p * ld + cq + seg * 8;
-          const uint32_t sp = st0 + p * (2 * kPlane) + rr * kC1StageRow + seg * 16;
-          *reinterpret_cast<uint4*>(dst) = lds128(sp);
-          if (lo_off) *reinterpret_cast<uint4*>(dst + lo_off) = lds128(sp + kPlane);
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
+constexpr int kC1Tile = 16;  // 16x16 output pixels per CTA of the conv1 im2col
 
 // =============================================================================================
 // conv1 as a tensor-core GEMM (backbone/resnet.py:101-103,143): the 7x7 stride-2 pad-3 window of
@@ -345,95 +63,6 @@ __global__ void __launch_bounds__(256) conv1_im2col_kernel(const void* __restric
       v[j] = col < 49 ? p_s[(2 * ly + ky) * P + 2 * lx + kx] : (col == 49 ? 1.f : 0.f);
     }
     store_split8(a_out + (((long long)b * OH + oy) * OW + ox) * ld, g * 8, v, lo_off ? 64 : 0);
-  }
-}
-
-// =============================================================================================
-// out = a + bilinear_x2(b), align_corners=True   (backbone/resnet.py:151-152,155-156)
-// torch semantics: src = dst * (in-1)/(out-1); i0 = floor(src); i1 = min(i0+1, in-1)
-// =============================================================================================
-__global__ void __launch_bounds__(256) upsample2x_add_kernel(const __half* __restrict__ a,
-                                                             const __half* __restrict__ bsrc,
-                                                             __half* __restrict__ out, int B,
-                                                             int h, int w, int C, int lo_off) {
-  const int cg = C / 8;
-  const int ld = lo_off ? 2 * C : C;
-  const long long total = (long long)B * (2 * h) * (2 * w) * cg;
-  const float sy = (float)(h - 1) / (float)(2 * h - 1);
-  const float sx = (float)(w - 1) / (float)(2 * w - 1);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cg);
-    long long p = i / cg;
-    const int x = (int)(p % (2 * w));
-    p /= (2 * w);
-    const int y = (int)(p % (2 * h));
-    const int b = (int)(p / (2 * h));
-    const float fy = sy * (float)y, fx = sx * (float)x;
-    const int y0 = (int)fy, x0 = (int)fx;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0), x1 = x0 + (x0 < w - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, lx = fx - (float)x0;
-    const float hy = 1.f - ly, hx = 1.f - lx;
-    const __half* base = bsrc + (long long)b * h * w * ld;
-    float v00[8], v01[8], v10[8], v11[8], va[8], r[8];
-    load_split8(base + ((long long)y0 * w + x0) * ld, c8 * 8, v00, lo_off);
-    load_split8(base + ((long long)y0 * w + x1) * ld, c8 * 8, v01, lo_off);
-    load_split8(base + ((long long)y1 * w + x0) * ld, c8 * 8, v10, lo_off);
-    load_split8(base + ((long long)y1 * w + x1) * ld, c8 * 8, v11, lo_off);
-    const long long off = (((long long)b * 2 * h + y) * (2 * w) + x) * ld;
-    load_split8(a + off, c8 * 8, va, lo_off);
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      r[j] = va[j] + (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]));
-    store_split8(out + off, c8 * 8, r, lo_off);
-  }
-}
-
-// Row-mapped variant (opp_set_option("upsample_rows") / $OPP_UPSAMPLE_ROWS): one block per output
-// row, one warp per output pixel at a time, lane = 8-channel group.  The kernel above spends most
-// of its issue slots (ncu: SM 65 %, DRAM 47 %) on 64-bit div/mod index arithmetic per element;
-// here all index math is warp-uniform and division-free, the two source rows stay hot in L1, and
-// the arithmetic on the data is the same expression (bit-identical results).  C <= 256.
-__global__ void __launch_bounds__(256) upsample2x_add_rows_kernel(const __half* __restrict__ a,
-                                                                  const __half* __restrict__ bsrc,
-                                                                  __half* __restrict__ out, int B,
-                                                                  int h, int w, int C, int lo_off) {
-  const int cg = C / 8;
-  const int ld = lo_off ? 2 * C : C;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int H2 = 2 * h, W2 = 2 * w;
-  const float sy = (float)(h - 1) / (float)(2 * h - 1);
-  const float sx = (float)(w - 1) / (float)(2 * w - 1);
-  const long long rows = (long long)B * H2;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = (int)(row / H2);
-    const int y = (int)(row - (long long)b * H2);
-    const float fy = sy * (float)y;
-    const int y0 = (int)fy;
-    const int y1 = y0 + (y0 < h - 1 ? 1 : 0);
-    const float ly = fy - (float)y0, hy = 1.f - ly;
-    const __half* r0 = bsrc + ((long long)b * h + y0) * w * ld;
-    const __half* r1 = bsrc + ((long long)b * h + y1) * w * ld;
-    const long long obase = row * W2 * ld;
-    for (int x = warp; x < W2; x += 8) {
-      const float fx = sx * (float)x;
-      const int x0 = (int)fx;
-      const int x1 = x0 + (x0 < w - 1 ? 1 : 0);
-      const float lx = fx - (float)x0, hx = 1.f - lx;
-      if (lane < cg) {
-        float v00[8], v01[8], v10[8], v11[8], va[8], r[8];
-        load_split8(r0 + (long long)x0 * ld, lane * 8, v00, lo_off);
-        load_split8(r0 + (long long)x1 * ld, lane * 8, v01, lo_off);
-        load_split8(r1 + (long long)x0 * ld, lane * 8, v10, lo_off);
-        load_split8(r1 + (long long)x1 * ld, lane * 8, v11, lo_off);
-        const long long off = obase + (long long)x * ld;
-        load_split8(a + off, lane * 8, va, lo_off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          r[j] = va[j] + (hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]));
-        store_split8(out + off, lane * 8, r, lo_off);
-      }
-    }
   }
 }
 
@@ -606,84 +235,8 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
 // part[b][chunk][h][d][v] = sum_{s in chunk} K'[s,h,d] V[s,h,v];  row d = 32 holds sum_s K'[s,h,:]
 // =============================================================================================
 constexpr int kKvChunk = 128;   // tokens per CTA
-constexpr int kKvSub = 16;      // tokens staged in shared memory at a time
-
-// One CTA = one chunk of tokens and ALL heads (warp h <-> head h), so every token row is read
-// exactly once, fully coalesced (both planes), and converted to fp32 in shared memory.
-// Lane d of warp h owns row d of the 32x32 head state: acc[v] += K'[t,h,d] * V[t,h,v].
-__global__ void __launch_bounds__(256) kv_partial_kernel(const __half* __restrict__ kv16,
-                                                         float* __restrict__ part, int S, int d,
-                                                         int lo_off) {
-  __shared__ float xs[kKvSub][512];
-  const int chunk = blockIdx.x, b = blockIdx.y;
-  const int chunks = gridDim.x;
-  const int H = d >> 5;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s0 = chunk * kKvChunk;
-  const int cnt = min(kKvChunk, S - s0);
-  const int ld = lo_off ? 4 * d : 2 * d;
-  const int groups = (2 * d) >> 3;   // 8-value groups per token row (64 for d = 256)
-  const __half* src = kv16 + ((long long)b * S + s0) * ld;
-  float acc[32];
-#pragma unroll
-  for (int v = 0; v < 32; ++v) acc[v] = 0.f;
-  float ks = 0.f;
-  // software pipeline: the global loads of sub-chunk i+1 are in flight (registers) while the
-  // warps run the FMAs of sub-chunk i out of shared memory
-  constexpr int kPer = kKvSub * 64 / 256;   // 8-value groups per thread per sub-chunk (d = 256)
-  float x[kPer][8];
-  auto fetch = [&](int t0) {
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int i = threadIdx.x + u * 256;
-      const int t = i / groups, g = i - t * groups;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[u][j] = 0.f;
-      if (t0 + t < cnt) load_split8(src + (long long)(t0 + t) * ld, g * 8, x[u], lo_off);
-    }
-  };
-  fetch(0);
-  for (int t0 = 0; t0 < cnt; t0 += kKvSub) {
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      const int i = threadIdx.x + u * 256;
-      const int t = i / groups, g = i - t * groups;
-      float4* dst = reinterpret_cast<float4*>(&xs[t][g * 8]);
-      dst[0] = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
-      dst[1] = make_float4(x[u][4], x[u][5], x[u][6], x[u][7]);
-    }
-    __syncthreads();
-    if (t0 + kKvSub < cnt) fetch(t0 + kKvSub);
-    if (warp < H) {
-#pragma unroll 4
-      for (int t = 0; t < kKvSub; ++t) {
-        const float k = xs[t][warp * 32 + lane];
-        const float4* vrow = reinterpret_cast<const float4*>(&xs[t][d + warp * 32]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 vv = vrow[q];
-          acc[4 * q + 0] = fmaf(k, vv.x, acc[4 * q + 0]);
-          acc[4 * q + 1] = fmaf(k, vv.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(k, vv.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(k, vv.w, acc[4 * q + 3]);
-        }
-        ks += k;
-      }
-    }
-  }
-  if (warp < H) {
-    float* dst = part + ((((long long)b * chunks + chunk) * H + warp) * 33) * 32;
-    float4* row = reinterpret_cast<float4*>(dst + lane * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q)
-      row[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    dst[32 * 32 + lane] = ks;
-  }
-}
 
 // ---------------------------------------------------------------------------------------------
-// Tensor-core variant of the same state (selected by $OPP_KV_MMA, see opp_kv_partial).
 // Per head the state is a 32x32 GEMM over the tokens of the chunk, KV[d][v] = sum_t K'[t][d] V[t][v]:
 // M = d, N = v, K = token.  The tile is far too small for tcgen05 (M = 128 would compute 8x the
 // needed head blocks and wants token-major operands transposed), so each warp (= head) runs
@@ -899,9 +452,16 @@ __global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* _
 
 // column side of opp_sim_lse_cols: lse[b][s] = logsumexp over the row groups of (col_m, col_s)
 __global__ void lse_col_finalize_kernel(const float* __restrict__ cm, const float* __restrict__ cs,
-                                        float* __restrict__ lse, int batches, int groups, int cols) {
+                                        float* __restrict__ lse, int batches, int groups, int cols,
+                                        const unsigned char* __restrict__ col_mask) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)batches * cols) return;
+  if (col_mask && col_mask[idx] == 0) {
+    // padded query cell: every sim of this column is -1e9, so conf = 0 whatever the row
+    // (coarse_matching.py:108-115); +inf makes exp((2 sim - lse_pt) - lse_px) exactly 0
+    lse[idx] = INFINITY;
+    return;
+  }
   const int b = (int)(idx / cols);
   const int sidx = (int)(idx - (long long)b * cols);
   const float* pm = cm + (long long)b * groups * cols + sidx;
@@ -1133,8 +693,9 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const __half* __restrict__ fine, const float* __restrict__ desc3d,
     const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
     const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
-    int wf, int wc, int stride, int n, int lo_off, int desc_shared) {
+    int wf, int wc, int stride, int n, int lo_off, int desc_shared, const int* __restrict__ count_dev) {
   const int m = blockIdx.x, c = threadIdx.x;
+  if (count_dev && m >= *count_dev) return;   // launched at capacity, match count on the device
   const long long b = b_ids[m], i = i_ids[m], j = j_ids[m];
   const int jy = (int)(j / wc), jx = (int)(j - (long long)jy * wc);
   const long long row0 = (long long)m * 26;
@@ -1159,7 +720,9 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
 __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __restrict__ qkv,
                                                              __half* __restrict__ msg, int cross,
                                                              float eps, int lo_off_in,
-                                                             int lo_off_out) {
+                                                             int lo_off_out,
+                                                             const int* __restrict__ count_dev) {
+  if (count_dev && (int)blockIdx.x >= *count_dev) return;
   __shared__ float q_s[26][128];
   __shared__ float k_s[26][128];
   __shared__ float v_s[26][128];
@@ -1218,97 +781,17 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
   }
 }
 
-// Same attention with 16-byte global accesses (opp_set_option("fine_attn_vec") /
-// $OPP_FINE_ATTN_VEC; not yet validated on a GPU): the kernel above moves its 26 x 384 inputs and
-// 26 x 128 outputs with 2-byte loads/stores (about 200 memory instructions per thread for 40 KB
-// per match, ~9x off the HBM time); here rows are fetched as uint4 and the results are packed
-// through shared memory.  The arithmetic is the same code.
-__global__ void __launch_bounds__(128) fine_attention_vec_kernel(const __half* __restrict__ qkv,
-                                                                 __half* __restrict__ msg, int cross,
-                                                                 float eps, int lo_off_in,
-                                                                 int lo_off_out) {
-  __shared__ __align__(16) float q_s[26][128];
-  __shared__ __align__(16) float k_s[26][128];
-  __shared__ __align__(16) float v_s[26][128];
-  const int m = blockIdx.x, c = threadIdx.x;
-  const int ldi = lo_off_in ? 768 : 384;
-  const __half* src = qkv + (long long)m * 26 * ldi;
-  for (int i = c; i < 26 * 48; i += 128) {
-    const int t = i / 48, sg = i - t * 48;
-    float f[8];
-    load_split8(src + (long long)t * ldi, sg * 8, f, lo_off_in);
-    const int col = sg * 8;   // 0..383: q | k | v, 128 each
-    float* dstrow = col < 128 ? &q_s[t][col] : (col < 256 ? &k_s[t][col - 128] : &v_s[t][col - 256]);
-    reinterpret_cast<float4*>(dstrow)[0] = make_float4(f[0], f[1], f[2], f[3]);
-    reinterpret_cast<float4*>(dstrow)[1] = make_float4(f[4], f[5], f[6], f[7]);
-  }
-  __syncthreads();
-  const int h = c >> 4, v = c & 15;
-  float col[16];
-#pragma unroll
-  for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
-  float ksum_c = 0.f;
-  for (int t = 1; t < 26; ++t) {
-    const float vv = v_s[t][c];
-#pragma unroll
-    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(k_s[t][h * 16 + dd], vv, col[dd]);
-    ksum_c += k_s[t][c];
-  }
-  __syncthreads();
-  float (*kv2)[16][16] = reinterpret_cast<float (*)[16][16]>(&v_s[1][0]);
-  float* ks2 = &k_s[1][0];
-#pragma unroll
-  for (int dd = 0; dd < 16; ++dd) kv2[h][dd][v] = col[dd];
-  ks2[c] = ksum_c;
-  __syncthreads();
-  float o[26];
-#pragma unroll
-  for (int t = 0; t < 26; ++t) {
-    const bool use_window = cross ? (t == 0) : (t > 0);
-    float num = 0.f, den = 0.f;
-    if (use_window) {
-#pragma unroll
-      for (int dd = 0; dd < 16; ++dd) {
-        const float q = q_s[t][h * 16 + dd];
-        num = fmaf(q, kv2[h][dd][v], num);
-        den = fmaf(q, ks2[h * 16 + dd], den);
-      }
-    } else {
-      float qk = 0.f;
-#pragma unroll
-      for (int dd = 0; dd < 16; ++dd) qk = fmaf(q_s[t][h * 16 + dd], k_s[0][h * 16 + dd], qk);
-      num = qk * v_s[0][c];
-      den = qk;
-    }
-    o[t] = num / (den + eps);
-  }
-  __syncthreads();   // every read of q_s is done: reuse it as the output tile
-#pragma unroll
-  for (int t = 0; t < 26; ++t) q_s[t][c] = o[t];
-  __syncthreads();
-  const int ldo = lo_off_out ? 256 : 128;
-  __half* dst = msg + (long long)m * 26 * ldo;
-  for (int i = c; i < 26 * 16; i += 128) {
-    const int t = i >> 4, sg = i & 15;
-    float f[8];
-    const float4 a = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[0];
-    const float4 b = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[1];
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-    store_split8(dst + (long long)t * ldo, sg * 8, f, lo_off_out);
-  }
-}
-
 // =============================================================================================
 // fine matching   (utils/fine_matching.py:78-110): one warp per match
 // =============================================================================================
 __global__ void __launch_bounds__(128) fine_match_kernel(
     const float* __restrict__ x32, const float* __restrict__ mkpts_c,
     const long long* __restrict__ b_ids, const float* __restrict__ img_scale,
-    float* __restrict__ expec_f, float* __restrict__ mkpts_f, int M, float fine_scale) {
+    float* __restrict__ expec_f, float* __restrict__ mkpts_f, int M, float fine_scale,
+    const int* __restrict__ count_dev) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
-  if (m >= M) return;
+  if (m >= M || (count_dev && m >= *count_dev)) return;
   const float* f0 = x32 + (long long)m * 26 * 128;
   const float4 a = reinterpret_cast<const float4*>(f0)[lane];
   float my_sim = -INFINITY;
@@ -1371,70 +854,6 @@ extern "C" {
 int opp_version(void) { return 100; }
 int opp_num_sms(void) { return opp::num_sms(); }
 
-#ifndef OPP_CONV1_STAGED_DEFAULT
-#define OPP_CONV1_STAGED_DEFAULT 1
-#endif
-static int g_conv1_staged = -1;
-static int conv1_staged_enabled() {
-  if (g_conv1_staged < 0) {
-    const char* e = getenv("OPP_CONV1_STAGED");
-    g_conv1_staged = e ? atoi(e) : OPP_CONV1_STAGED_DEFAULT;
-  }
-  return g_conv1_staged;
-}
-
-#ifndef OPP_CONV1_PX4_DEFAULT
-#define OPP_CONV1_PX4_DEFAULT 0
-#endif
-static int g_conv1_px4 = -1;
-static int conv1_px4_enabled() {
-  if (g_conv1_px4 < 0) {
-    const char* e = getenv("OPP_CONV1_PX4");
-    g_conv1_px4 = e ? atoi(e) : OPP_CONV1_PX4_DEFAULT;
-  }
-  return g_conv1_px4;
-}
-
-int opp_conv1_7x7(const float* image, const float* w_t, const float* bias, void* out, int batch,
-                  int h, int w, int c_out, int split, opp_stream_t stream) {
-  OPP_REQUIRE(image && w_t && bias && out, "null pointer");
-  OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && c_out % 8 == 0 && c_out <= 256, "bad conv1 shape");
-  const bool px4 = conv1_px4_enabled() && c_out % 32 == 0;
-  const bool staged = !px4 && conv1_staged_enabled() && c_out % 32 == 0;
-  const int patch = (37 * 37 + 3) & ~3;
-  const int smem = px4 ? (49 * c_out + c_out + kC4PatchH * kC4PatchS) * 4 + 8 * 4 * 2 * 32 * kC1StageRow
-                  : staged ? (49 * c_out + c_out + patch) * 4 + 8 * 2 * 32 * kC1StageRow
-                           : (49 * c_out + c_out + 37 * 37) * 4;
-  static unsigned long long attr_done = 0;   // per device
-  int dev = 0;
-  OPP_CHECK_CUDA(cudaGetDevice(&dev));
-  if (dev < 64 && !((attr_done >> dev) & 1ull)) {
-    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_staged_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
-    OPP_CHECK_CUDA(cudaFuncSetAttribute(conv1_7x7_px4_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done |= 1ull << dev;
-  }
-  if (px4) {
-    dim3 grid((w / 2 + kC4TileX - 1) / kC4TileX, (h / 2 + kC4TileY - 1) / kC4TileY, batch);
-    conv1_7x7_px4_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
-                                                                    c_out, split ? c_out : 0);
-    OPP_CHECK_CUDA(cudaGetLastError());
-    return OPP_OK;
-  }
-  dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
-  if (staged)
-    conv1_7x7_staged_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
-        image, w_t, bias, (__half*)out, h, w, c_out, split ? c_out : 0);
-  else
-    conv1_7x7_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(image, w_t, bias, (__half*)out, h, w,
-                                                                c_out, split ? c_out : 0);
-  OPP_CHECK_CUDA(cudaGetLastError());
-  return OPP_OK;
-}
-
 int opp_conv1_im2col(const void* image, int image_u8, void* a_out, int batch, int h, int w, int split,
                      opp_stream_t stream) {
   OPP_REQUIRE(image && a_out, "null pointer");
@@ -1444,36 +863,6 @@ int opp_conv1_im2col(const void* image, int image_u8, void* a_out, int batch, in
     conv1_im2col_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
   else
     conv1_im2col_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
-  OPP_CHECK_CUDA(cudaGetLastError());
-  return OPP_OK;
-}
-
-#ifndef OPP_UPSAMPLE_ROWS_DEFAULT
-#define OPP_UPSAMPLE_ROWS_DEFAULT 0
-#endif
-static int g_upsample_rows = -1;
-static int upsample_rows_enabled() {
-  if (g_upsample_rows < 0) {
-    const char* e = getenv("OPP_UPSAMPLE_ROWS");
-    g_upsample_rows = e ? atoi(e) : OPP_UPSAMPLE_ROWS_DEFAULT;
-  }
-  return g_upsample_rows;
-}
-
-int opp_upsample2x_add(const void* a, const void* b, void* out, int batch, int h, int w, int c,
-                       int split, opp_stream_t stream) {
-  OPP_REQUIRE(a && b && out, "null pointer");
-  OPP_REQUIRE(c % 8 == 0 && h > 1 && w > 1, "bad upsample shape");
-  if (upsample_rows_enabled() && c <= 256) {
-    const long long rows = (long long)batch * 2 * h;
-    const long long cap = (long long)opp::num_sms() * 8;
-    upsample2x_add_rows_kernel<<<(unsigned)(rows < cap ? rows : cap), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
-  } else {
-    const long long total = (long long)batch * 4 * h * w * (c / 8);
-    upsample2x_add_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)a, (const __half*)b, (__half*)out, batch, h, w, c, split ? c : 0);
-  }
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1500,95 +889,67 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
 
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 
-#ifndef OPP_FINE_ATTN_VEC_DEFAULT
-#define OPP_FINE_ATTN_VEC_DEFAULT 0
-#endif
-static int g_fine_attn_vec = -1;
-static int fine_attn_vec_enabled() {
-  if (g_fine_attn_vec < 0) {
-    const char* e = getenv("OPP_FINE_ATTN_VEC");
-    g_fine_attn_vec = e ? atoi(e) : OPP_FINE_ATTN_VEC_DEFAULT;
-  }
-  return g_fine_attn_vec;
+// Process-wide integer switches (opp_set_option / opp_get_option): selection between alternative
+// kernels behind one entry point while a new variant is being validated.  Unknown names fail.
+struct OppOption {
+  const char* name;
+  const char* env;
+  int value;   // -1 = not read yet
+  int dflt;
+};
+static OppOption g_options[] = {
+    {"gemm_w_resident", "OPP_GEMM_W_RESIDENT", -1, 0},
+};
+static OppOption* find_option(const char* name) {
+  if (!name) return nullptr;
+  for (auto& o : g_options)
+    if (strcmp(o.name, name) == 0) return &o;
+  return nullptr;
 }
-
-// $OPP_KV_MMA (or opp_set_option("kv_mma", v)) selects the linear-attention state kernel:
-// 1 = mma.sync tensor-core stream, 0 = SIMT (fp32 FMA).  Both write the same partial layout.
-#ifndef OPP_KV_MMA_DEFAULT
-#define OPP_KV_MMA_DEFAULT 1
-#endif
-static int g_kv_mma = -1;
-static int kv_mma_enabled() {
-  if (g_kv_mma < 0) {
-    const char* e = getenv("OPP_KV_MMA");
-    g_kv_mma = e ? atoi(e) : OPP_KV_MMA_DEFAULT;
+namespace opp {
+int option_value(const char* name) {
+  OppOption* o = find_option(name);
+  if (!o) return -1;
+  if (o->value < 0) {
+    const char* e = getenv(o->env);
+    o->value = e ? atoi(e) : o->dflt;
   }
-  return g_kv_mma;
+  return o->value;
 }
+}  // namespace opp
 
 int opp_set_option(const char* name, int value) {
-  OPP_REQUIRE(name, "null option name");
-  if (strcmp(name, "kv_mma") == 0) {
-    g_kv_mma = value ? 1 : 0;
-    return OPP_OK;
+  OppOption* o = find_option(name);
+  if (!o) {
+    set_last_error("unknown option '%s'", name ? name : "(null)");
+    return OPP_ERR_INVALID;
   }
-  if (strcmp(name, "conv1_staged") == 0) {
-    g_conv1_staged = value ? 1 : 0;
-    return OPP_OK;
-  }
-  if (strcmp(name, "conv1_px4") == 0) {
-    g_conv1_px4 = value ? 1 : 0;
-    return OPP_OK;
-  }
-  if (strcmp(name, "fine_attn_vec") == 0) {
-    g_fine_attn_vec = value ? 1 : 0;
-    return OPP_OK;
-  }
-  if (strcmp(name, "upsample_rows") == 0) {
-    g_upsample_rows = value ? 1 : 0;
-    return OPP_OK;
-  }
-  set_last_error("unknown option '%s'", name);
-  return OPP_ERR_INVALID;
+  o->value = value < 0 ? 0 : value;
+  return OPP_OK;
 }
 
-int opp_get_option(const char* name) {
-  if (name && strcmp(name, "kv_mma") == 0) return kv_mma_enabled();
-  if (name && strcmp(name, "conv1_staged") == 0) return conv1_staged_enabled();
-  if (name && strcmp(name, "upsample_rows") == 0) return upsample_rows_enabled();
-  if (name && strcmp(name, "conv1_px4") == 0) return conv1_px4_enabled();
-  if (name && strcmp(name, "fine_attn_vec") == 0) return fine_attn_vec_enabled();
-  return -1;
-}
+int opp_get_option(const char* name) { return opp::option_value(name); }
 
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");
-  OPP_REQUIRE(d % 32 == 0, "d=%d must be a multiple of the head size 32", d);
   OPP_REQUIRE(d == 256, "kv_partial is built for d = 256 (8 heads x 32), got %d", d);
   dim3 grid((s + kKvChunk - 1) / kKvChunk, batch);
-  if (kv_mma_enabled()) {
-    const int smem = kKvmStages * kKvmTok * ((split ? 2048 : 1024) + 16);
-    static unsigned long long attr_done = 0;   // per device
-    int dev = 0;
-    OPP_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev < 64 && !((attr_done >> dev) & 1ull)) {
-      OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<true>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<false>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr_done |= 1ull << dev;
-    }
-    if (split)
-      kv_partial_mma_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16,
-                                                                              part, s);
-    else
-      kv_partial_mma_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16,
-                                                                               part, s);
-  } else {
-    kv_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)kv16, part, s, d,
-                                                              split ? 2 * d : 0);
+  const int smem = kKvmStages * kKvmTok * ((split ? 2048 : 1024) + 16);
+  static unsigned long long attr_done = 0;   // per device
+  int dev = 0;
+  OPP_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !((attr_done >> dev) & 1ull)) {
+    OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    OPP_CHECK_CUDA(cudaFuncSetAttribute(kv_partial_mma_kernel<false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done |= 1ull << dev;
   }
+  if (split)
+    kv_partial_mma_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16, part, s);
+  else
+    kv_partial_mma_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16, part, s);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1615,11 +976,11 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
 }
 
 int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
-                         int cols, opp_stream_t stream) {
+                         int cols, const unsigned char* col_mask, opp_stream_t stream) {
   OPP_REQUIRE(col_m && col_s && lse && batches > 0 && groups > 0 && cols > 0, "bad lse_col_finalize arguments");
   const long long n = (long long)batches * cols;
   lse_col_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      col_m, col_s, lse, batches, groups, cols);
+      col_m, col_s, lse, batches, groups, cols, col_mask);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1677,39 +1038,34 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
                     int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
-                    opp_stream_t stream) {
+                    const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x16, "null pointer");
   fine_gather_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)fine, desc3d, b_ids,
                                                           i_ids, j_ids, x32, (__half*)x16, hf, wf,
-                                                          wc, stride, n, split ? 128 : 0, bank_shared);
+                                                          wc, stride, n, split ? 128 : 0, bank_shared,
+                                                          count_dev);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, int split,
-                       opp_stream_t stream) {
+                       const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(qkv && msg, "null pointer");
-  if (fine_attn_vec_enabled())
-    fine_attention_vec_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
-                                                                   cross, eps, split ? 384 : 0,
-                                                                   split ? 128 : 0);
-  else
-    fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg,
-                                                               cross, eps, split ? 384 : 0,
-                                                               split ? 128 : 0);
+  fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg, cross, eps,
+                                                             split ? 384 : 0, split ? 128 : 0, count_dev);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_ids,
                    const float* img_scale, float* expec_f, float* mkpts_f, int m, float fine_scale,
-                   opp_stream_t stream) {
+                   const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(x32 && mkpts_c && b_ids && expec_f && mkpts_f, "null pointer");
   fine_match_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts_c, b_ids, img_scale,
-                                                                   expec_f, mkpts_f, m, fine_scale);
+                                                                   expec_f, mkpts_f, m, fine_scale, count_dev);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -7,8 +7,9 @@ sm_100a kernels of ``libopp_b200.so``.  The ``nn.Module`` tree below only *holds
 the reference's names and initialisers; there is no PyTorch math on the hot path and no fallback:
 CPU tensors, training mode, or a missing extension raise.
 
-Round-1 scope: inference (``eval()``, no autograd), linear attention, no
-``query_image_mask`` (cold in every shipped config).
+Scope: inference (``eval()``, no autograd), linear attention; extensions of the input
+path (resident bank, uint8 frames, lazy ``conf_matrix``, CUDA-graph replay) are documented at
+``forward`` / ``set_bank`` / ``enable_cuda_graphs``.
 """
 import math
 import os
@@ -277,6 +278,7 @@ class OnePosePlus_model(nn.Module):
         self._bank = None
         self._graphs = {}
         self._fwd_count = 0
+        self.use_cuda_graphs = os.environ.get("OPP_B200_GRAPHS", "0") == "1"
         # data["conf_matrix"]: "eager" = fp32 [B, N, S] written every forward (reference contract,
         # coarse_matching.py:119; what the training loss reads); "lazy" = a LazyConfMatrix handle
         # that materialises on demand (no inference consumer reads the matrix:
@@ -304,7 +306,7 @@ class OnePosePlus_model(nn.Module):
     def __setstate__(self, st):
         self.__dict__.update(st)
         for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
-                     ("_graphs", {}), ("_fwd_count", 0)):
+                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False)):
             self.__dict__.setdefault(k, v)
 
     # ------------------------------------------------------------------ weight preparation
@@ -481,7 +483,7 @@ class OnePosePlus_model(nn.Module):
         x1_out = cv("layer1_outconv2.3", t, "x1_out", 3, 1)
         return tok, x1_out, (hc, wc)
 
-    def _src_state(self, L, tag, src, B, ls):
+    def _src_state(self, L, tag, src, B, ls, src_mask=None):
         """Source side of linear attention for one layer (linear_attention.py:46,55-57 +
         transformer.py:78-79,85): K' = elu(Wk src)+1, V = Wv src, per-head KV / Ksum, with `merge`
         folded in -> (Mt [B, 256, pl*256] fp16, Ksum [B, 256] fp32)."""
@@ -491,30 +493,34 @@ class OnePosePlus_model(nn.Module):
         pl = 2 if split else 1
         kv_split = split and not self.kv_single_plane
         kv16 = self._buf(tag + "kv16", (B * ls, (2 if kv_split else 1) * 512), f16, dev)
-        ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split, out_split=kv_split)
+        ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split, out_split=kv_split,
+                       row_mask=src_mask)
         part = self._buf(tag + "part", (B, ops.kv_chunks(ls), 8, 33, 32), torch.float32, dev)
         mt = self._buf(tag + "mt", (B, 256, pl * 256), f16, dev)
         ksum = self._buf(tag + "ksum", (B, 256), torch.float32, dev)
         ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split, kv_split=kv_split)
         return mt, ksum
 
-    def _encoder_layer(self, L, tag, x, src, B, lx, ls, out, x_shared=False, state=None):
+    def _encoder_layer(self, L, tag, x, src, B, lx, ls, out, x_shared=False, state=None, x_mask=None,
+                       src_mask=None):
         """LoFTREncoderLayer.forward (transformer.py:65-94) with linear attention
         (linear_attention.py:29-61) for d_model 256.  x, src, out: fp16 planes [B, len, pl*256].
         x_shared: x is [1, lx, ..] — one object's tokens, the same for every image of the batch.
-        state = (Mt [1, ...], Ksum [B, 256]): precomputed source state shared by the batch."""
+        state = (Mt [1, ...], Ksum [B, 256]): precomputed source state shared by the batch.
+        x_mask / src_mask (uint8 [B * len]): padded positions of query_image_mask — Q rows resp.
+        K', V rows are zeroed (linear_attention.py:49-53)."""
         dev = x.device
         f16 = torch.float16
         split = self.split
         pl = 2 if split else 1
         if state is None:
-            mt, ksum = self._src_state(L, tag, src, B, ls)
+            mt, ksum = self._src_state(L, tag, src, B, ls, src_mask)
             mt_batched = True
         else:
             mt, ksum = state
             mt_batched = False
         qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
-        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split, x_shared=x_shared)
+        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split, x_shared=x_shared, row_mask=x_mask)
         msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
         ops.linear_ln(qz, None, mt, mt_batched, *L["n1"], B, lx, split, out16=msg)
         h = self._buf(tag + "h", (B * lx, pl * 512), f16, dev)
@@ -594,11 +600,12 @@ class OnePosePlus_model(nn.Module):
             b["state"] = self._encode_bank(*b["raw"], persistent=True)
         return b["state"]
 
-    def _coarse_transformer(self, q2, bank, B, S, N):
+    def _coarse_transformer(self, q2, bank, B, S, N, qmask=None):
         """LocalFeatureTransformer.forward (transformer.py:133-171): self layers update each
         sequence from itself; cross layers update BOTH from the pre-update tensors.  `bank` is the
         state of _encode_bank; with one shared object the 3D work of the first (self, cross) pair
-        that does not depend on the image comes from it."""
+        that does not depend on the image comes from it.  qmask (uint8 [B*S]) = query_image_mask:
+        it masks the 2D side only (transformer.py:150-159)."""
         dev = q2.device
         f16 = torch.float16
         pl = 2 if self.split else 1
@@ -611,14 +618,14 @@ class OnePosePlus_model(nn.Module):
             # state, the 3D side reads the shared 3D tokens in place (no per-image copies)
             L0, L1 = self._plan["coarse"][0], self._plan["coarse"][1]
             o2 = self._buf("q2_1", (B, S, pl * 256), f16, dev)
-            self._encoder_layer(L0, "c2_", cur2, cur2, B, S, S, o2)
+            self._encoder_layer(L0, "c2_", cur2, cur2, B, S, S, o2, x_mask=qmask, src_mask=qmask)
             d3 = bank["d3_l0"]
             ksum_b = self._buf("l1_ksum_b", (B, 256), torch.float32, dev)
             ksum_b.copy_(bank["l1_ksum"].expand(B, -1))
             o2b = self._buf("q2_0", (B, S, pl * 256), f16, dev)
             o3 = self._buf("d3_0", (B, N, pl * 256), f16, dev)
-            self._encoder_layer(L1, "c2_", o2, None, B, S, N, o2b, state=(bank["l1_mt"], ksum_b))
-            self._encoder_layer(L1, "c3_", d3, o2, B, N, S, o3, x_shared=True)
+            self._encoder_layer(L1, "c2_", o2, None, B, S, N, o2b, state=(bank["l1_mt"], ksum_b), x_mask=qmask)
+            self._encoder_layer(L1, "c3_", d3, o2, B, N, S, o3, x_shared=True, src_mask=qmask)
             cur2, cur3 = o2b, o3
             first = 2
         elif shared:
@@ -631,13 +638,13 @@ class OnePosePlus_model(nn.Module):
             o3 = self._buf(f"d3_{nxt}", (B, N, pl * 256), f16, dev)
             self_layer = names[i] == "self"
             self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
-                                S if self_layer else N, o2)
+                                S if self_layer else N, o2, x_mask=qmask, src_mask=qmask if self_layer else None)
             self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
-                                N if self_layer else S, o3)
+                                N if self_layer else S, o3, src_mask=None if self_layer else qmask)
             cur2, cur3 = o2, o3
         return cur2, cur3
 
-    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out):
+    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None):
         """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch.
         Enqueues everything up to the ordered match lists (capacity B*min(N,S)) and the device-side
         match count; nothing here synchronises.  Fills `out` with the full-capacity tensors."""
@@ -652,11 +659,15 @@ class OnePosePlus_model(nn.Module):
         ps_pt = self._buf("ps_pt", (B * N, ts), f32, dev)
         lse_pt = self._buf("lse_pt", (B, N), f32, dev)
         lse_px = self._buf("lse_px", (B, S), f32, dev)
+        if qmask is not None and not (self.coarse_lse_cols and self.coarse_colmax):
+            raise NotImplementedError("query_image_mask is built for the one-pass dual softmax "
+                                      "(coarse_lse_cols and coarse_colmax on)")
         if self.coarse_lse_cols:
             groups = (N + 31) // 32
             col_m = self._buf("lse_col_m", (B, groups, S), f32, dev)
             col_s = self._buf("lse_col_s", (B, groups, S), f32, dev)
-            ops.sim_lse_cols(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, col_m, col_s, lse_px, split)
+            ops.sim_lse_cols(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, col_m, col_s, lse_px, split,
+                             col_mask=qmask)
         else:
             pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
             ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
@@ -717,9 +728,11 @@ class OnePosePlus_model(nn.Module):
                      self._buf("lz_bi", (B, N), torch.int32, dev), self.split)
         return conf
 
-    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, mcount=None):
+    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, count=None):
         """FinePreprocess (fine_preprocess.py:32-55) -> loftr_fine -> FineMatching
-        (fine_matching.py:28-110) on the first M entries of the match lists."""
+        (fine_matching.py:28-110) on the first M entries of the match lists.  With `count` (the
+        device-side match counter) M is only the CAPACITY: every kernel reads the real number of
+        matches on the device, so nothing here needs the host to know it."""
         dev = fine_map.device
         f16, f32 = torch.float16, torch.float32
         split = self.split
@@ -731,8 +744,10 @@ class OnePosePlus_model(nn.Module):
         x32 = self._buf("fx32", (rows, 128), f32, dev)
         fine_layers = self.loftr_fine.layer_names if self.config["loftr_fine"]["enable"] else []
         b_ids, i_ids, j_ids, mkc = ids
+        dyn = {} if count is None else {"count": count}
+        dyn26 = {} if count is None else {"count": count, "rows_per_count": 26}
         ops.fine_gather(fine_map, bank["fine"], b_ids, i_ids, j_ids, None if fine_layers else x32, x[0], M,
-                        hf, wf, wc, stride, bank["N"], split, bank_shared=bank["Bb"] == 1)
+                        hf, wf, wc, stride, bank["N"], split, bank_shared=bank["Bb"] == 1, **dyn)
         cur = 0
         if fine_layers:
             qkv = self._buf("f_qkv", (rows, pl * 384), f16, dev)
@@ -742,17 +757,17 @@ class OnePosePlus_model(nn.Module):
             for i, name in enumerate(fine_layers):
                 L = self._plan["fine"][i]
                 last = i == len(fine_layers) - 1
-                ops.linear_act(x[cur], None, L["wqkv"], qkv, rows, 2, 256, split)
-                ops.fine_attention(qkv, att, M, name == "cross", split)
-                ops.linear_ln(att, None, L["merge16"], False, *L["n1"], 1, rows, split, out16=msg)
-                ops.linear_act(x[cur], msg, L["mlp0"], h, rows, 1, 256, split)
+                ops.linear_act(x[cur], None, L["wqkv"], qkv, rows, 2, 256, split, **dyn26)
+                ops.fine_attention(qkv, att, M, name == "cross", split, **dyn)
+                ops.linear_ln(att, None, L["merge16"], False, *L["n1"], 1, rows, split, out16=msg, **dyn26)
+                ops.linear_act(x[cur], msg, L["mlp0"], h, rows, 1, 256, split, **dyn26)
                 ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, rows, split, resid=x[cur],
-                              out16=None if last else x[1 - cur], out32=x32 if last else None)
+                              out16=None if last else x[1 - cur], out32=x32 if last else None, **dyn26)
                 cur = 1 - cur
         expec_f = torch.empty((M, 3), dtype=f32, device=dev)
         mkpts_f = torch.empty((M, 2), dtype=f32, device=dev)
         fine_scale = float(q_hw_i[0] / hf)
-        ops.fine_match(x32, mkc, b_ids, img_scale, expec_f, mkpts_f, M, fine_scale)
+        ops.fine_match(x32, mkc, b_ids, img_scale, expec_f, mkpts_f, M, fine_scale, **dyn)
         out.update({"expec_f": expec_f, "mkpts_query_f": mkpts_f})
 
     # ------------------------------------------------------------------ input checks
@@ -811,13 +826,19 @@ class OnePosePlus_model(nn.Module):
         absent after set_bank(); a bank given as [1, N, .] tensors or stride-0 expanded views is
         encoded once for the whole batch."""
         if self.training:
-            raise NotImplementedError(
-                "onepose_plus_plus_b200 builds the inference path only: call .eval() "
-                "(training/autograd is listed under 'next' in DESIGN.md)")
-        if data.get("query_image_mask") is not None:
-            raise NotImplementedError("query_image_mask (cold path, img_pad=False in every shipped "
-                                      "config) is not built")
+            # train_onepose_plus.py: differentiable PyTorch path on the same parameters (the CUDA
+            # kernels implement the inference forward only) — see train_path.py
+            from . import train_path
+            return train_path.forward_train(self, data)
         img, img_scale, bank_raw = self._check_inputs(data)
+        qmask = data.get("query_image_mask")
+        if qmask is not None:
+            # OnePosePlusModel.py:158: mask at coarse resolution, flattened to [B, S]; nonzero = valid
+            B_, H_, W_ = img.shape[0], img.shape[2], img.shape[3]
+            if qmask.numel() != B_ * (H_ // 8) * (W_ // 8) or qmask.shape[0] != B_:
+                raise ValueError(f"query_image_mask must be [B, H/8, W/8] = [{B_}, {H_ // 8}, {W_ // 8}], "
+                                 f"got {tuple(qmask.shape)}")
+            qmask = (qmask.to(img.device) != 0).to(torch.uint8).reshape(-1).contiguous()
         self._fwd_count += 1
         # kernels are enqueued on the current stream of the tensors' device
         with torch.no_grad(), torch.cuda.device(img.device):
@@ -827,38 +848,130 @@ class OnePosePlus_model(nn.Module):
                 self._plan = self._prepare(dev)
                 self._plan["device"] = dev
                 self._plan_sig = sig
+                self._graphs = {}
             if img.dtype != torch.uint8 and img.dtype != torch.float32:
                 img = img.float()
             img = img.contiguous()
-            B, _, H, W = img.shape
-            data.update({"bs": B, "q_hw_i": img.shape[2:]})
-            q2, fine_map, (hc, wc) = self._backbone(img)
-            data.update({"q_hw_c": torch.Size((hc, wc)), "q_hw_f": torch.Size(fine_map.shape[1:3])})
-            if bank_raw is None:
-                bank = self._resident_bank_state()
-            else:
-                kp, dco, dfine = bank_raw
-                # one object for the whole batch ([1, N, .] tensors or stride-0 expanded views)
-                one = kp.shape[0] == 1 or (B > 1 and kp.stride(0) == 0 and dco.stride(0) == 0
-                                           and dfine.stride(0) == 0)
-                if one:
-                    kp, dco, dfine = kp[:1], dco[:1], dfine[:1]
-                bank = self._encode_bank(kp.float().contiguous(), dco.float().contiguous(),
-                                         dfine.float().contiguous(), persistent=False)
-            N = bank["N"]
             if img_scale is not None:
                 img_scale = img_scale.to(device=dev, dtype=torch.float32).contiguous()
-            q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N)
-            out = {}
-            count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out)
-            M = int(count.item())  # the one host sync of the forward (the reference syncs in torch.where)
+            B, _, H, W = img.shape
             fine_on = self.config["fine_matching"]["enable"]
+            data.update({"bs": B, "q_hw_i": img.shape[2:], "q_hw_c": torch.Size((H // 8, W // 8)),
+                         "q_hw_f": torch.Size((H // 2, W // 2))})
             if fine_on:
                 data["W"] = self.fine_preprocess.W   # fine_preprocess.py:33 (not reached when disabled)
-            if fine_on and M > 0:
-                self._fine(fine_map, bank, (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"]),
-                           M, img_scale, hc, wc, data["q_hw_i"], out)
+            if self.use_cuda_graphs:
+                if qmask is not None:
+                    raise NotImplementedError("query_image_mask is not supported in CUDA-graph mode")
+                out, M = self._replay(img, img_scale, bank_raw, fine_on)
+            else:
+                out, count, cap = self._enqueue(img, img_scale, bank_raw, fine_on, dynamic=False, qmask=qmask)
+                M = out.pop("M")
             self._publish(data, out, M, dev, fine_on)
+
+    def _enqueue(self, img, img_scale, bank_raw, fine_on, dynamic, qmask=None):
+        """The whole forward as kernel launches on the current stream.  dynamic=False: one host
+        sync reads the match count M between the coarse and the fine stage (the reference syncs in
+        torch.where, coarse_matching.py:170) and the fine stage runs on exactly M matches.
+        dynamic=True: no sync at all — the fine stage is launched at its capacity
+        (B * min(N, S) matches) and reads M on the device; this is the capturable form."""
+        B, _, H, W = img.shape
+        q2, fine_map, (hc, wc) = self._backbone(img)
+        if bank_raw is None:
+            bank = self._resident_bank_state()
+        else:
+            kp, dco, dfine = bank_raw
+            # one object for the whole batch ([1, N, .] tensors or stride-0 expanded views)
+            one = kp.shape[0] == 1 or (B > 1 and kp.stride(0) == 0 and dco.stride(0) == 0
+                                       and dfine.stride(0) == 0)
+            if one:
+                kp, dco, dfine = kp[:1], dco[:1], dfine[:1]
+            bank = self._encode_bank(kp.float().contiguous(), dco.float().contiguous(),
+                                     dfine.float().contiguous(), persistent=False)
+        N = bank["N"]
+        q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N, qmask)
+        out = {}
+        count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask)
+        ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
+        if dynamic:
+            fcap = min(cap, B * min(N, hc * wc))
+            if fine_on:
+                self._fine(fine_map, bank, ids, fcap, img_scale, hc, wc, (H, W), out, count=count)
+            out["fcap"] = fcap
+        else:
+            M = int(count.item())  # the one host sync of the forward
+            if fine_on and M > 0:
+                self._fine(fine_map, bank, ids, M, img_scale, hc, wc, (H, W), out)
+            out["M"] = M
+        return out, count, cap
+
+    # ------------------------------------------------------------------ CUDA graphs
+    def enable_cuda_graphs(self, on=True):
+        """Latency mode (extension): capture the forward once per input signature
+        (B, H, W, N, dtypes) and replay it — one graph launch instead of ~115 kernel launches from
+        Python, one host sync at the END (to size the outputs) instead of one in the middle.  The
+        results are the same bits as the eager path.  Returned tensors are copies (the graph owns
+        its buffers); conf_matrix_mode "eager" therefore costs an extra copy of the matrix —
+        prefer "lazy"/"skip" here."""
+        self.use_cuda_graphs = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
+
+    def _replay(self, img, img_scale, bank_raw, fine_on):
+        resident = bank_raw is None
+        if resident:
+            bkey = ("resident", id(self._bank))
+        else:
+            one = bank_raw[0].shape[0] == 1 or (img.shape[0] > 1 and all(t.stride(0) == 0 for t in bank_raw))
+            if one:
+                bank_raw = tuple(t[:1] for t in bank_raw)
+            bkey = tuple((tuple(t.shape), t.dtype) for t in bank_raw)
+        key = (tuple(img.shape), img.dtype, img_scale is not None, bkey, fine_on, self.conf_matrix_mode,
+               self.coarse_colmax, self.coarse_lse_cols, self.kv_single_plane)
+        ent = self._graphs.get(key)
+        if ent is not None and ent["ws_epoch"] != self._ws_epoch:
+            ent = None            # a workspace buffer was re-allocated: the captured pointers are stale
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.clear()
+            s_img = torch.empty_like(img)
+            s_scale = torch.empty_like(img_scale) if img_scale is not None else None
+            s_bank = None if resident else tuple(torch.empty_like(t.contiguous()) for t in bank_raw)
+
+            def load():
+                s_img.copy_(img)
+                if s_scale is not None:
+                    s_scale.copy_(img_scale)
+                if s_bank is not None:
+                    for d, t in zip(s_bank, bank_raw):
+                        d.copy_(t)
+            load()
+            # warm-up outside the capture: sizes the workspace, sets kernel attributes
+            self._enqueue(s_img, s_scale, s_bank, fine_on, dynamic=True)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out, count, cap = self._enqueue(s_img, s_scale, s_bank, fine_on, dynamic=True)
+            ent = {"graph": g, "out": out, "count": count, "ws_epoch": self._ws_epoch,
+                   "inputs": (s_img, s_scale, s_bank)}
+            self._graphs[key] = ent
+        s_img, s_scale, s_bank = ent["inputs"]
+        s_img.copy_(img)
+        if s_scale is not None:
+            s_scale.copy_(img_scale)
+        if s_bank is not None:
+            for d, t in zip(s_bank, bank_raw):
+                d.copy_(t)
+        ent["graph"].replay()
+        src = ent["out"]
+        M = min(int(ent["count"].item()), src["fcap"])   # the only host sync, after everything is queued
+        out = {k: (v[:M].clone() if torch.is_tensor(v) and k != "conf_matrix" else v) for k, v in src.items()}
+        if torch.is_tensor(src["conf_matrix"]):
+            out["conf_matrix"] = src["conf_matrix"].clone()
+        elif src["conf_matrix"] is not None:     # lazy handle: re-issue it for this forward
+            out["conf_matrix"] = LazyConfMatrix(self, *src["conf_matrix"]._args)
+        return out, M
 
     def _publish(self, data, out, M, dev, fine_on):
         """Write the reference's output keys (coarse_matching.py:231-241, fine_matching.py:46-55,107-110)."""

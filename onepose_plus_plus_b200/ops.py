@@ -50,14 +50,6 @@ def conv1_gemm(image, w64, a_buf, out, split):
     return out
 
 
-def conv1_7x7(image, w_t, bias, out, split):
-    B, _, H, W = image.shape
-    _chk(image, torch.float32, "image")
-    call("opp_conv1_7x7", ptr(image), ptr(w_t), ptr(bias), ptr(out), B, H, W, w_t.shape[1],
-         int(split), stream())
-    return out
-
-
 def conv2d_nhwc(x, w, bias, out, ksize, stride, split, act=0, resid=None, slope=0.01, tok=None,
                 pe=None, up=None):
     """x NHWC fp16 [B,H,W,planes*Cin_pad]; w fp16 [Cout_pad, planes*k*k*Cin_pad];
@@ -72,15 +64,6 @@ def conv2d_nhwc(x, w, bias, out, ksize, stride, split, act=0, resid=None, slope=
     return out
 
 
-def upsample2x_add(a, b, out, split):
-    B, h, w, C = b.shape
-    _chk(a, torch.float16, "a")
-    _chk(b, torch.float16, "b")
-    call("opp_upsample2x_add", ptr(a), ptr(b), ptr(out), B, h, w, C // (2 if split else 1),
-         int(split), stream())
-    return out
-
-
 def kpt_encode(kpts, desc, mlp, stats, tok, split):
     B, N, _ = kpts.shape
     _chk(kpts, torch.float32, "keypoints3d")
@@ -91,10 +74,14 @@ def kpt_encode(kpts, desc, mlp, stats, tok, split):
          ptr(w3), ptr(b3), ptr(w4), ptr(b4), ptr(tok), B, N, int(split), stream())
 
 
-def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None, batches=1, a0_shared=False):
+def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None, batches=1, a0_shared=False,
+               count=None, rows_per_count=1, row_mask=None):
     """a_i fp16 [rows, planes*k_i]; w fp16 [n, planes*(k0+k1)]; out fp16 [rows, planes*n]
     (out_split=False with split=True: split operands, single-plane output [rows, n]).
-    batches > 1: rows is per batch; a0_shared: a0 is [1, rows, ..] shared by every batch."""
+    batches > 1: rows is per batch; a0_shared: a0 is [1, rows, ..] shared by every batch.
+    count (int32 device tensor): `rows` is the capacity, the kernel uses count * rows_per_count rows.
+    row_mask (uint8 [batches*rows]): rows with mask 0 are written as zeros."""
+    _chk(row_mask, torch.uint8, "row_mask")
     _chk(a0, torch.float16, "a0")
     _chk(a1, torch.float16, "a1")
     _chk(w, torch.float16, "w")
@@ -103,25 +90,30 @@ def linear_act(a0, a1, w, out, rows, act, act_cols, split, out_split=None, batch
     k1 = a1.shape[-1] // planes if a1 is not None else 0
     if split and out_split is False:
         call("opp_linear_act_f16_out1", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
-             act_cols, stream())
+             act_cols, ptr(row_mask), stream())
         return out
-    if batches > 1 or a0_shared:
+    if count is not None:
+        call("opp_linear_act_f16_dyn", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, ptr(count),
+             rows_per_count, w.shape[0], act, act_cols, int(split), stream())
+        return out
+    if batches > 1 or a0_shared or row_mask is not None:
         call("opp_linear_act_f16_b", ptr(a0), k0, int(a0_shared), ptr(a1), k1, ptr(w), ptr(out), batches, rows,
-             w.shape[0], act, act_cols, int(split), stream())
+             w.shape[0], act, act_cols, int(split), ptr(row_mask), stream())
         return out
     call("opp_linear_act_f16", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(out), rows, w.shape[0], act,
          act_cols, int(split), stream())
     return out
 
 
-def linear_q(x16, wq, ksum, out, batches, rows, v_len, split, eps=1e-6, x_shared=False):
+def linear_q(x16, wq, ksum, out, batches, rows, v_len, split, eps=1e-6, x_shared=False, row_mask=None):
+    _chk(row_mask, torch.uint8, "row_mask")
     call("opp_linear_q_f16", ptr(x16), ptr(wq), ptr(ksum), ptr(out), batches, rows, wq.shape[0],
-         float(v_len), float(eps), int(split), int(x_shared), stream())
+         float(v_len), float(eps), int(split), int(x_shared), ptr(row_mask), stream())
     return out
 
 
 def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=None, out16=None,
-              out32=None, eps=1e-5, resid_shared=False):
+              out32=None, eps=1e-5, resid_shared=False, count=None, rows_per_count=1):
     _chk(a0, torch.float16, "a0")
     _chk(w, torch.float16, "w")
     _chk(resid, torch.float16, "resid")
@@ -129,6 +121,10 @@ def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=Non
     k0 = a0.shape[-1] // planes
     k1 = a1.shape[-1] // planes if a1 is not None else 0
     n = w.shape[-2]
+    if count is not None:
+        call("opp_linear_ln_dyn", ptr(a0), k0, ptr(a1), k1, ptr(w), ptr(gamma), ptr(beta), float(eps),
+             ptr(resid), ptr(out16), ptr(out32), rows, ptr(count), rows_per_count, n, int(split), stream())
+        return
     call("opp_linear_ln", ptr(a0), k0, ptr(a1), k1, ptr(w), int(w_batched), ptr(gamma), ptr(beta),
          float(eps), ptr(resid), int(resid_shared), ptr(out16), ptr(out32), batches, rows, n, int(split),
          stream())
@@ -167,14 +163,17 @@ def sim_conf(a, b, lse_own, lse_other, own_is_pt, conf, batches, rows, cols, k, 
 
 
 def sim_lse_cols(a, b, batches, rows, cols, k, scale, part_m, part_s, lse_rows, col_m, col_s, lse_cols,
-                 split):
-    """lse over columns for every row (as sim_lse) AND lse over rows for every column, one GEMM pass."""
+                 split, col_mask=None):
+    """lse over columns for every row (as sim_lse) AND lse over rows for every column, one GEMM pass.
+    col_mask uint8 [batches, cols]: masked columns (0) get sim - 1e9 and lse_cols = +inf (conf = 0)."""
+    _chk(col_mask, torch.uint8, "col_mask")
     tiles = sim_tiles(cols)
     groups = (rows + 31) // 32
     call("opp_sim_lse_cols", ptr(a), ptr(b), ptr(part_m), ptr(part_s), ptr(col_m), ptr(col_s), batches,
-         rows, cols, k, float(scale), int(split), stream())
+         rows, cols, k, float(scale), int(split), ptr(col_mask), stream())
     call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse_rows), batches * rows, tiles, stream())
-    call("opp_lse_col_finalize", ptr(col_m), ptr(col_s), ptr(lse_cols), batches, groups, cols, stream())
+    call("opp_lse_col_finalize", ptr(col_m), ptr(col_s), ptr(lse_cols), batches, groups, cols, ptr(col_mask),
+         stream())
 
 
 def sim_conf_colmax(a, b, lse_own, lse_other, conf, batches, rows, cols, k, scale, part_val, part_idx,
@@ -202,16 +201,16 @@ def match_select(pt_val, pt_idx, px_idx, kpts, img_scale, batch, l, hc, wc, thr,
 
 
 def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stride, n, split,
-                bank_shared=False):
+                bank_shared=False, count=None):
     _chk(desc3d, torch.float32, "descriptors3d_db")
     call("opp_fine_gather", ptr(fine), ptr(desc3d), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x32),
-         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), stream())
+         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), ptr(count), stream())
 
 
-def fine_attention(qkv, msg, m, cross, split, eps=1e-6):
-    call("opp_fine_attention", ptr(qkv), ptr(msg), m, int(cross), float(eps), int(split), stream())
+def fine_attention(qkv, msg, m, cross, split, eps=1e-6, count=None):
+    call("opp_fine_attention", ptr(qkv), ptr(msg), m, int(cross), float(eps), int(split), ptr(count), stream())
 
 
-def fine_match(x32, mkpts_c, b_ids, img_scale, expec_f, mkpts_f, m, fine_scale):
+def fine_match(x32, mkpts_c, b_ids, img_scale, expec_f, mkpts_f, m, fine_scale, count=None):
     call("opp_fine_match", ptr(x32), ptr(mkpts_c), ptr(b_ids), ptr(img_scale), ptr(expec_f),
-         ptr(mkpts_f), m, float(fine_scale), stream())
+         ptr(mkpts_f), m, float(fine_scale), ptr(count), stream())

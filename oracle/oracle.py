@@ -131,9 +131,14 @@ def keypoint_encoding(sd, kpts, descriptors, prefix="kpt_3d_pos_encoding.encoder
 # ---------------------------------------------------------------------------------------------
 # transformer  (loftr_module/linear_attention.py:29-61, transformer.py:65-94, 133-171)
 # ---------------------------------------------------------------------------------------------
-def linear_attention(q, k, v, eps=1e-6):
+def linear_attention(q, k, v, eps=1e-6, q_mask=None, kv_mask=None):
     Q = F.elu(q) + 1
     K = F.elu(k) + 1
+    if q_mask is not None:      # linear_attention.py:49-53: padded positions are zeroed
+        Q = Q * q_mask[:, :, None, None]
+    if kv_mask is not None:
+        K = K * kv_mask[:, :, None, None]
+        v = v * kv_mask[:, :, None, None]
     v_len = v.size(1)
     v = v / v_len
     KV = torch.einsum("nshd,nshv->nhdv", K, v)
@@ -141,13 +146,13 @@ def linear_attention(q, k, v, eps=1e-6):
     return torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * v_len
 
 
-def encoder_layer(sd, p, x, source, nhead):
+def encoder_layer(sd, p, x, source, nhead, x_mask=None, source_mask=None):
     bs, d = x.size(0), x.size(2)
     dim = d // nhead
     q = F.linear(x, sd[p + "q_proj.weight"]).view(bs, -1, nhead, dim)
     k = F.linear(source, sd[p + "k_proj.weight"]).view(bs, -1, nhead, dim)
     v = F.linear(source, sd[p + "v_proj.weight"]).view(bs, -1, nhead, dim)
-    msg = linear_attention(q, k, v).reshape(bs, -1, d)
+    msg = linear_attention(q, k, v, q_mask=x_mask, kv_mask=source_mask).reshape(bs, -1, d)
     msg = F.layer_norm(F.linear(msg, sd[p + "merge.weight"]), (d,), sd[p + "norm1.weight"],
                        sd[p + "norm1.bias"], 1e-5)
     msg = F.linear(F.relu(F.linear(torch.cat([x, msg], 2), sd[p + "mlp.0.weight"])),
@@ -156,18 +161,21 @@ def encoder_layer(sd, p, x, source, nhead):
     return x + msg
 
 
-def local_feature_transformer(sd, prefix, cfg, desc3d, desc2d, collect=None):
+def local_feature_transformer(sd, prefix, cfg, desc3d, desc2d, collect=None, query_mask=None):
     """transformer.py:133-171.  desc3d [B,C,L] -> [B,L,C]; cross layers update both sequences from
-    the PRE-update tensors (transformer.py:154-159)."""
+    the PRE-update tensors (transformer.py:154-159); query_mask [B, S] masks the 2D side only
+    (:150-159: x_mask and source_mask of the 2D self layer, x_mask of 2D<-3D, source_mask of 3D<-2D)."""
     names = list(cfg["layer_names"]) * cfg["layer_iter_n"]
     d3 = desc3d.transpose(1, 2)
     d2 = desc2d
     for i, name in enumerate(names):
         p = f"{prefix}layers.{i}."
         if name == "self":
-            d2, d3 = encoder_layer(sd, p, d2, d2, cfg["nhead"]), encoder_layer(sd, p, d3, d3, cfg["nhead"])
+            d2, d3 = (encoder_layer(sd, p, d2, d2, cfg["nhead"], query_mask, query_mask),
+                      encoder_layer(sd, p, d3, d3, cfg["nhead"]))
         elif name == "cross":
-            d2, d3 = encoder_layer(sd, p, d2, d3, cfg["nhead"]), encoder_layer(sd, p, d3, d2, cfg["nhead"])
+            d2, d3 = (encoder_layer(sd, p, d2, d3, cfg["nhead"], x_mask=query_mask),
+                      encoder_layer(sd, p, d3, d2, cfg["nhead"], source_mask=query_mask))
         else:
             raise NotImplementedError(name)
         if collect is not None:
@@ -178,11 +186,15 @@ def local_feature_transformer(sd, prefix, cfg, desc3d, desc2d, collect=None):
 # ---------------------------------------------------------------------------------------------
 # coarse matching  (utils/coarse_matching.py:76-123, 125-242; inference branch)
 # ---------------------------------------------------------------------------------------------
-def coarse_matching(cfg, feat3d, feat2d, data):
+def coarse_matching(cfg, feat3d, feat2d, data, mask_query=None):
     c = feat3d.size(2)
     a = feat3d / c ** 0.5
     b = feat2d / c ** 0.5
     sim = torch.einsum("nlc,nsc->nls", a, b) / (cfg["dual_softmax"]["temperature"] + 1e-4)
+    if mask_query is not None:   # coarse_matching.py:108-114: -1e9 added on the masked query cells
+        neg = torch.zeros_like(sim)
+        neg[~mask_query.bool()[:, None].expand_as(sim)] = -1e9
+        sim = sim + neg
     conf = F.softmax(sim, 1) * F.softmax(sim, 2)
     data["conf_matrix"] = conf
     hc, wc = data["q_hw_c"]
@@ -272,9 +284,10 @@ def forward(sd, data, cfg=DEFAULT_CONFIG, stages=None):
     if stages is not None:
         stages.update(feat_c=feat_c, feat_f=feat_f, tok2d_in=q_c, tok3d_in=d3.transpose(1, 2))
         stages["layers"] = []
+    query_mask = data["query_image_mask"].flatten(-2) if "query_image_mask" in data else None
     d3, q_c = local_feature_transformer(sd, "loftr_coarse.", cfg["loftr_coarse"], d3, q_c,
-                                        None if stages is None else stages["layers"])
-    coarse_matching(cfg["coarse_matching"], d3, q_c, data)
+                                        None if stages is None else stages["layers"], query_mask)
+    coarse_matching(cfg["coarse_matching"], d3, q_c, data, mask_query=query_mask)
     W = cfg["loftr_fine"]["window_size"]
     f3d, f2d = fine_preprocess(W, cfg["loftr_fine"]["d_model"], data, data["descriptors3d_db"], feat_f)
     if f2d.size(0) != 0 and cfg["loftr_fine"]["enable"]:

@@ -179,6 +179,18 @@ def hetero_workload(sd, h=256, w=320, n_points=1500, n_planted=700, batch=3, see
     }
 
 
+def pad_mask(batch, hc, wc, seed=3):
+    """query_image_mask as the img_pad data flow produces it (bool [B, hc, wc], False = padding):
+    every image keeps a different top-left rectangle of valid coarse cells."""
+    g = torch.Generator().manual_seed(seed)
+    m = torch.zeros(batch, hc, wc, dtype=torch.bool)
+    for b in range(batch):
+        vh = hc - int(torch.randint(0, max(hc // 3, 1) + 1, (1,), generator=g))
+        vw = wc - int(torch.randint(0, max(wc // 3, 1) + 1, (1,), generator=g))
+        m[b, :vh, :vw] = True
+    return m
+
+
 def random_workload(h=512, w=512, n_points=5000, batch=1, seed=1):
     """BASELINE.json config 1 taken literally: random image, random descriptors (yields M = 0)."""
     g = torch.Generator().manual_seed(seed)

@@ -108,8 +108,8 @@ def timing(label):
 # options: C-ABI switches (opp_set_option) except "colmax" / "lse_cols", host-flow switches of the
 # model (column maxima of conf / column log-sum-exp from the first pass instead of a second GEMM).  Every config
 # starts from the defaults; its label lists the options it turns on.
-EXPERIMENTAL_CHECK = {"fine_attn_vec": "fine_attn_vec", "kv1": "kv_single_plane"}
-DEFAULTS = {"colmax": 1, "lse_cols": 1, "fine_attn_vec": 0, "kv1": 0, "lazy": 0}
+EXPERIMENTAL_CHECK = {}
+DEFAULTS = {"colmax": 1, "lse_cols": 1, "kv1": 0, "lazy": 0, "gemm_w_resident": 0}
 MODEL_ATTR = {"colmax": "coarse_colmax", "lse_cols": "coarse_lse_cols", "kv1": "kv_single_plane",
               "lazy": "conf_matrix_mode"}
 ATTR_VALUE = {"lazy": {0: "eager", 1: "lazy"}}
@@ -138,7 +138,7 @@ for cfg in configs:
         first = False
     for k, v in cfg.items():
         if v and k in EXPERIMENTAL_CHECK:   # these set and restore their own option
-            guarded(f"{EXPERIMENTAL_CHECK[k]}[{label}]", kernel_checks.EXPERIMENTAL[EXPERIMENTAL_CHECK[k]])
+            guarded(f"{EXPERIMENTAL_CHECK[k]}[{label}]", kernel_checks.CHECKS[EXPERIMENTAL_CHECK[k]])
     apply(cfg)
     guarded(f"kv_state[{label}]", kernel_checks.check_kv_state)
     guarded(f"golden[{label}]", lambda label=label: golden(label))

@@ -124,7 +124,7 @@ def check_linear_q():
             out = torch.full((B * rows, pl * d), float("nan"), device=DEV, dtype=torch.half)
             x, wq = _planes(xf, split), _planes(wf, split)
             _lib.call("opp_linear_q_f16", _lib.ptr(x), _lib.ptr(wq), _lib.ptr(ksum), _lib.ptr(out), B, rows,
-                      d, 4096.0, 1e-6, split, int(shared), _lib.stream())
+                      d, 4096.0, 1e-6, split, int(shared), None, _lib.stream())
             torch.cuda.synchronize()
             xq = _q(xf, split).double()
             if shared:
@@ -281,25 +281,6 @@ def check_sim():
 
 
 # ------------------------------------------------------------------------------------------ SIMT
-def _conv1_case(split, B, H, W, C):
-    img = torch.rand(B, 1, H, W, device=DEV)
-    w = _rand(C, 1, 7, 7, scale=0.15, seed=2)
-    bias = _rand(C, seed=3) * 0.1
-    pl = 2 if split else 1
-    out = torch.full((B, H // 2, W // 2, pl * C), float("nan"), device=DEV, dtype=torch.half)
-    w_t = w.view(C, 49).t().contiguous()
-    _lib.call("opp_conv1_7x7", _lib.ptr(img), _lib.ptr(w_t), _lib.ptr(bias), _lib.ptr(out), B, H, W,
-              C, split, _lib.stream())
-    torch.cuda.synchronize()
-    ref = torch.relu(F.conv2d(img.double(), w.double(), bias.double(), stride=2, padding=3)).permute(0, 2, 3, 1).float()
-    _close(f"conv1_7x7 split={split} {H}x{W}", _unplanes(out, split), ref, *_tol(split, (1e-3, 1e-3), (2e-6, 2e-6)))
-
-
-def check_conv1():
-    for split in (0, 1):
-        _conv1_case(split, 2, 96, 128, 128)
-
-
 def _conv1_gemm_case(split, B, H, W, C, u8):
     """conv1 as im2col + one 64-wide tcgen05 K chunk (bias in K column 49), fp32 and uint8 images"""
     if u8:
@@ -328,21 +309,6 @@ def check_conv1_gemm():
     for split in (0, 1):
         _conv1_gemm_case(split, 2, 96, 128, 128, False)
         _conv1_gemm_case(split, 1, 72, 200, 128, True)     # ragged 16x16 im2col tiles, uint8 image
-
-
-def check_upsample():
-    for split in (0, 1):
-        B, h, w, C = 2, 30, 40, 208
-        af, bf = _rand(B, 2 * h, 2 * w, C, seed=1), _rand(B, h, w, C, seed=2)
-        a, b = _planes(af, split), _planes(bf, split)
-        out = torch.empty_like(a)
-        _lib.call("opp_upsample2x_add", _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), B, h, w, C, split,
-                  _lib.stream())
-        torch.cuda.synchronize()
-        up = F.interpolate(_q(bf, split).permute(0, 3, 1, 2), scale_factor=2.0, mode="bilinear",
-                           align_corners=True).permute(0, 2, 3, 1)
-        _close(f"upsample2x_add split={split}", _unplanes(out, split), _q(af, split) + up,
-               *_tol(split, (1e-3, 2e-3), (2e-6, 2e-6)))
 
 
 def check_kpt_encode():
@@ -463,7 +429,7 @@ def check_fine():
         x32 = torch.empty(M * 26, 128, device=DEV)
         x16 = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
         _lib.call("opp_fine_gather", _lib.ptr(fine), _lib.ptr(desc), _lib.ptr(b_ids), _lib.ptr(i_ids),
-                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, 0, _lib.stream())
+                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, 0, None, _lib.stream())
         torch.cuda.synchronize()
         unf = F.unfold(_q(finef, split).permute(0, 3, 1, 2), kernel_size=5, stride=4, padding=2)
         unf = unf.view(B, 128, 25, -1).permute(0, 3, 2, 1)  # n l ww c
@@ -476,7 +442,7 @@ def check_fine():
         qkv = _planes(qkvf, split)
         for cross in (0, 1):
             msg = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
-            _lib.call("opp_fine_attention", _lib.ptr(qkv), _lib.ptr(msg), M, cross, 1e-6, split, _lib.stream())
+            _lib.call("opp_fine_attention", _lib.ptr(qkv), _lib.ptr(msg), M, cross, 1e-6, split, None, _lib.stream())
             torch.cuda.synchronize()
             t = _q(qkvf, split).double().view(M, 26, 3, 8, 16)
             Q, K, V = t[:, :, 0], t[:, :, 1], t[:, :, 2]
@@ -507,7 +473,7 @@ def check_fine():
     ef = torch.empty(M, 3, device=DEV)
     mf = torch.empty(M, 2, device=DEV)
     _lib.call("opp_fine_match", _lib.ptr(xf), _lib.ptr(mkc), _lib.ptr(b_ids), _lib.ptr(scale),
-              _lib.ptr(ef), _lib.ptr(mf), M, 2.0, _lib.stream())
+              _lib.ptr(ef), _lib.ptr(mf), M, 2.0, None, _lib.stream())
     torch.cuda.synchronize()
     x = xf.view(M, 26, 128)
     sim = torch.einsum("mc,mrc->mr", x[:, 0], x[:, 1:]) / math.sqrt(128)
@@ -523,9 +489,7 @@ def check_fine():
     _close("fine_match mkpts_f", mf, mkc + co * 2 * (2.0 * scale[b_ids][:, [1, 0]]), 1e-5, 1e-4)
 
 
-# ------------------------------------------------------------------------------ experimental paths
-# Kernels that are built but not yet selected by default (scripts/variant_probe.py runs these on
-# a GPU before a default is flipped); they are NOT part of CHECKS / the pytest -m gpu suite.
+# ------------------------------------------------------------------------------ one-pass dual softmax
 def check_sim_colmax():
     for split in (0, 1):
         for (B, L, S, K) in [(2, 700, 520, 256), (1, 300, 100, 256), (1, 5000, 4096, 256)]:
@@ -613,41 +577,6 @@ def check_kv_single_plane():
     _close("kv1 mt", _unplanes(mt, 1), ref_mt, 2e-5, 1e-6)
 
 
-def check_upsample_rows():
-    _lib.set_option("upsample_rows", 1)
-    try:
-        check_upsample()
-    finally:
-        _lib.set_option("upsample_rows", 0)
-
-
-def check_conv1_px4():
-    _lib.set_option("conv1_px4", 1)
-    try:
-        for split in (0, 1):
-            _conv1_case(split, 2, 96, 128, 128)
-            _conv1_case(split, 1, 72, 200, 128)    # ragged in x (100 = 64 + 36) and y (36 = 2 x 16 + 4)
-    finally:
-        _lib.set_option("conv1_px4", 0)
-
-
-def check_fine_attn_vec():
-    _lib.set_option("fine_attn_vec", 1)
-    try:
-        check_fine()
-    finally:
-        _lib.set_option("fine_attn_vec", 0)
-
-
-def check_conv1_ragged():
-    for split in (0, 1):
-        _conv1_case(split, 1, 72, 200, 128)
-
-
-EXPERIMENTAL = {"sim_colmax": check_sim_colmax, "sim_lse_cols": check_sim_lse_cols, "upsample_rows": check_upsample_rows,
-                "conv1_px4": check_conv1_px4, "conv1_ragged": check_conv1_ragged,
-                "fine_attn_vec": check_fine_attn_vec, "kv_single_plane": check_kv_single_plane}
-
 CHECKS = {
     "linear_act": check_linear_act,
     "linear_ln": check_linear_ln,
@@ -655,13 +584,14 @@ CHECKS = {
     "linear_act_shared": check_linear_act_shared,
     "conv": check_conv,
     "sim": check_sim,
-    "conv1": check_conv1,
     "conv1_gemm": check_conv1_gemm,
-    "upsample": check_upsample,
     "kpt_encode": check_kpt_encode,
     "kv_state": check_kv_state,
     "match_select": check_match_select,
     "fine": check_fine,
+    "sim_colmax": check_sim_colmax,
+    "sim_lse_cols": check_sim_lse_cols,
+    "kv_single_plane": check_kv_single_plane,
 }
 
 

@@ -41,15 +41,12 @@ def test_version_and_tiles_without_gpu():
 
 def test_runtime_options_roundtrip():
     """opp_set_option / opp_get_option (include/opp_b200.h): known names toggle, unknown names fail."""
-    for name in ("kv_mma", "conv1_staged", "upsample_rows", "conv1_px4", "fine_attn_vec"):
+    for name in ("gemm_w_resident",):
         before = _lib.get_option(name)
         assert before in (0, 1)
         _lib.set_option(name, 1 - before)
         assert _lib.get_option(name) == 1 - before
         _lib.set_option(name, before)
-    assert _lib.get_option("kv_mma") == 1 and _lib.get_option("conv1_staged") == 1   # validated defaults
-    for name in ("upsample_rows", "conv1_px4", "fine_attn_vec"):                        # not validated yet
-        assert _lib.get_option(name) == 0
     with pytest.raises(ValueError):
         _lib.set_option("no_such_option", 1)
     assert _lib.get_option("no_such_option") == -1
@@ -76,9 +73,6 @@ def test_no_cpu_fallback_and_config_errors():
     m = OnePosePlus_model(oracle.DEFAULT_CONFIG).eval()
     data = workload.random_workload(64, 64, 50)
     with pytest.raises(RuntimeError, match="no CPU path"):
-        m(data)
-    m.train()
-    with pytest.raises(NotImplementedError):
         m(data)
     import copy
     bad = copy.deepcopy(oracle.DEFAULT_CONFIG)

@@ -135,6 +135,73 @@ def test_resident_bank_uint8_and_lazy_conf_are_bit_identical():
         assert torch.equal(base[k], e[k]), f"skip conf: {k}"
 
 
+def test_query_image_mask_parity_vs_oracle():
+    """img_pad data flow (OnePosePlusModel.py:158-167, linear_attention.py:49-53,
+    coarse_matching.py:108-114): padded coarse cells are zeroed in Q / K / V of the 2D side and get
+    -1e9 in the similarity matrix.  Distinct valid rectangles per batch element."""
+    sd = _sd()
+    data, _ = workload.planted_workload(sd, 256, 320, 1500, 700, batch=3)
+    data["query_image_mask"] = workload.pad_mask(3, 32, 40)
+    ref = {k: v.clone() for k, v in data.items()}
+    oracle.forward(sd, ref)
+    got = parity.run_cuda(data)
+    rep = parity.compare(got, ref)
+    print("query mask", rep)
+    assert rep["M"] >= 100
+    conf = got["conf_matrix"].cpu()
+    assert (conf - ref["conf_matrix"]).abs().max().item() <= 1e-3
+    pad = ~data["query_image_mask"].flatten(1)
+    assert conf.transpose(1, 2)[pad].abs().max().item() == 0.0, "padded cells must have conf exactly 0"
+    # no match lands on a padded cell, and the mask really changes the result
+    assert not pad[got["b_ids"].cpu(), got["j_ids"].cpu()].any()
+    plain = parity.run_cuda({k: v for k, v in data.items() if k != "query_image_mask"})
+    assert plain["b_ids"].numel() != got["b_ids"].numel() or not torch.equal(plain["mconf"], got["mconf"])
+
+
+def test_cuda_graph_mode_is_bit_identical():
+    """enable_cuda_graphs(): the captured forward (fine stage at capacity, match count read on the
+    device, one sync at the end) returns the same bits as the eager path — per-call banks, resident
+    bank, M = 0 — and survives shape changes and replays."""
+    sd = _sd()
+    m = parity.cuda_model()
+    keys = ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f", "mkpts_3d_db", "mkpts_query_c",
+            "conf_matrix")
+    cases = [workload.planted_workload(sd, 512, 512, 5000, 3000, batch=1)[0],
+             workload.planted_workload(sd, 256, 320, 1500, 700, batch=3)[0],
+             workload.random_workload(192, 192, 2000)]
+    eager = [parity.run_cuda(d) for d in cases]
+    try:
+        m.enable_cuda_graphs(True)
+        for rep in range(2):            # second round replays the cached graphs
+            for d, e in zip(cases, eager):
+                g = parity.run_cuda(d)
+                for k in keys:
+                    if k in e:
+                        assert torch.equal(e[k], g[k]), f"graph mode: {k} differs (round {rep})"
+                assert g["gt_mask"].shape == e["gt_mask"].shape and g["W"] == 5
+        # outputs are copies: a later replay must not change tensors handed out earlier
+        first = parity.run_cuda(cases[0])
+        snap = first["mkpts_query_f"].clone()
+        other = dict(cases[0])
+        other["query_image"] = torch.rand_like(other["query_image"])
+        parity.run_cuda(other)
+        assert torch.equal(first["mkpts_query_f"], snap)
+        # resident bank + uint8 frames under graphs
+        d0 = cases[0]
+        m.set_bank(d0["keypoints3d"], d0["descriptors3d_db"], d0["descriptors3d_coarse_db"])
+        img8 = (d0["query_image"] * 255).round().to(torch.uint8)
+        ref = parity.run_cuda({**d0, "query_image": img8.float() / 255})
+        m.enable_cuda_graphs(False)
+        m.enable_cuda_graphs(True)
+        r = {"query_image": img8.cuda(), "query_image_scale": d0["query_image_scale"].cuda()}
+        m(r)
+        for k in keys[:-1]:
+            assert torch.equal(ref[k], r[k]), k
+    finally:
+        m.enable_cuda_graphs(False)
+        m.clear_bank()
+
+
 def test_workspace_is_bounded_across_shapes():
     """Different point counts / image sizes reuse one allocation per buffer name (high-water mark)."""
     m = parity.cuda_model()
@@ -226,19 +293,19 @@ def test_shared_bank_views_match_materialised_bank():
         assert torch.equal(a[k], shared[k]), k
 
 
-def test_alternate_kernels_behind_options():
-    """The SIMT kv_partial and the unstaged conv1 kernels stay in the library behind
-    opp_set_option: they must keep passing their kernel checks and the golden end-to-end parity."""
-    from onepose_plus_plus_b200 import _lib
-    from tests import kernel_checks
+def test_four_pass_dual_softmax_flow_matches():
+    """The older flow (two lse + two conf GEMM passes, index-based mutual test) stays selectable
+    (model.coarse_colmax / coarse_lse_cols = False): same matches as the one-pass default."""
+    m = parity.cuda_model()
     case = golden_io.cases()[0]
     data, z = golden_io.load(case)
-    for name, check in (("kv_mma", kernel_checks.check_kv_state), ("conv1_staged", kernel_checks.check_conv1)):
-        default = _lib.get_option(name)
-        try:
-            _lib.set_option(name, 1 - default)
-            check()
-            got = parity.run_cuda(data)
-            parity.compare(got, {k: z[k] for k in z.files}, max_borderline=0)
-        finally:
-            _lib.set_option(name, default)
+    a = parity.run_cuda(data)
+    try:
+        m.coarse_colmax = m.coarse_lse_cols = False
+        b = parity.run_cuda(data)
+        parity.compare(b, {k: z[k] for k in z.files}, max_borderline=0)
+    finally:
+        m.coarse_colmax = m.coarse_lse_cols = True
+    for k in ("b_ids", "i_ids", "j_ids"):
+        assert torch.equal(a[k], b[k])
+    assert torch.allclose(a["mconf"], b["mconf"], atol=1e-6) and torch.allclose(a["conf_matrix"], b["conf_matrix"], atol=1e-6)
