@@ -373,6 +373,39 @@ def main():
     h2d = imgs8_host.numel() + scale_host.numel() * 4
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
 
+    # pose stage on the device: matcher + batched RANSAC-PnP per step, vs the
+    # reference's per-frame cv2.solvePnPRansac on the host (metric_utils.py:121-204)
+    pose = None
+    if rank == 0:
+        try:
+            from onepose_plus_plus_b200 import pnp as dpnp
+            Kmat = torch.tensor([[600.0, 0, W / 2], [0, 600.0, H / 2], [0, 0, 1]], device=dev).expand(B, 3, 3).contiguous()
+
+            def step_pose():
+                dd = step_resident()
+                return dd, dpnp.ransac_pnp_batched(dd["m_bids"], dd["mkpts_3d_db"], dd["mkpts_query_f"], Kmat,
+                                                   reprojection_error=5.0)
+            ms_pose = cuda_time(lambda: step_pose(), max(args.steps // 2, 3))
+            dd, rr = step_pose()
+            ms_pnp = cuda_time(lambda: dpnp.ransac_pnp_batched(dd["m_bids"], dd["mkpts_3d_db"], dd["mkpts_query_f"],
+                                                               Kmat, reprojection_error=5.0), 5)
+            pose = {"frames_per_s_matcher_plus_pnp": B / ms_pose * 1e3, "ms_per_step": ms_pose,
+                    "pnp_ms_per_batch": ms_pnp, "pnp_us_per_frame": ms_pnp / B * 1e3,
+                    "matches_per_frame": dd["m_bids"].numel() / B,
+                    "note": "opp_pnp_ransac: one CTA per frame, 1024 P3P hypotheses + 3 Gauss-Newton refinement "
+                            "rounds, consuming the match lists in place (no D2H before the pose)"}
+            if world == 1 and not args.no_cpu_baseline:
+                from oracle import pnp as opnp      # cpu_baseline leg: the reference's cv2 call, one frame
+                sel = dd["m_bids"] == 0
+                p2 = dd["mkpts_query_f"][sel].cpu().numpy()
+                p3 = dd["mkpts_3d_db"][sel].cpu().numpy()
+                t_c = time.perf_counter()
+                for _ in range(5):
+                    opnp.ransac_pnp(Kmat[0].cpu().numpy(), p2, p3, pnp_reprojection_error=5)
+                pose["cpu_cv2_ms_per_frame"] = (time.perf_counter() - t_c) / 5 * 1e3
+        except Exception as e:  # noqa: BLE001
+            pose = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
     # BASELINE configs[1] (one image per forward): latency view of the same path, wall clock incl.
     # host launch overhead and the per-forward match-count sync
     b1 = None
@@ -520,6 +553,7 @@ def main():
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
                 "tensor_pipe_pct_ncu": "sm__pipe_tensor_cycles_active per launch at this batch: profiles/r2_ncu_xfmr_b64.md"},
             "configs": {"c5": c5},
+            "pose_stage": pose,
             "latency_b1": b1,
             "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH),
                                "one_pass_dual_softmax": bool(model.coarse_colmax and model.coarse_lse_cols),

@@ -150,6 +150,13 @@ int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w,
                   int resid_shared, void* out16, float* out32, int batches, long long rows, int n,
                   int split, opp_stream_t stream);
 
+/* FullAttention.forward (linear_attention.py:64-95): out = softmax(Q K^T / sqrt(head_dim)) V per
+ * head; `attention: "full"` in the transformer config (no shipped configuration selects it).
+ * q fp16 [B][l][planes*heads*head_dim] = q_proj(x); kv fp16 [B][s][planes*2*heads*head_dim] =
+ * (k_proj(source) | v_proj(source)); out like q.  head_dim 32 (coarse) or 16 (fine). */
+int opp_full_attention(const void* q, const void* kv, void* out, int batch, int l, int s, int heads,
+                       int head_dim, int split, opp_stream_t stream);
+
 /* Source side state of linear attention (linear_attention.py:55-57):
  * kv16 fp16 [B][S][planes*2d] holds K' = elu(k)+1 in columns [0,d) and V in [d,2d) of each plane.
  * part fp32 [B][chunks][H][33][32], chunks = opp_kv_chunks(S): per-chunk sum_s K'^T V (rows 0..31)

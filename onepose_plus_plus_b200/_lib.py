@@ -33,6 +33,7 @@ SIGNATURES = {
     "opp_linear_act_f16_b": [P, I, I, P, I, P, P, I, L, I, I, I, I, P, P],
     "opp_linear_q_f16": [P, P, P, P, I, I, I, F, F, I, I, P, P],
     "opp_linear_ln": [P, I, P, I, P, I, P, P, F, P, I, P, P, I, L, I, I, P],
+    "opp_full_attention": [P, P, P, I, I, I, I, I, I, P],
     "opp_kv_partial": [P, P, I, I, I, I, P],
     "opp_kv_finalize": [P, P, P, P, I, I, I, F, I, P],
     "opp_sim_lse": [P, P, P, P, I, I, I, I, F, I, P],

@@ -98,9 +98,10 @@ static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long ro
   return make_map(map, ptr, 3, dims, str, box);
 }
 
+// rows_dev != nullptr: the DYN kernel (device-side row count, rows = *rows_dev * rows_mult)
 template <int A_MODE, class Epi, bool DYN = false>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const int* rows_dev = nullptr, int rows_mult = 1) {
   s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair);
   {
     static int dbg = -1;
@@ -117,7 +118,9 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
     if (cap > 1 && s.stages > cap) s.stages = cap;
   }
   const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair);
-  auto kern = gemm_kernel<A_MODE, Epi, DYN>;
+  const void* kern;
+  if constexpr (DYN) kern = (const void*)gemm_kernel_dyn<A_MODE, Epi>;
+  else kern = (const void*)gemm_kernel<A_MODE, Epi>;
   // function attributes are per device: set once per (template instantiation, device)
   static unsigned long long attr_done = 0;
   int dev = 0;
@@ -143,7 +146,8 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, kern, maps, s, ep);
+  void* kargs[5] = {(void*)&maps, (void*)&s, (void*)&ep, (void*)&rows_dev, (void*)&rows_mult};
+  cudaError_t le = cudaLaunchKernelExC(&cfg, kern, kargs);
   if (le != cudaSuccess) {
     set_last_error("cudaLaunchKernelEx failed: %s (grid %d cluster %d pair %d smem %d stages %d "
                    "block_n %d m_tiles %d n_tiles %d batches %d)",
@@ -303,10 +307,8 @@ int opp_linear_act_f16_dyn(const void* a0, int k0, const void* a1, int k1, const
   if (rc) return rc;
   OPP_REQUIRE(out && count && rows_per_count > 0, "bad dynamic-row arguments");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
-  s.rows_dev = count;
-  s.rows_mult = rows_per_count;
   EpiStoreF16::Params ep{(__half*)out, (long long)n * (split ? 2 : 1), split ? n : 0, act, act_cols, nullptr};
-  return launch<A_ROWS, EpiStoreF16, true>(maps, s, ep, (cudaStream_t)stream);
+  return launch<A_ROWS, EpiStoreF16, true>(maps, s, ep, (cudaStream_t)stream, count, rows_per_count);
 }
 
 int opp_linear_ln_dyn(const void* a0, int k0, const void* a1, int k1, const void* w, const float* gamma,
@@ -320,11 +322,9 @@ int opp_linear_ln_dyn(const void* a0, int k0, const void* a1, int k1, const void
   if (rc) return rc;
   OPP_REQUIRE(gamma && beta && count && rows_per_count > 0, "bad dynamic-row arguments");
   OPP_REQUIRE(out16 || out32, "no output requested");
-  s.rows_dev = count;
-  s.rows_mult = rows_per_count;
   EpiLN::Params ep{gamma, beta, eps, (const __half*)resid, 0, (__half*)out16,
                    (long long)n * (split ? 2 : 1), split ? n : 0, out32};
-  return launch<A_ROWS, EpiLN, true>(maps, s, ep, (cudaStream_t)stream);
+  return launch<A_ROWS, EpiLN, true>(maps, s, ep, (cudaStream_t)stream, count, rows_per_count);
 }
 
 int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out, int batches,
@@ -465,7 +465,8 @@ int opp_sim_lse_cols(const void* a, const void* b, float* part_m, float* part_s,
   int rc = setup_rows(maps, s, a, k, nullptr, 0, b, 1, batches, rows, cols, split, 1);
   if (rc) return rc;
   OPP_REQUIRE(part_m && part_s && col_m && col_s, "null pointer");
-  EpiLseCol::Params ep{part_m, part_s, scale, col_m, col_s, (rows + 31) / 32, col_mask};
+  EpiLseColParams ep{part_m, part_s, scale, col_m, col_s, (rows + 31) / 32, col_mask};
+  if (col_mask) return launch<A_ROWS, EpiLseColMasked>(maps, s, ep, (cudaStream_t)stream);
   return launch<A_ROWS, EpiLseCol>(maps, s, ep, (cudaStream_t)stream);
 }
 

@@ -28,6 +28,8 @@
 // (paths relative to the reference repo zju3dv/OnePose_Plus_Plus).
 #pragma once
 
+#include <type_traits>
+
 #include "opp_common.cuh"
 
 #ifndef OPP_CONV_GROUPS
@@ -98,10 +100,6 @@ struct GemmShape {
   int k_chunks_a0;  // chunks read through maps.a[0]; the rest through maps.a[1]
   int a0_lo, a1_lo; // element offsets of the lo planes of the two A arrays (= their K)
   int a0_shared;    // the first A array is [1][rows][..]: one object shared by every batch element
-  // device-side row count (DYN kernels): rows = *rows_dev * rows_mult, read when the kernel starts;
-  // the host-side `rows` / `m_tiles` then only describe the CAPACITY the tensor maps were built for
-  const int* rows_dev;
-  int rows_mult;
   // A_CONV
   int conv_cchunks; // K chunks per filter tap
   int conv_c;       // padded input channels (multiple of 16); also the lo-plane offset
@@ -133,9 +131,17 @@ struct EpiCtx {
   // only grow (row index in the output) and validity, computed once per tile
   long long sgrow[4];
   unsigned svalid;
+  int next_b, next_m_tile;   // the (batch, M tile) this CTA processes next, or next_b = -1
+  int it;                    // how many tiles this CTA has processed before this one
 };
 
 __device__ __forceinline__ void epi_sync(const EpiCtx& c) { named_bar_sync(1 + c.group, 128); }
+
+// epilogues that look one tile ahead declare `static constexpr bool kNeedsNext`
+template <class E, class = void>
+struct EpiNeedsNext : std::false_type {};
+template <class E>
+struct EpiNeedsNext<E, std::void_t<decltype(E::kNeedsNext)>> : std::true_type {};
 
 // (global row, validity) of row `rr` (0..31) of this warp's quarter of the tile
 __device__ __forceinline__ bool epi_row_info(const GemmShape& s, const EpiCtx& c, int rr,
@@ -402,12 +408,13 @@ struct EpiLN {
   // instruction = 32 L1 wavefronts at ~2 clk each, which made this epilogue wavefront-bound
   // (28-34 k clk per tile against 6-12 k clk of MMA work).
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    epi_sync(c);
-    for (int i = c.etid; i < c.ncols; i += 128) {
-      sts32f(c.smem_s + 4 * i, p.gamma[i]);
-      sts32f(c.smem_s + 4 * (256 + i), p.beta[i]);
+    if (c.it == 0) {   // gamma / beta are the same for every tile (single N tile): staged once per CTA
+      for (int i = c.etid; i < c.ncols; i += 128) {
+        sts32f(c.smem_s + 4 * i, p.gamma[i]);
+        sts32f(c.smem_s + 4 * (256 + i), p.beta[i]);
+      }
+      epi_sync(c);
     }
-    epi_sync(c);
     float x0 = 0.f, s1 = 0.f, s2 = 0.f;
     int cnt = 0;
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
@@ -528,8 +535,7 @@ struct EpiConvParams {
   int up_h, up_w;
   float up_sy, up_sx;   // (in - 1) / (out - 1)
 };
-template <bool kUp>
-struct EpiConvT {
+struct EpiConv {
   static constexpr int kGroups = OPP_CONV_GROUPS;
   using Params = EpiConvParams;
   // Called before the accumulator wait: pull this row of the residual towards L2 while the MMAs
@@ -570,43 +576,6 @@ struct EpiConvT {
     };
     if (has_res && c.col_first < c.ncols) issue(c.col_first);
 #endif
-    // Fused bilinear x2 upsample-add (torch semantics: src = dst * (in-1)/(out-1), i0 = floor(src),
-    // i1 = min(i0+1, in-1)).  A warp owns 2 output rows x 16 columns of the 8x16 tile; their
-    // neighbours lie in a 3 x 10 window of the coarse map (15 * 0.5 < 8 columns, 1 * 0.5 < 1 row),
-    // so per 32-channel chunk and plane the warp fetches those <= 30 pixels' 64-byte segments
-    // coalesced into its transpose buffer (slot = wy * 10 + wx) and every lane then reads its own
-    // four neighbours from shared memory.
-    const int lane_ = threadIdx.x & 31;
-    float uw00 = 0.f, uw01 = 0.f, uw10 = 0.f, uw11 = 0.f;
-    uint32_t us00 = 0, us01 = 0, us10 = 0, us11 = 0;   // shared addresses of the 4 neighbour slots
-    long long upix[4] = {0, 0, 0, 0};                  // source pixel (element offset) staged by this lane
-    if constexpr (kUp) {
-      const int rit = c.q * 32 + lane_;
-      const int ty = c.m_tile / s.tiles_x;
-      const int ly = rit / s.tile_w;
-      const int oy = min(ty * s.tile_h + ly, s.out_h - 1);
-      const int ox = min((c.m_tile - ty * s.tiles_x) * s.tile_w + (rit - ly * s.tile_w), s.out_w - 1);
-      const float fy = p.up_sy * (float)oy, fx = p.up_sx * (float)ox;
-      const int y0 = (int)fy, x0 = (int)fx;
-      const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
-      const float wy = fy - (float)y0, wx = fx - (float)x0;
-      uw00 = (1.f - wy) * (1.f - wx);
-      uw01 = (1.f - wy) * wx;
-      uw10 = wy * (1.f - wx);
-      uw11 = wy * wx;
-      const int ymin = __shfl_sync(0xffffffffu, y0, 0), xmin = __shfl_sync(0xffffffffu, x0, 0);
-      us00 = c.wstage_s + ((y0 - ymin) * 10 + (x0 - xmin)) * kStageRowH;
-      us01 = c.wstage_s + ((y0 - ymin) * 10 + (x1 - xmin)) * kStageRowH;
-      us10 = c.wstage_s + ((y1 - ymin) * 10 + (x0 - xmin)) * kStageRowH;
-      us11 = c.wstage_s + ((y1 - ymin) * 10 + (x1 - xmin)) * kStageRowH;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int slot = min((lane_ >> 2) + 8 * i, 29);
-        const int sy_ = slot / 10, sx_ = slot - sy_ * 10;
-        upix[i] = (((long long)c.b * p.up_h + min(ymin + sy_, p.up_h - 1)) * p.up_w +
-                   min(xmin + sx_, p.up_w - 1)) * p.ld;
-      }
-    }
     tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
       const int g0 = c.n0 + col;
       const int nvalid = c.ncols - col;   // >= 8, multiple of 8; columns past it are padding
@@ -617,40 +586,6 @@ struct EpiConvT {
         v[4 * g + 1] += __uint_as_float(bq.y);
         v[4 * g + 2] += __uint_as_float(bq.z);
         v[4 * g + 3] += __uint_as_float(bq.w);
-      }
-      if constexpr (kUp) {
-        const int seg = lane_ & 3;
-        const bool seg_ok = seg * 8 < nvalid;
-#pragma unroll
-        for (int plane = 0; plane < 2; ++plane) {
-          if (plane == 1 && p.out_lo == 0) break;
-          uint4 u[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            u[i] = seg_ok ? *reinterpret_cast<const uint4*>(p.up + upix[i] + plane * p.out_lo + g0 + seg * 8)
-                          : make_uint4(0, 0, 0, 0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            sts128(c.wstage_s + ((lane_ >> 2) + 8 * i) * kStageRowH + seg * 16, u[i]);
-          __syncwarp();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 q00 = lds128(us00 + g * 16), q01 = lds128(us01 + g * 16);
-            const uint4 q10 = lds128(us10 + g * 16), q11 = lds128(us11 + g * 16);
-            const __half2* h00 = reinterpret_cast<const __half2*>(&q00);
-            const __half2* h01 = reinterpret_cast<const __half2*>(&q01);
-            const __half2* h10 = reinterpret_cast<const __half2*>(&q10);
-            const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 a = __half22float2(h00[j]), b = __half22float2(h01[j]);
-              const float2 cc = __half22float2(h10[j]), d = __half22float2(h11[j]);
-              v[8 * g + 2 * j] += (uw00 * a.x + uw01 * b.x) + (uw10 * cc.x + uw11 * d.x);
-              v[8 * g + 2 * j + 1] += (uw00 * a.y + uw01 * b.y) + (uw10 * cc.y + uw11 * d.y);
-            }
-          }
-          __syncwarp();
-        }
       }
 #if OPP_CONV_RESID_STAGED
       if (has_res) {
@@ -709,8 +644,152 @@ struct EpiConvT {
   }
 };
 
-using EpiConv = EpiConvT<false>;
-using EpiConvUp = EpiConvT<true>;   // + fused bilinear x2 upsample-add of the coarser FPN level
+// Lateral 1x1 convolution of the FPN top-down path with the bilinear x2 upsample-add fused in
+// (resnet.py:149-157: layerN_outconv(x) + F.interpolate(coarser, scale_factor=2, mode="bilinear",
+// align_corners=True)); torch semantics: src = dst * (in-1)/(out-1), i0 = floor(src),
+// i1 = min(i0+1, in-1).  No residual / activation / tokens on these layers.
+//
+// A warp owns 2 output rows x 16 columns of the 8x16 tile; their neighbours lie in a 3 x 10 window
+// of the coarse map (15 * 0.5 < 8 columns, 1 * 0.5 < 1 row).  Per 32-channel chunk and plane the
+// warp fetches those <= 30 pixels' 64-byte segments coalesced into its transpose buffer
+// (slot = wy * 10 + wx) and every lane reads its own four neighbours from shared memory.
+// The first version did these loads on demand, one dependent DRAM round trip per chunk and plane
+// (the coarse map does not fit in L2): 28 k clk per tile, 8 % tensor pipe (profiles/r2_ncu_b64_s2.md).
+// Now (i) the NEXT tile's window is pulled into L2 while this tile is processed, (ii) both planes
+// of a chunk are loaded together and (iii) the loads of chunk i+1 are issued before the plane-1
+// math and the stores of chunk i.
+struct EpiConvUp {
+  static constexpr int kGroups = OPP_CONV_GROUPS;
+  static constexpr bool kNeedsNext = true;   // EpiCtx::next_b / next_m_tile are filled in
+  using Params = EpiConvParams;
+
+  struct Geo {
+    int ymin, xmin;
+  };
+  // (ymin, xmin) of the 3 x 10 source window of warp quarter q of tile (m_tile): floor of the source
+  // coordinate of the warp's first output pixel (its minimum in both axes)
+  __device__ static Geo window(const Params& p, const GemmShape& s, int m_tile, int q) {
+    const int ty = m_tile / s.tiles_x;
+    const int oy = min(ty * s.tile_h + (q * 32) / s.tile_w, s.out_h - 1);
+    const int ox = min((m_tile - ty * s.tiles_x) * s.tile_w, s.out_w - 1);
+    return Geo{(int)(p.up_sy * (float)oy), (int)(p.up_sx * (float)ox)};
+  }
+  // pixel index (not yet multiplied by the pixel stride) of window slot `slot` (0..29)
+  __device__ static long long slot_pixel(const Params& p, int b, const Geo& g, int slot) {
+    const int sy_ = slot / 10, sx_ = slot - sy_ * 10;
+    return ((long long)b * p.up_h + min(g.ymin + sy_, p.up_h - 1)) * p.up_w + min(g.xmin + sx_, p.up_w - 1);
+  }
+  __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    // L2 prefetch of the NEXT tile's window for this warp: 30 pixels x (planes * C * 2 B), lane = slot
+    if (c.next_b < 0) return;
+    const int lane = threadIdx.x & 31;
+    if (lane >= 30) return;
+    const Geo g = window(p, s, c.next_m_tile, c.q);
+    const char* px = reinterpret_cast<const char*>(p.up + slot_pixel(p, c.next_b, g, lane) * p.ld);
+    const int bytes = (p.out_lo ? 2 : 1) * s.n_total * 2;
+    // the two epilogue groups split the lines of a pixel between them
+    for (int o = c.group * 128; o < bytes; o += 128 * kGroups) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
+  }
+  __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    epi_sync(c);
+    for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
+    epi_sync(c);
+    const int lane = threadIdx.x & 31;
+    const int seg = lane & 3;
+    // this lane's output pixel and its interpolation weights / neighbour slots
+    const Geo g = window(p, s, c.m_tile, c.q);
+    float w00, w01, w10, w11;
+    uint32_t a00, a01, a10, a11;
+    {
+      const int rit = c.q * 32 + lane;
+      const int ty = c.m_tile / s.tiles_x;
+      const int ly = rit / s.tile_w;
+      const int oy = min(ty * s.tile_h + ly, s.out_h - 1);
+      const int ox = min((c.m_tile - ty * s.tiles_x) * s.tile_w + (rit - ly * s.tile_w), s.out_w - 1);
+      const float fy = p.up_sy * (float)oy, fx = p.up_sx * (float)ox;
+      const int y0 = (int)fy, x0 = (int)fx;
+      const int y1 = y0 + (y0 < p.up_h - 1 ? 1 : 0), x1 = x0 + (x0 < p.up_w - 1 ? 1 : 0);
+      const float wy = fy - (float)y0, wx = fx - (float)x0;
+      w00 = (1.f - wy) * (1.f - wx);
+      w01 = (1.f - wy) * wx;
+      w10 = wy * (1.f - wx);
+      w11 = wy * wx;
+      a00 = c.wstage_s + ((y0 - g.ymin) * 10 + (x0 - g.xmin)) * kStageRowH;
+      a01 = c.wstage_s + ((y0 - g.ymin) * 10 + (x1 - g.xmin)) * kStageRowH;
+      a10 = c.wstage_s + ((y1 - g.ymin) * 10 + (x0 - g.xmin)) * kStageRowH;
+      a11 = c.wstage_s + ((y1 - g.ymin) * 10 + (x1 - g.xmin)) * kStageRowH;
+    }
+    // the four window pixels this lane stages (slot = lane / 4 + 8 i, 16-byte segment lane % 4)
+    int spix[4];   // 32-bit pixel indices (64-bit pointers here spilled and serialised the loads on LDL)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) spix[i] = (int)slot_pixel(p, c.b, g, min((lane >> 2) + 8 * i, 29));
+    const __half* upb = p.up + seg * 8 + c.n0;
+    const bool two = p.out_lo != 0;
+    uint4 nb[8];   // [plane][slot]: the window segments of the chunk about to be processed
+    auto issue = [&](int col) {
+      const bool ok = seg * 8 < c.ncols - col;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half* px = upb + (long long)spix[i] * p.ld + col;
+        nb[i] = ok ? *reinterpret_cast<const uint4*>(px) : make_uint4(0, 0, 0, 0);
+        nb[4 + i] = (ok && two) ? *reinterpret_cast<const uint4*>(px + p.out_lo) : make_uint4(0, 0, 0, 0);
+      }
+    };
+    auto stage = [&](int plane) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        sts128(c.wstage_s + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16, nb[plane * 4 + i]);
+      __syncwarp();
+    };
+    auto blend = [&](float* v) {
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint4 q00 = lds128(a00 + q4 * 16), q01 = lds128(a01 + q4 * 16);
+        const uint4 q10 = lds128(a10 + q4 * 16), q11 = lds128(a11 + q4 * 16);
+        const __half2* h00 = reinterpret_cast<const __half2*>(&q00);
+        const __half2* h01 = reinterpret_cast<const __half2*>(&q01);
+        const __half2* h10 = reinterpret_cast<const __half2*>(&q10);
+        const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fa = __half22float2(h00[j]), fb = __half22float2(h01[j]);
+          const float2 fc = __half22float2(h10[j]), fd = __half22float2(h11[j]);
+          v[8 * q4 + 2 * j] += (w00 * fa.x + w01 * fb.x) + (w10 * fc.x + w11 * fd.x);
+          v[8 * q4 + 2 * j + 1] += (w00 * fa.y + w01 * fb.y) + (w10 * fc.y + w11 * fd.y);
+        }
+      }
+      __syncwarp();
+    };
+    if (c.col_first < c.ncols) issue(c.col_first);
+    for (int col = c.col_first; col < c.ncols; col += c.col_step) {
+      float v[32];
+      tmem_ld32(c.tmem + col, v);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const uint4 bq = lds128(c.smem_s + 4 * ((col + 4 * q4) & 255));
+        v[4 * q4 + 0] += __uint_as_float(bq.x);
+        v[4 * q4 + 1] += __uint_as_float(bq.y);
+        v[4 * q4 + 2] += __uint_as_float(bq.z);
+        v[4 * q4 + 3] += __uint_as_float(bq.w);
+      }
+      stage(0);
+      blend(v);
+      if (two) stage(1);
+      // nb is free again: fetch the next chunk's window while this chunk is blended and stored
+      const int ncol = col + c.col_step;
+      if (ncol < c.ncols) issue(ncol);
+      if (two) blend(v);
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+      }
+      staged_store_h32(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, c.ncols - col);
+    }
+  }
+};
 
 // Dual-softmax statistics (coarse_matching.py:102-115): per row, over this tile's columns,
 // (max, sum exp) of sim = acc*scale.  Partials [grow][n_tile] are merged by a finalize kernel.
@@ -813,25 +892,27 @@ struct EpiConf {
 // its 32 rows with two butterflies (max, then sum of exp(x - column max of these 32 rows)) and
 // writes the pair to  col_m / col_s [batch][row group][n_total]  (row group = 32 rows; coalesced:
 // lane j owns column j).  opp_lse_col_finalize merges the row groups.
-struct EpiLseCol {
+struct EpiLseColParams {
+  float* part_m;
+  float* part_s;
+  float scale;
+  float* col_m;   // [batches][row_groups][n_total]
+  float* col_s;
+  int row_groups; // ceil(rows / 32)
+  // query_image_mask: columns with col_mask[b][col] == 0 get sim + (-1e9) (coarse_matching.py:108-114), or null
+  const unsigned char* col_mask;
+};
+template <bool kMask>
+struct EpiLseColT {
   static constexpr int kGroups = OPP_ROW_GROUPS;   // row partial slot = kGroups*n_tile + group
-  struct Params {
-    float* part_m;
-    float* part_s;
-    float scale;
-    float* col_m;   // [batches][row_groups][n_total]
-    float* col_s;
-    int row_groups; // ceil(rows / 32)
-    // query_image_mask: columns with col_mask[b][col] == 0 get sim + (-1e9) (coarse_matching.py:108-114), or null
-    const unsigned char* col_mask;
-  };
+  using Params = EpiLseColParams;
   __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
     const int lane = threadIdx.x & 31;
     const int rg = c.m_tile * 4 + c.q;   // 32-row group of this warp inside the batch
     const bool rg_ok = rg < p.row_groups;
     const long long cbase = ((long long)c.b * p.row_groups + rg) * s.n_total + c.n0;
-    if (p.col_mask) {   // additive column bias (0 / -1e9) of this tile, shared by the epilogue group
+    if constexpr (kMask) {   // additive column bias (0 / -1e9) of this tile, shared by the epilogue group
       epi_sync(c);
       for (int i = c.etid; i < c.ncols; i += 128)
         sts32f(c.smem_s + 4 * i, p.col_mask[(long long)c.b * s.n_total + c.n0 + i] ? 0.f : -1e9f);
@@ -842,7 +923,8 @@ struct EpiLseCol {
       float t[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float cb_ = p.col_mask ? lds32f(c.smem_s + 4 * ((col + j) & 255)) : 0.f;
+        float cb_ = 0.f;
+        if constexpr (kMask) cb_ = lds32f(c.smem_s + 4 * ((col + j) & 255));
         v[j] = (c.valid && col + j < c.ncols) ? v[j] * p.scale + cb_ : -INFINITY;
         m = fmaxf(m, v[j]);
         t[j] = v[j];
@@ -883,7 +965,8 @@ struct EpiLseCol {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (col + j < c.ncols) {
-          const float cb_ = p.col_mask ? lds32f(c.smem_s + 4 * ((col + j) & 255)) : 0.f;
+          float cb_ = 0.f;
+          if constexpr (kMask) cb_ = lds32f(c.smem_s + 4 * ((col + j) & 255));
           sum += fast_exp((v[j] * p.scale + cb_) - m);
         }
     });
@@ -893,6 +976,9 @@ struct EpiLseCol {
     }
   }
 };
+
+using EpiLseCol = EpiLseColT<false>;
+using EpiLseColMasked = EpiLseColT<true>;   // + query_image_mask (-1e9 on the padded query cells)
 
 // conf pass with the column maxima folded in (replaces the second conf pass): rows are 3D points,
 // conf is stored as in EpiConf, and for every 32x32 chunk the warp reduces each COLUMN over its 32
@@ -970,21 +1056,9 @@ struct EpiConfCol {
 // =============================================================================================
 // The kernel
 // =============================================================================================
-template <int A_MODE, class Epi, bool DYN = false>
-__global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
-gemm_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ GemmShape s_in,
-            const typename Epi::Params ep) {
-  // DYN: the number of valid rows lives in device memory (the match count of the coarse stage), so
-  // a whole forward can be enqueued — or captured in a CUDA graph — without a host round trip
-  GemmShape s_dyn;
-  if constexpr (DYN) {
-    s_dyn = s_in;
-    const int r = *s_in.rows_dev * s_in.rows_mult;
-    s_dyn.rows = r < s_in.rows ? r : s_in.rows;
-    s_dyn.m_tiles = (s_dyn.rows + kBlockM - 1) / kBlockM;
-    s_dyn.msup = (s_dyn.m_tiles + s_in.cluster - 1) / s_in.cluster;
-  }
-  const GemmShape& s = DYN ? s_dyn : s_in;
+template <int A_MODE, class Epi>
+__device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShape& s,
+                                          const typename Epi::Params& ep) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -1283,6 +1357,16 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Gem
       c.n0 = c.n_tile * s.block_n;
       const int rem = s.n_total - c.n0;
       c.ncols = rem < s.block_n ? rem : s.block_n;
+      if constexpr (EpiNeedsNext<Epi>::value) {
+        const int tn = t + n_clusters;
+        c.next_b = -1;
+        c.next_m_tile = 0;
+        if (tn < total_tiles) {
+          c.next_b = tn / tiles_per_batch;
+          c.next_m_tile = ((tn - c.next_b * tiles_per_batch) / s.n_tiles) * csize + crank;
+        }
+      }
+      c.it = it;
       c.valid = epi_row_info(s, c, lane, c.grow, c.row);
       c.svalid = 0;
 #pragma unroll
@@ -1316,6 +1400,27 @@ gemm_kernel(const __grid_constant__ TensorMaps maps, const __grid_constant__ Gem
     tc_fence_after();
     if (pair) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+template <int A_MODE, class Epi>
+__global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
+gemm_kernel(const __grid_constant__ TensorMaps maps, const GemmShape s, const typename Epi::Params ep) {
+  gemm_body<A_MODE, Epi>(maps, s, ep);
+}
+
+// Same kernel with the number of valid rows in device memory (the match count of the coarse
+// stage): rows = *rows_dev * rows_mult, so a whole forward can be enqueued — or captured in a CUDA
+// graph — without a host round trip.  The host-side rows / m_tiles describe the CAPACITY.
+template <int A_MODE, class Epi>
+__global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
+gemm_kernel_dyn(const __grid_constant__ TensorMaps maps, const GemmShape s_in,
+                const typename Epi::Params ep, const int* rows_dev, int rows_mult) {
+  GemmShape s = s_in;
+  const int r = *rows_dev * rows_mult;
+  s.rows = r < s_in.rows ? r : s_in.rows;
+  s.m_tiles = (s.rows + kBlockM - 1) / kBlockM;
+  s.msup = (s.m_tiles + s_in.cluster - 1) / s_in.cluster;
+  gemm_body<A_MODE, Epi>(maps, s, ep);
 }
 
 // dynamic shared memory a launch needs (ring + epilogue scratch + barriers + alignment slack)

@@ -723,61 +723,170 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
                                                              int lo_off_out,
                                                              const int* __restrict__ count_dev) {
   if (count_dev && (int)blockIdx.x >= *count_dev) return;
-  __shared__ float q_s[26][128];
-  __shared__ float k_s[26][128];
-  __shared__ float v_s[26][128];
+  // ncu (batch 64, 24 k matches): the first version was bound by shared-memory instructions — 32-bit
+  // loads of values every lane of a head shares, and the per-head state re-read from shared memory
+  // although each thread owns its column.  Now rows are fetched with 16-byte global loads, shared
+  // operands are read as float4 broadcasts and the window state column stays in registers.
+  __shared__ __align__(16) float q_s[26][128];
+  __shared__ __align__(16) float k_s[26][128];
+  __shared__ __align__(16) float v_s[26][128];
+  __shared__ __align__(16) float ks2[128];
   const int m = blockIdx.x, c = threadIdx.x;
   const int ldi = lo_off_in ? 768 : 384;
   const __half* src = qkv + (long long)m * 26 * ldi;
-  for (int t = 0; t < 26; ++t) {
-    q_s[t][c] = load_split1(src + t * ldi, c, lo_off_in);
-    k_s[t][c] = load_split1(src + t * ldi, 128 + c, lo_off_in);
-    v_s[t][c] = load_split1(src + t * ldi, 256 + c, lo_off_in);
+  for (int i = c; i < 26 * 48; i += 128) {
+    const int t = i / 48, sg = i - t * 48;
+    float f[8];
+    load_split8(src + (long long)t * ldi, sg * 8, f, lo_off_in);
+    const int col = sg * 8;   // 0..383: q | k | v, 128 each
+    float* dstrow = col < 128 ? &q_s[t][col] : (col < 256 ? &k_s[t][col - 128] : &v_s[t][col - 256]);
+    reinterpret_cast<float4*>(dstrow)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dstrow)[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
   __syncthreads();
-  const int h = c >> 4, v = c & 15;
-  // window state: thread (h, v) owns column v of head h
+  const int h = c >> 4;
+  // window state: thread (h, v) owns column v of head h:  col[dd] = sum_t K'[t, h, dd] V[t, h, v]
   float col[16];
 #pragma unroll
   for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
   float ksum_c = 0.f;  // thread c also owns ks2[c]
   for (int t = 1; t < 26; ++t) {
     const float vv = v_s[t][c];
+    const float4* kr = reinterpret_cast<const float4*>(&k_s[t][h * 16]);
 #pragma unroll
-    for (int dd = 0; dd < 16; ++dd) col[dd] = fmaf(k_s[t][h * 16 + dd], vv, col[dd]);
+    for (int g = 0; g < 4; ++g) {
+      const float4 k4 = kr[g];
+      col[4 * g + 0] = fmaf(k4.x, vv, col[4 * g + 0]);
+      col[4 * g + 1] = fmaf(k4.y, vv, col[4 * g + 1]);
+      col[4 * g + 2] = fmaf(k4.z, vv, col[4 * g + 2]);
+      col[4 * g + 3] = fmaf(k4.w, vv, col[4 * g + 3]);
+    }
     ksum_c += k_s[t][c];
   }
-  // rows 1..25 of k_s / v_s are dead once every thread has its partial state: reuse them for the
-  // window state kv2[h][dd][v] and ks2[c]
-  __syncthreads();
-  float (*kv2)[16][16] = reinterpret_cast<float (*)[16][16]>(&v_s[1][0]);
-  float* ks2 = &k_s[1][0];
-#pragma unroll
-  for (int dd = 0; dd < 16; ++dd) kv2[h][dd][v] = col[dd];
   ks2[c] = ksum_c;
   __syncthreads();
-  const int ldo = lo_off_out ? 256 : 128;
-  __half* dst = msg + (long long)m * 26 * ldo;
+  float ksw[16], k0[16];   // window Ksum and the 3D token's K' of this head
+  {
+    const float4* a = reinterpret_cast<const float4*>(&ks2[h * 16]);
+    const float4* b = reinterpret_cast<const float4*>(&k_s[0][h * 16]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 x = a[g], y = b[g];
+      ksw[4 * g] = x.x; ksw[4 * g + 1] = x.y; ksw[4 * g + 2] = x.z; ksw[4 * g + 3] = x.w;
+      k0[4 * g] = y.x; k0[4 * g + 1] = y.y; k0[4 * g + 2] = y.z; k0[4 * g + 3] = y.w;
+    }
+  }
+  const float v0 = v_s[0][c];
+  float o[26];
+#pragma unroll
   for (int t = 0; t < 26; ++t) {
     // which source state does token t read?  self: own sequence; cross: the other one
     const bool use_window = cross ? (t == 0) : (t > 0);
+    const float4* qr = reinterpret_cast<const float4*>(&q_s[t][h * 16]);
     float num = 0.f, den = 0.f;
-    if (use_window) {
 #pragma unroll
-      for (int dd = 0; dd < 16; ++dd) {
-        const float q = q_s[t][h * 16 + dd];
-        num = fmaf(q, kv2[h][dd][v], num);
-        den = fmaf(q, ks2[h * 16 + dd], den);
+    for (int g = 0; g < 4; ++g) {
+      const float4 q4 = qr[g];
+      const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (use_window) {
+          num = fmaf(qv[j], col[4 * g + j], num);
+          den = fmaf(qv[j], ksw[4 * g + j], den);
+        } else {   // source is the single 3D token (row 0): KV = k0^T v0, Ksum = k0
+          den = fmaf(qv[j], k0[4 * g + j], den);
+        }
       }
-    } else {
-      // source is the single 3D token (row 0): KV = k0^T v0, Ksum = k0
-      float qk = 0.f;
-#pragma unroll
-      for (int dd = 0; dd < 16; ++dd) qk = fmaf(q_s[t][h * 16 + dd], k_s[0][h * 16 + dd], qk);
-      num = qk * v_s[0][c];
-      den = qk;
     }
-    store_split1(dst + t * ldo, c, num / (den + eps), lo_off_out);
+    if (!use_window) num = den * v0;
+    o[t] = num / (den + eps);
+  }
+  __syncthreads();   // every read of q_s is done: reuse it as the output tile
+#pragma unroll
+  for (int t = 0; t < 26; ++t) q_s[t][c] = o[t];
+  __syncthreads();
+  const int ldo = lo_off_out ? 256 : 128;
+  __half* dst = msg + (long long)m * 26 * ldo;
+  for (int i = c; i < 26 * 16; i += 128) {
+    const int t = i >> 4, sg = i & 15;
+    float f[8];
+    const float4 a = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[0];
+    const float4 b = reinterpret_cast<const float4*>(&q_s[t][sg * 8])[1];
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    store_split8(dst + (long long)t * ldo, sg * 8, f, lo_off_out);
+  }
+}
+
+// =============================================================================================
+// FullAttention.forward   (loftr_module/linear_attention.py:64-95): softmax(Q K^T / sqrt(D)) V per
+// head.  Selected by `attention: "full"` in the transformer config — never by a shipped
+// configuration (cold path), so this is a plain fp32 SIMT kernel: one thread per query row with an
+// online softmax over 64-key tiles staged in shared memory; no S x L matrix is materialised.
+//   q   fp16 [B][L][planes*(H*D)]           (q_proj output)
+//   kv  fp16 [B][S][planes*(2*H*D)]         (k_proj | v_proj outputs)
+//   out fp16 [B][L][planes*(H*D)]
+// =============================================================================================
+constexpr int kFaKeys = 64;
+
+template <int D>
+__global__ void __launch_bounds__(128) full_attention_kernel(const __half* __restrict__ q,
+                                                             const __half* __restrict__ kv,
+                                                             __half* __restrict__ out, int L, int S,
+                                                             int heads, int lo_q, int lo_kv) {
+  __shared__ __align__(16) float k_s[kFaKeys][D];
+  __shared__ __align__(16) float v_s[kFaKeys][D];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  const int dm = heads * D;
+  const int ldq = lo_q ? 2 * dm : dm, ldk = lo_kv ? 4 * dm : 2 * dm;
+  const float temp = rsqrtf((float)D);
+  float qr[D], acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    acc[d] = 0.f;
+    qr[d] = 0.f;
+  }
+  if (row < L) {
+    const __half* qp = q + ((long long)b * L + row) * ldq + h * D;
+#pragma unroll
+    for (int d = 0; d < D; d += 8) load_split8(qp, d, qr + d, lo_q);
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int s0 = 0; s0 < S; s0 += kFaKeys) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFaKeys * (D / 8) * 2; i += 128) {
+      const int which = i / (kFaKeys * (D / 8));          // 0 = K, 1 = V
+      const int r = (i / (D / 8)) % kFaKeys, g = i % (D / 8);
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (s0 + r < S)
+        load_split8(kv + ((long long)b * S + s0 + r) * ldk + which * dm + h * D, g * 8, f, lo_kv);
+      float* dst = which ? &v_s[r][g * 8] : &k_s[r][g * 8];
+      reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    const int cnt = min(kFaKeys, S - s0);
+    for (int j = 0; j < cnt; ++j) {
+      float sc = 0.f;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sc = fmaf(qr[d], k_s[j][d], sc);
+      sc *= temp;
+      const float mn = fmaxf(m, sc);
+      const float corr = expf(m - mn), pj = expf(sc - mn);
+      l = l * corr + pj;
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] = fmaf(pj, v_s[j][d], acc[d] * corr);
+      m = mn;
+    }
+  }
+  if (row < L) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] *= inv;
+    __half* op = out + ((long long)b * L + row) * ldq + h * D;
+#pragma unroll
+    for (int d = 0; d < D; d += 8) store_split8(op, d, acc + d, lo_q);
   }
 }
 
@@ -1055,6 +1164,25 @@ int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, 
   OPP_REQUIRE(qkv && msg, "null pointer");
   fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg, cross, eps,
                                                              split ? 384 : 0, split ? 128 : 0, count_dev);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_full_attention(const void* q, const void* kv, void* out, int batch, int l, int s, int heads,
+                       int head_dim, int split, opp_stream_t stream) {
+  OPP_REQUIRE(q && kv && out, "null pointer");
+  OPP_REQUIRE(batch > 0 && l > 0 && s > 0 && heads > 0, "empty attention");
+  OPP_REQUIRE(head_dim == 32 || head_dim == 16, "full attention is built for head_dim 32 / 16, got %d", head_dim);
+  dim3 grid((l + 127) / 128, heads, batch);
+  const int dm = heads * head_dim;
+  if (head_dim == 32)
+    full_attention_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+                                                                     (__half*)out, l, s, heads, split ? dm : 0,
+                                                                     split ? 2 * dm : 0);
+  else
+    full_attention_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+                                                                     (__half*)out, l, s, heads, split ? dm : 0,
+                                                                     split ? 2 * dm : 0);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -124,8 +124,9 @@ class LoFTREncoderLayer(nn.Module):
 
     def __init__(self, d_model, nhead, attention="linear", norm_method="layernorm", rezero=None):
         super().__init__()
-        if attention != "linear":
-            raise NotImplementedError("only attention='linear' is built (the shipped configs)")
+        if attention not in ("linear", "full"):
+            raise NotImplementedError(f"attention {attention!r}: 'linear' and 'full' are built")
+        self.attention_type = attention
         if norm_method != "layernorm":
             raise NotImplementedError("only norm_method='layernorm' is built")
         if rezero is not None:
@@ -250,6 +251,9 @@ class OnePosePlus_model(nn.Module):
             raise NotImplementedError("coarse kernels are built for d_model 256, 8 heads")
         if config["loftr_fine"]["d_model"] != 128 or config["loftr_fine"]["nhead"] != 8:
             raise NotImplementedError("fine kernels are built for d_model 128, 8 heads")
+        if config["loftr_fine"]["attention"] != "linear":
+            raise NotImplementedError("the fine-level kernels implement attention='linear' (every shipped "
+                                      "config); 'full' is built for the coarse transformer only")
         if config["loftr_fine"]["window_size"] != 5:
             raise NotImplementedError("fine kernels are built for window_size 5")
         b = config["loftr_backbone"]["resnetfpn"]
@@ -288,9 +292,10 @@ class OnePosePlus_model(nn.Module):
         # butterflies in the epilogue) instead of two more sim GEMM passes
         self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "1") == "1"
         self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "1") == "1"
-        # K'/V rows of the coarse attention state stored as ONE fp16 plane (their consumer sums over
-        # thousands of tokens; oracle experiment: conf changes by 1e-4)
-        self.kv_single_plane = os.environ.get("OPP_B200_KV1", "0") == "1"
+        # K'/V rows of the coarse attention state stored as ONE fp16 plane: their only consumer sums
+        # them over thousands of tokens, so the 2^-12 rounding averages out (oracle experiment: conf
+        # changes by 1e-4; the whole GPU parity suite passes with it: profiles/r2_kv1_adoption.md)
+        self.kv_single_plane = os.environ.get("OPP_B200_KV1", "1") == "1"
 
     @property
     def split(self):
@@ -513,16 +518,30 @@ class OnePosePlus_model(nn.Module):
         f16 = torch.float16
         split = self.split
         pl = 2 if split else 1
-        if state is None:
-            mt, ksum = self._src_state(L, tag, src, B, ls, src_mask)
-            mt_batched = True
-        else:
-            mt, ksum = state
-            mt_batched = False
-        qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
-        ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split, x_shared=x_shared, row_mask=x_mask)
         msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
-        ops.linear_ln(qz, None, mt, mt_batched, *L["n1"], B, lx, split, out16=msg)
+        if self.config["loftr_coarse"]["attention"] == "full":
+            # FullAttention (linear_attention.py:64-95): q/k/v projections, softmax(QK^T/sqrt(D))V per
+            # head, merge + LayerNorm (transformer.py:77-86).  Cold path (no shipped config).
+            if x_mask is not None or src_mask is not None:
+                raise NotImplementedError("query_image_mask with attention='full' is not built")
+            q16 = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
+            ops.linear_act(x, None, L["wq"], q16, lx if x_shared else B * lx, 0, 0, split,
+                           batches=B if x_shared else 1, a0_shared=x_shared)
+            kv16 = self._buf(tag + "kv16", (B * ls, pl * 512), f16, dev)
+            ops.linear_act(src, None, L["wkv"], kv16, B * ls, 0, 0, split)
+            att = self._buf(tag + "att", (B * lx, pl * 256), f16, dev)
+            ops.full_attention(q16, kv16, att, B, lx, ls, 8, 32, split)
+            ops.linear_ln(att, None, L["merge16"], False, *L["n1"], 1, B * lx, split, out16=msg)
+        else:
+            if state is None:
+                mt, ksum = self._src_state(L, tag, src, B, ls, src_mask)
+                mt_batched = True
+            else:
+                mt, ksum = state
+                mt_batched = False
+            qz = self._buf(tag + "qz", (B * lx, pl * 256), f16, dev)
+            ops.linear_q(x, L["wq"], ksum, qz, B, lx, ls, split, x_shared=x_shared, row_mask=x_mask)
+            ops.linear_ln(qz, None, mt, mt_batched, *L["n1"], B, lx, split, out16=msg)
         h = self._buf(tag + "h", (B * lx, pl * 512), f16, dev)
         if x_shared:
             ops.linear_act(x, msg, L["mlp0"], h, lx, 1, 512, split, batches=B, a0_shared=True)
@@ -551,7 +570,8 @@ class OnePosePlus_model(nn.Module):
                        self.split)
         st["d3_in"] = d3
         names = self.loftr_coarse.layer_names
-        if Bb == 1 and len(names) >= 2 and names[0] == "self" and names[1] == "cross":
+        linear = self.config["loftr_coarse"]["attention"] == "linear"
+        if Bb == 1 and linear and len(names) >= 2 and names[0] == "self" and names[1] == "cross":
             d3_l0 = alloc("d3_l0", (1, N, pl * 256), f16)
             self._encoder_layer(self._plan["coarse"][0], "c3s_", d3, d3, 1, N, N, d3_l0)
             mt, ksum = self._src_state(self._plan["coarse"][1], "c3s_", d3_l0, 1, N)

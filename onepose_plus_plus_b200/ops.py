@@ -130,6 +130,14 @@ def linear_ln(a0, a1, w, w_batched, gamma, beta, batches, rows, split, resid=Non
          stream())
 
 
+def full_attention(q16, kv16, out, batch, l, s, heads, head_dim, split):
+    """softmax(Q K^T / sqrt(D)) V per head (attention: "full"); q16 [B*l, planes*H*D], kv16 [B*s, planes*2*H*D]."""
+    _chk(q16, torch.float16, "q")
+    _chk(kv16, torch.float16, "kv")
+    call("opp_full_attention", ptr(q16), ptr(kv16), ptr(out), batch, l, s, heads, head_dim, int(split), stream())
+    return out
+
+
 def kv_chunks(s):
     return _lib.load().opp_kv_chunks(s)
 

@@ -146,13 +146,23 @@ def linear_attention(q, k, v, eps=1e-6, q_mask=None, kv_mask=None):
     return torch.einsum("nlhd,nhdv,nlh->nlhv", Q, KV, Z) * v_len
 
 
-def encoder_layer(sd, p, x, source, nhead, x_mask=None, source_mask=None):
+def full_attention(q, k, v):
+    """FullAttention.forward (linear_attention.py:64-95), no masks, no dropout"""
+    qk = torch.einsum("nlhd,nshd->nlsh", q, k)
+    a = torch.softmax(qk / q.size(3) ** 0.5, dim=2)
+    return torch.einsum("nlsh,nshd->nlhd", a, v).contiguous()
+
+
+def encoder_layer(sd, p, x, source, nhead, x_mask=None, source_mask=None, attention="linear"):
     bs, d = x.size(0), x.size(2)
     dim = d // nhead
     q = F.linear(x, sd[p + "q_proj.weight"]).view(bs, -1, nhead, dim)
     k = F.linear(source, sd[p + "k_proj.weight"]).view(bs, -1, nhead, dim)
     v = F.linear(source, sd[p + "v_proj.weight"]).view(bs, -1, nhead, dim)
-    msg = linear_attention(q, k, v, q_mask=x_mask, kv_mask=source_mask).reshape(bs, -1, d)
+    if attention == "full":
+        msg = full_attention(q, k, v).reshape(bs, -1, d)
+    else:
+        msg = linear_attention(q, k, v, q_mask=x_mask, kv_mask=source_mask).reshape(bs, -1, d)
     msg = F.layer_norm(F.linear(msg, sd[p + "merge.weight"]), (d,), sd[p + "norm1.weight"],
                        sd[p + "norm1.bias"], 1e-5)
     msg = F.linear(F.relu(F.linear(torch.cat([x, msg], 2), sd[p + "mlp.0.weight"])),
@@ -166,16 +176,17 @@ def local_feature_transformer(sd, prefix, cfg, desc3d, desc2d, collect=None, que
     the PRE-update tensors (transformer.py:154-159); query_mask [B, S] masks the 2D side only
     (:150-159: x_mask and source_mask of the 2D self layer, x_mask of 2D<-3D, source_mask of 3D<-2D)."""
     names = list(cfg["layer_names"]) * cfg["layer_iter_n"]
+    att = cfg.get("attention", "linear")
     d3 = desc3d.transpose(1, 2)
     d2 = desc2d
     for i, name in enumerate(names):
         p = f"{prefix}layers.{i}."
         if name == "self":
-            d2, d3 = (encoder_layer(sd, p, d2, d2, cfg["nhead"], query_mask, query_mask),
-                      encoder_layer(sd, p, d3, d3, cfg["nhead"]))
+            d2, d3 = (encoder_layer(sd, p, d2, d2, cfg["nhead"], query_mask, query_mask, att),
+                      encoder_layer(sd, p, d3, d3, cfg["nhead"], attention=att))
         elif name == "cross":
-            d2, d3 = (encoder_layer(sd, p, d2, d3, cfg["nhead"], x_mask=query_mask),
-                      encoder_layer(sd, p, d3, d2, cfg["nhead"], source_mask=query_mask))
+            d2, d3 = (encoder_layer(sd, p, d2, d3, cfg["nhead"], x_mask=query_mask, attention=att),
+                      encoder_layer(sd, p, d3, d2, cfg["nhead"], source_mask=query_mask, attention=att))
         else:
             raise NotImplementedError(name)
         if collect is not None:

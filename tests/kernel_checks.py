@@ -489,6 +489,26 @@ def check_fine():
     _close("fine_match mkpts_f", mf, mkc + co * 2 * (2.0 * scale[b_ids][:, [1, 0]]), 1e-5, 1e-4)
 
 
+def check_full_attention():
+    """opp_full_attention against softmax(QK^T/sqrt(D))V in fp64 (linear_attention.py:64-95)"""
+    for split in (0, 1):
+        for (B, L, S, H, D) in [(2, 300, 517, 8, 32), (1, 130, 64, 8, 32), (3, 26, 25, 8, 16)]:
+            dm = H * D
+            qf = _rand(B * L, dm, seed=1)
+            kvf = torch.cat([_rand(B * S, dm, seed=2), _rand(B * S, dm, seed=3)], 1)
+            pl = 2 if split else 1
+            out = torch.full((B * L, pl * dm), float("nan"), device=DEV, dtype=torch.half)
+            ops.full_attention(_planes(qf, split), _planes(kvf, split), out, B, L, S, H, D, split)
+            torch.cuda.synchronize()
+            q = _q(qf, split).double().view(B, L, H, D)
+            k = _q(kvf[:, :dm], split).double().view(B, S, H, D)
+            v = _q(kvf[:, dm:], split).double().view(B, S, H, D)
+            a = torch.softmax(torch.einsum("nlhd,nshd->nlsh", q, k) / D ** 0.5, dim=2)
+            ref = torch.einsum("nlsh,nshd->nlhd", a, v).reshape(B * L, dm).float()
+            _close(f"full_attention split={split} B={B} L={L} S={S} D={D}", _unplanes(out, split), ref,
+                   *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
+
+
 # ------------------------------------------------------------------------------ one-pass dual softmax
 def check_sim_colmax():
     for split in (0, 1):
@@ -589,6 +609,7 @@ CHECKS = {
     "kv_state": check_kv_state,
     "match_select": check_match_select,
     "fine": check_fine,
+    "full_attention": check_full_attention,
     "sim_colmax": check_sim_colmax,
     "sim_lse_cols": check_sim_lse_cols,
     "kv_single_plane": check_kv_single_plane,

@@ -179,6 +179,7 @@ def test_full_forward_host_flow(monkeypatch):
     m.load_state_dict(workload.synthetic_state_dict(0))
     dev = torch.device("cpu")
     m._plan = m._prepare(dev)
+    assert m.kv_single_plane and m._buf("probe_kv16", (8, 512), torch.float16, dev).shape[1] == 512
     B, H, W, N = 2, 64, 96, 200
     img = torch.rand(B, 1, H, W)
     q2, fine_map, (hc, wc) = m._backbone(img)

@@ -67,15 +67,29 @@ def test_random_workload_has_no_matches():
 
 
 @pytest.mark.skipif(not ref_shims.available(), reason="/root/reference only exists in the build container")
-@pytest.mark.parametrize("shape", [(96, 128, 300, 120, 2, False), (512, 512, 5000, 3000, 1, False),
-                                   (96, 128, 300, 120, 2, True)],
-                         ids=["small_b2", "baseline_512_n5000", "small_b2_query_mask"])
+@pytest.mark.parametrize("shape", [(96, 128, 300, 120, 2, False, "linear"), (512, 512, 5000, 3000, 1, False, "linear"),
+                                   (96, 128, 300, 120, 2, True, "linear"), (96, 128, 300, 120, 2, False, "full")],
+                         ids=["small_b2", "baseline_512_n5000", "small_b2_query_mask", "small_b2_full_attention"])
 def test_oracle_matches_reference_live(shape):
+    import copy
     sd = weights()
-    h, w, n, npl, batch, masked = shape
+    h, w, n, npl, batch, masked, attention = shape
     data, meta = workload.planted_workload(sd, h, w, n, npl, batch=batch, seed=5)
     if masked:   # img_pad flow (OnePosePlusModel.py:158): bottom / right of the coarse grid is padding
         data["query_image_mask"] = workload.pad_mask(batch, h // 8, w // 8)
+    cfg = copy.deepcopy(oracle.DEFAULT_CONFIG)
+    cfg["loftr_coarse"]["attention"] = attention      # "full": FullAttention (linear_attention.py:64-95)
+    if attention == "full":
+        ref = ref_shims.build_reference_model(sd, cfg)
+        d_ref = {k: v.clone() for k, v in data.items()}
+        with torch.no_grad():
+            ref(d_ref)
+        d_or = {k: v.clone() for k, v in data.items()}
+        oracle.forward(sd, d_or, cfg=cfg)
+        # same weights, different attention: the planted bank no longer matches, compare the raw matrix
+        assert torch.allclose(d_ref["conf_matrix"], d_or["conf_matrix"], atol=1e-4)
+        assert torch.equal(d_ref["b_ids"], d_or["b_ids"]) and torch.equal(d_ref["j_ids"], d_or["j_ids"])
+        return
     ref = ref_shims.build_reference_model(sd, oracle.DEFAULT_CONFIG)
     d_ref = {k: v.clone() for k, v in data.items()}
     with torch.no_grad():
