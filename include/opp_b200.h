@@ -277,6 +277,45 @@ int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_id
                    const int* count_dev, opp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * LoFTR 2D-2D matcher — LoFTR_for_OnePose_Plus.forward
+ * (src/KeypointFreeSfM/loftr_for_sfm/loftr.py:35-127; modules of submodules/LoFTR/src/loftr).
+ * Backbone, transformer layers and dual-softmax passes are the entry points above; these four
+ * are what differs from the 2D-3D matcher.
+ * ---------------------------------------------------------------------------------------- */
+
+/* LoFTR get_coarse_match (utils/coarse_matching.py:133-259, inference): threshold, `border` cells
+ * removed on ALL sides of BOTH grids (:9-28), mutual nearest neighbour by value (rowmax == colmax),
+ * ordered compaction.  pt_val/pt_idx [B][h0*w0] row maxima / argmax over image 1's cells, colmax
+ * [B][h1*w1] (from opp_sim_conf_colmax).  scale0/scale1 fp32 [B][2] or NULL multiply (x, y) as
+ * given (:248-253).  Capacity of the outputs: B*h0*w0.  scratch int32 [ceil(B*h0*w0/1024) + 2]. */
+int opp_match_select_2d(const float* pt_val, const int* pt_idx, const unsigned* colmax, const float* scale0,
+                        const float* scale1, int batch, int h0, int w0, int h1, int w1, float thr,
+                        int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
+                        long long* j_ids, float* mconf, float* mkpts0_c, float* mkpts1_c, int* count_out,
+                        opp_stream_t stream);
+
+/* LoFTR FinePreprocess (loftr_module/fine_preprocess.py:30-59, fine_concat_coarse_feat False):
+ * window x window patches (zero outside the map) of both fine maps, sequence-major rows
+ * (seq * m + match) * window^2 + ww; seq 0 = image 0 centred on cell i_ids, seq 1 = image 1 on j_ids.
+ * fine0/fine1 NHWC fp16 [B][hf][wf][planes*128]; x16 fp16 [2*m*window^2][planes*128]. */
+int opp_fine_gather_2d(const void* fine0, const void* fine1, const long long* b_ids, const long long* i_ids,
+                       const long long* j_ids, void* x16, int m, int hf0, int wf0, int wc0, int hf1, int wf1,
+                       int wc1, int stride, int window, int split, opp_stream_t stream);
+
+/* LinearAttention.forward (linear_attention.py:29-61) between small token groups, 8 heads x 16:
+ * group g: q fp16 [g][l][planes*128] = elu(q_proj x)+1, kv fp16 [g][s][planes*256] =
+ * (elu(k_proj src)+1 | v_proj src); out like q. */
+int opp_seq_attention(const void* q, const void* kv, void* out, int groups, int l, int s, float eps, int split,
+                      opp_stream_t stream);
+
+/* LoFTR FineMatching.forward (utils/fine_matching.py:17-74): x32 fp32 [2][m][window^2][128]
+ * (sequence-major), centre token of seq 0 against seq 1; expec_f [m][3], mkpts1_f [m][2] =
+ * mkpts1_c + coords * (window // 2) * fine_scale * scale1[b]. */
+int opp_fine_match_2d(const float* x32, const float* mkpts1_c, const long long* b_ids, const float* scale1,
+                      float* expec_f, float* mkpts1_f, int m, int window, float fine_scale,
+                      opp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Pose from the matches — ransac_PnP (src/utils/metric_utils.py:121-204: cv2.solvePnPRansac with
  * EPnP, iterationsCount 10000, reprojectionError `pnp_reprojection_error`, per frame on the CPU
  * after a D2H copy; callers: compute_query_pose_errors metric_utils.py:207-292, demo.py:132)

@@ -5,6 +5,7 @@
 C ABI in ``include/opp_b200.h``.
 """
 from .model import LazyConfMatrix, OnePosePlus_model, build_backbone  # noqa: F401
+from .loftr import LoFTR_for_OnePose_Plus  # noqa: F401  (2D-2D matcher of the SfM / demo stages)
 from . import pnp  # noqa: F401  (device-side RANSAC-PnP front end: metric_utils.ransac_PnP)
 
 __version__ = "0.2.0"

@@ -50,6 +50,10 @@ SIGNATURES = {
     "opp_fine_match": [P, P, P, P, P, P, I, F, P, P],
     "opp_linear_act_f16_dyn": [P, I, P, I, P, P, L, P, I, I, I, I, I, P],
     "opp_linear_ln_dyn": [P, I, P, I, P, P, P, F, P, P, P, L, P, I, I, I, P],
+    "opp_match_select_2d": [P, P, P, P, P, I, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, P],
+    "opp_fine_gather_2d": [P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, I, P],
+    "opp_seq_attention": [P, P, P, I, I, I, F, I, P],
+    "opp_fine_match_2d": [P, P, P, P, P, P, I, I, F, P],
     "opp_pnp_ransac": [P, P, P, I, P, I, F, F, I, ctypes.c_uint, I, P, P, P, P, P],
 }
 PLAIN = {"opp_version": ([], c_int), "opp_num_sms": ([], c_int), "opp_sim_tiles": ([I], c_int),

@@ -102,7 +102,8 @@ static int map_rows(CUtensorMap* map, const void* ptr, long long k, long long ro
 template <int A_MODE, class Epi, bool DYN = false>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream, const int* rows_dev = nullptr, int rows_mult = 1) {
-  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair);
+  constexpr int kEpiBytes = epi_smem_bytes<Epi>();
+  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair, kEpiBytes);
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -117,7 +118,7 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
     }
     if (cap > 1 && s.stages > cap) s.stages = cap;
   }
-  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair);
+  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair, kEpiBytes);
   const void* kern;
   if constexpr (DYN) kern = (const void*)gemm_kernel_dyn<A_MODE, Epi>;
   else kern = (const void*)gemm_kernel<A_MODE, Epi>;

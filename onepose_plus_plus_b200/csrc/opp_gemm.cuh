@@ -137,6 +137,21 @@ struct EpiCtx {
 
 __device__ __forceinline__ void epi_sync(const EpiCtx& c) { named_bar_sync(1 + c.group, 128); }
 
+// bytes of private staging per epilogue warp: kWarpStageBytes unless the epilogue declares
+// `static constexpr int kWarpStage` (EpiConvUp stages both planes of a chunk at once)
+template <class E, class = void>
+struct EpiWarpStage {
+  static constexpr int value = 32 * 80;
+};
+template <class E>
+struct EpiWarpStage<E, std::void_t<decltype(E::kWarpStage)>> {
+  static constexpr int value = E::kWarpStage;
+};
+template <class E>
+constexpr int epi_smem_bytes() {
+  return 4096 + 8 * EpiWarpStage<E>::value;   // kEpiParamBytes + kMaxEpiWarps * stage
+}
+
 // epilogues that look one tile ahead declare `static constexpr bool kNeedsNext`
 template <class E, class = void>
 struct EpiNeedsNext : std::false_type {};
@@ -661,6 +676,7 @@ struct EpiConv {
 struct EpiConvUp {
   static constexpr int kGroups = OPP_CONV_GROUPS;
   static constexpr bool kNeedsNext = true;   // EpiCtx::next_b / next_m_tile are filled in
+  static constexpr int kWarpStage = 2 * 32 * 80;   // hi and lo windows of a chunk side by side
   using Params = EpiConvParams;
 
   struct Geo {
@@ -735,27 +751,38 @@ struct EpiConvUp {
         nb[4 + i] = (ok && two) ? *reinterpret_cast<const uint4*>(px + p.out_lo) : make_uint4(0, 0, 0, 0);
       }
     };
-    auto stage = [&](int plane) {
+    // both planes of the window are staged side by side (lo at +kLo) and blended in one sweep: two
+    // independent FMA chains per element instead of two dependent stage/sync/blend rounds
+    constexpr uint32_t kLo = 32 * kStageRowH;
+    auto stage = [&]() {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        sts128(c.wstage_s + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16, nb[plane * 4 + i]);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t a = c.wstage_s + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16;
+        sts128(a, nb[i]);
+        if (two) sts128(a + kLo, nb[4 + i]);
+      }
       __syncwarp();
     };
     auto blend = [&](float* v) {
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
-        const uint4 q00 = lds128(a00 + q4 * 16), q01 = lds128(a01 + q4 * 16);
-        const uint4 q10 = lds128(a10 + q4 * 16), q11 = lds128(a11 + q4 * 16);
-        const __half2* h00 = reinterpret_cast<const __half2*>(&q00);
-        const __half2* h01 = reinterpret_cast<const __half2*>(&q01);
-        const __half2* h10 = reinterpret_cast<const __half2*>(&q10);
-        const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 fa = __half22float2(h00[j]), fb = __half22float2(h01[j]);
-          const float2 fc = __half22float2(h10[j]), fd = __half22float2(h11[j]);
-          v[8 * q4 + 2 * j] += (w00 * fa.x + w01 * fb.x) + (w10 * fc.x + w11 * fd.x);
-          v[8 * q4 + 2 * j + 1] += (w00 * fa.y + w01 * fb.y) + (w10 * fc.y + w11 * fd.y);
+        for (int plane = 0; plane < 2; ++plane) {
+          if (plane == 1 && !two) break;
+          const uint32_t o = plane * kLo + q4 * 16;
+          const uint4 q00 = lds128(a00 + o), q01 = lds128(a01 + o);
+          const uint4 q10 = lds128(a10 + o), q11 = lds128(a11 + o);
+          const __half2* h00 = reinterpret_cast<const __half2*>(&q00);
+          const __half2* h01 = reinterpret_cast<const __half2*>(&q01);
+          const __half2* h10 = reinterpret_cast<const __half2*>(&q10);
+          const __half2* h11 = reinterpret_cast<const __half2*>(&q11);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 fa = __half22float2(h00[j]), fb = __half22float2(h01[j]);
+            const float2 fc = __half22float2(h10[j]), fd = __half22float2(h11[j]);
+            v[8 * q4 + 2 * j] += (w00 * fa.x + w01 * fb.x) + (w10 * fc.x + w11 * fd.x);
+            v[8 * q4 + 2 * j + 1] += (w00 * fa.y + w01 * fb.y) + (w10 * fc.y + w11 * fd.y);
+          }
         }
       }
       __syncwarp();
@@ -772,13 +799,11 @@ struct EpiConvUp {
         v[4 * q4 + 2] += __uint_as_float(bq.z);
         v[4 * q4 + 3] += __uint_as_float(bq.w);
       }
-      stage(0);
-      blend(v);
-      if (two) stage(1);
+      stage();
       // nb is free again: fetch the next chunk's window while this chunk is blended and stored
       const int ncol = col + c.col_step;
       if (ncol < c.ncols) issue(ncol);
-      if (two) blend(v);
+      blend(v);
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -1072,7 +1097,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
   uint8_t* smem_b = smem + s.stages * a_stage;
   float* epi_smem = reinterpret_cast<float*>(smem_b + s.stages * b_stage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_smem) +
-                                               kEpiSmemBytes);
+                                               epi_smem_bytes<Epi>());
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
@@ -1342,7 +1367,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
     c.col_first = 32 * c.group;
     c.col_step = 32 * Epi::kGroups;
     c.smem = epi_smem + c.group * (kEpiParamBytes / 8);   // 2 KB (512 floats) per group
-    c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + warp * kWarpStageBytes;
+    c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + warp * EpiWarpStage<Epi>::value;
     c.smem_s = smem_u32(c.smem);
     c.wstage_s = smem_u32(c.wstage);
     int it = 0;
@@ -1427,12 +1452,12 @@ gemm_kernel_dyn(const __grid_constant__ TensorMaps maps, const GemmShape s_in,
 inline int gemm_stage_bytes(int block_n, int split, int pair) {
   return (kABytes + (pair ? block_n / 2 : block_n) * kBlockK * 2) * (split ? 2 : 1);
 }
-inline int gemm_smem_bytes(int stages, int block_n, int split, int pair) {
-  return stages * gemm_stage_bytes(block_n, split, pair) + kEpiSmemBytes + (2 * kMaxStages + 4) * 8 +
+inline int gemm_smem_bytes(int stages, int block_n, int split, int pair, int epi_bytes = kEpiSmemBytes) {
+  return stages * gemm_stage_bytes(block_n, split, pair) + epi_bytes + (2 * kMaxStages + 4) * 8 +
          16 + 1024;
 }
-inline int gemm_pick_stages(int block_n, int k_chunks, int split, int pair) {
-  int st = (227 * 1024 - kEpiSmemBytes - 2048) / gemm_stage_bytes(block_n, split, pair);
+inline int gemm_pick_stages(int block_n, int k_chunks, int split, int pair, int epi_bytes = kEpiSmemBytes) {
+  int st = (227 * 1024 - epi_bytes - 2048) / gemm_stage_bytes(block_n, split, pair);
   if (st > kMaxStages) st = kMaxStages;
   if (st > k_chunks * 2 && k_chunks * 2 >= 2) st = k_chunks * 2;
   return st < 2 ? 2 : st;

@@ -450,30 +450,55 @@ __global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* _
   lse[r] = m + logf(s);
 }
 
-// column side of opp_sim_lse_cols: lse[b][s] = logsumexp over the row groups of (col_m, col_s)
-__global__ void lse_col_finalize_kernel(const float* __restrict__ cm, const float* __restrict__ cs,
-                                        float* __restrict__ lse, int batches, int groups, int cols,
-                                        const unsigned char* __restrict__ col_mask) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)batches * cols) return;
-  if (col_mask && col_mask[idx] == 0) {
-    // padded query cell: every sim of this column is -1e9, so conf = 0 whatever the row
-    // (coarse_matching.py:108-115); +inf makes exp((2 sim - lse_pt) - lse_px) exactly 0
-    lse[idx] = INFINITY;
-    return;
+// column side of opp_sim_lse_cols: lse[b][s] = logsumexp over the row groups of (col_m, col_s).
+// Block = 32 columns x 8 group slices (coalesced 128 B rows; 8 independent load chains per column
+// instead of one thread walking all ~150 groups: the old form took 63 us for ONE image), merged
+// through shared memory.
+__global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __restrict__ cm,
+                                                               const float* __restrict__ cs,
+                                                               float* __restrict__ lse, int batches,
+                                                               int groups, int cols,
+                                                               const unsigned char* __restrict__ col_mask) {
+  __shared__ float m_s[8][32], s_s[8][32];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int sidx = blockIdx.x * 32 + lane;
+  float m = -INFINITY, sum = 0.f;
+  if (sidx < cols) {
+    const float* pm = cm + (long long)b * groups * cols + sidx;
+    const float* ps = cs + (long long)b * groups * cols + sidx;
+    for (int g = slice; g < groups; g += 8) {
+      const float pg = pm[(long long)g * cols];
+      if (pg == -INFINITY) continue;
+      const float sg = ps[(long long)g * cols];
+      if (pg > m) {
+        sum = sum * expf(m - pg) + sg;
+        m = pg;
+      } else {
+        sum += sg * expf(pg - m);
+      }
+    }
   }
-  const int b = (int)(idx / cols);
-  const int sidx = (int)(idx - (long long)b * cols);
-  const float* pm = cm + (long long)b * groups * cols + sidx;
-  const float* ps = cs + (long long)b * groups * cols + sidx;
-  float m = -INFINITY;
-  for (int g = 0; g < groups; ++g) m = fmaxf(m, pm[(long long)g * cols]);
-  float sum = 0.f;
-  for (int g = 0; g < groups; ++g) {
-    const float pg = pm[(long long)g * cols];
-    if (pg != -INFINITY) sum += ps[(long long)g * cols] * expf(pg - m);
+  m_s[slice][lane] = m;
+  s_s[slice][lane] = sum;
+  __syncthreads();
+  if (slice == 0 && sidx < cols) {
+    const long long idx = (long long)b * cols + sidx;
+    if (col_mask && col_mask[idx] == 0) {
+      // padded query cell: every sim of this column is -1e9, so conf = 0 whatever the row
+      // (coarse_matching.py:108-115); +inf makes exp((2 sim - lse_pt) - lse_px) exactly 0
+      lse[idx] = INFINITY;
+      return;
+    }
+    float mm = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mm = fmaxf(mm, m_s[k][lane]);
+    float tot = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (m_s[k][lane] != -INFINITY) tot += s_s[k][lane] * expf(m_s[k][lane] - mm);
+    lse[idx] = mm + logf(tot);
   }
-  lse[idx] = m + logf(sum);
 }
 
 __global__ void best_finalize_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
@@ -948,6 +973,276 @@ __global__ void __launch_bounds__(128) fine_match_kernel(
   }
 }
 
+// =============================================================================================
+// LoFTR 2D-2D matcher: LoFTR_for_OnePose_Plus.forward
+// (src/KeypointFreeSfM/loftr_for_sfm/loftr.py:35-127 on submodules/LoFTR/src/loftr).  The backbone,
+// the coarse transformer layers and the dual-softmax passes are the engine's; the kernels below are
+// what differs from the 2D-3D matcher: symmetric border + two image grids in the match selection,
+// W x W windows from BOTH fine maps, linear attention between two token groups, and the centre
+// token of image 0's window correlated with image 1's window.
+// =============================================================================================
+
+// keep (b, i) iff conf_max > thr, i and its argmax j are >= border cells away from ALL four sides of
+// their grids (LoFTR utils/coarse_matching.py:9-28,197-203) and i is the column maximum of j
+__device__ __forceinline__ bool match_flag_2d(const float* pt_val, const int* pt_idx,
+                                              const unsigned* colmax, long long r, int l, int s,
+                                              int h0, int w0, int h1, int w1, float thr, int border) {
+  const float v = pt_val[r];
+  if (!(v > thr)) return false;
+  const int j = pt_idx[r];
+  const long long b = r / l;
+  const int i = (int)(r - b * l);
+  const int iy = i / w0, ix = i - iy * w0, jy = j / w1, jx = j - jy * w1;
+  if (iy < border || ix < border || iy >= h0 - border || ix >= w0 - border) return false;
+  if (jy < border || jx < border || jy >= h1 - border || jx >= w1 - border) return false;
+  return colmax[b * s + j] == __float_as_uint(v);
+}
+
+__global__ void __launch_bounds__(1024) match_count_2d_kernel(const float* pt_val, const int* pt_idx,
+                                                              const unsigned* colmax, long long rows,
+                                                              int l, int s, int h0, int w0, int h1,
+                                                              int w1, float thr, int border,
+                                                              int* block_counts) {
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag_2d(pt_val, pt_idx, colmax, r, l, s, h0, w0, h1, w1, thr, border);
+  const int c = __syncthreads_count(f);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(1024)
+match_scatter_2d_kernel(const float* pt_val, const int* pt_idx, const unsigned* colmax,
+                        const float* scale0, const float* scale1, long long rows, int l, int s, int h0,
+                        int w0, int h1, int w1, float thr, int border, float cell,
+                        const int* block_offsets, long long* b_ids, long long* i_ids, long long* j_ids,
+                        float* mconf, float* mk0, float* mk1) {
+  __shared__ int warp_sums[32];
+  const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
+  const bool f = r < rows && match_flag_2d(pt_val, pt_idx, colmax, r, l, s, h0, w0, h1, w1, thr, border);
+  const unsigned ballot = __ballot_sync(0xffffffffu, f);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) warp_sums[warp] = __popc(ballot);
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += y;
+    }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  if (!f) return;
+  const int pos = block_offsets[blockIdx.x] + (warp > 0 ? warp_sums[warp - 1] : 0) +
+                  __popc(ballot & ((1u << lane) - 1u));
+  const long long b = r / l;
+  const int i = (int)(r - b * l);
+  const int j = pt_idx[r];
+  b_ids[pos] = b;
+  i_ids[pos] = i;
+  j_ids[pos] = j;
+  mconf[pos] = pt_val[r];
+  // LoFTR coarse_matching.py:248-253: [idx % w, idx // w] * scale * scale0[b]  (no axis swap here)
+  const float s0x = scale0 ? cell * scale0[b * 2] : cell, s0y = scale0 ? cell * scale0[b * 2 + 1] : cell;
+  const float s1x = scale1 ? cell * scale1[b * 2] : cell, s1y = scale1 ? cell * scale1[b * 2 + 1] : cell;
+  mk0[pos * 2 + 0] = (float)(i % w0) * s0x;
+  mk0[pos * 2 + 1] = (float)(i / w0) * s0y;
+  mk1[pos * 2 + 0] = (float)(j % w1) * s1x;
+  mk1[pos * 2 + 1] = (float)(j / w1) * s1y;
+}
+
+// W x W windows of both fine maps (LoFTR loftr_module/fine_preprocess.py:41-49), sequence-major:
+// row (seq * M + m) * WW + ww;  seq 0 = image 0's window centred on cell i, seq 1 = image 1's on j.
+__global__ void __launch_bounds__(128) fine_gather_2d_kernel(
+    const __half* __restrict__ f0, const __half* __restrict__ f1, const long long* __restrict__ b_ids,
+    const long long* __restrict__ i_ids, const long long* __restrict__ j_ids, __half* __restrict__ x16,
+    int M, int hf0, int wf0, int wc0, int hf1, int wf1, int wc1, int stride, int W, int lo_off) {
+  const int m = blockIdx.x, seq = blockIdx.y, c = threadIdx.x;
+  const long long b = b_ids[m];
+  const long long cell = seq ? j_ids[m] : i_ids[m];
+  const int wc = seq ? wc1 : wc0, hf = seq ? hf1 : hf0, wf = seq ? wf1 : wf0;
+  const int cy = (int)(cell / wc), cx = (int)(cell - (long long)cy * wc);
+  const int ld = lo_off ? 256 : 128;
+  const __half* fb = (seq ? f1 : f0) + b * hf * wf * ld;
+  const int WW = W * W, half = W / 2;
+  const long long row0 = ((long long)seq * M + m) * WW;
+  for (int ww = 0; ww < WW; ++ww) {
+    const int y = cy * stride + ww / W - half, x = cx * stride + ww % W - half;
+    float v = 0.f;
+    if (y >= 0 && y < hf && x >= 0 && x < wf) v = load_split1(fb + ((long long)y * wf + x) * ld, c, lo_off);
+    store_split1(x16 + (row0 + ww) * ld, c, v, lo_off);
+  }
+}
+
+// Linear attention between two small token groups (linear_attention.py:29-61; 8 heads x 16):
+// group g: queries q[g][0..L), source kv[g][0..S) = (K' | V).  One CTA per group, thread (h, v) owns
+// column v of head h of the 16 x 16 state; tokens stream through shared memory in slabs of 27.
+constexpr int kSaSlab = 27;
+__global__ void __launch_bounds__(128) seq_attention_kernel(const __half* __restrict__ q,
+                                                            const __half* __restrict__ kv,
+                                                            __half* __restrict__ out, int L, int S,
+                                                            float eps, int lo_q, int lo_kv) {
+  __shared__ __align__(16) float a_s[kSaSlab][128];
+  __shared__ __align__(16) float b_s[kSaSlab][128];
+  __shared__ __align__(16) float ks2[128];
+  const int g = blockIdx.x, c = threadIdx.x, h = c >> 4;
+  const int ldq = lo_q ? 256 : 128, ldk = lo_kv ? 512 : 256;
+  const __half* kvp = kv + (long long)g * S * ldk;
+  float col[16];
+#pragma unroll
+  for (int dd = 0; dd < 16; ++dd) col[dd] = 0.f;
+  float ksum_c = 0.f;
+  for (int t0 = 0; t0 < S; t0 += kSaSlab) {
+    const int cnt = min(kSaSlab, S - t0);
+    __syncthreads();
+    for (int i = c; i < cnt * 32; i += 128) {     // 32 groups of 8 values per token: K' (16) | V (16)
+      const int t = i >> 5, sg = i & 31;
+      float f[8];
+      load_split8(kvp + (long long)(t0 + t) * ldk, sg * 8, f, lo_kv);
+      float* dst = sg < 16 ? &a_s[t][sg * 8] : &b_s[t][(sg - 16) * 8];
+      reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    for (int t = 0; t < cnt; ++t) {
+      const float vv = b_s[t][c];
+      const float4* kr = reinterpret_cast<const float4*>(&a_s[t][h * 16]);
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const float4 k4 = kr[gq];
+        col[4 * gq + 0] = fmaf(k4.x, vv, col[4 * gq + 0]);
+        col[4 * gq + 1] = fmaf(k4.y, vv, col[4 * gq + 1]);
+        col[4 * gq + 2] = fmaf(k4.z, vv, col[4 * gq + 2]);
+        col[4 * gq + 3] = fmaf(k4.w, vv, col[4 * gq + 3]);
+      }
+      ksum_c += a_s[t][c];
+    }
+  }
+  __syncthreads();
+  ks2[c] = ksum_c;
+  __syncthreads();
+  float ksw[16];
+  {
+    const float4* a = reinterpret_cast<const float4*>(&ks2[h * 16]);
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) {
+      const float4 x = a[gq];
+      ksw[4 * gq] = x.x; ksw[4 * gq + 1] = x.y; ksw[4 * gq + 2] = x.z; ksw[4 * gq + 3] = x.w;
+    }
+  }
+  const __half* qp = q + (long long)g * L * ldq;
+  __half* op = out + (long long)g * L * ldq;
+  for (int t0 = 0; t0 < L; t0 += kSaSlab) {
+    const int cnt = min(kSaSlab, L - t0);
+    __syncthreads();
+    for (int i = c; i < cnt * 16; i += 128) {
+      const int t = i >> 4, sg = i & 15;
+      float f[8];
+      load_split8(qp + (long long)(t0 + t) * ldq, sg * 8, f, lo_q);
+      reinterpret_cast<float4*>(&a_s[t][sg * 8])[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(&a_s[t][sg * 8])[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    for (int t = 0; t < cnt; ++t) {
+      const float4* qr = reinterpret_cast<const float4*>(&a_s[t][h * 16]);
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const float4 q4 = qr[gq];
+        num = fmaf(q4.x, col[4 * gq + 0], num);
+        den = fmaf(q4.x, ksw[4 * gq + 0], den);
+        num = fmaf(q4.y, col[4 * gq + 1], num);
+        den = fmaf(q4.y, ksw[4 * gq + 1], den);
+        num = fmaf(q4.z, col[4 * gq + 2], num);
+        den = fmaf(q4.z, ksw[4 * gq + 2], den);
+        num = fmaf(q4.w, col[4 * gq + 3], num);
+        den = fmaf(q4.w, ksw[4 * gq + 3], den);
+      }
+      b_s[t][c] = num / (den + eps);
+    }
+    __syncthreads();
+    for (int i = c; i < cnt * 16; i += 128) {
+      const int t = i >> 4, sg = i & 15;
+      float f[8];
+      const float4 a = reinterpret_cast<const float4*>(&b_s[t][sg * 8])[0];
+      const float4 b = reinterpret_cast<const float4*>(&b_s[t][sg * 8])[1];
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+      f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      store_split8(op + (long long)(t0 + t) * ldq, sg * 8, f, lo_q);
+    }
+  }
+}
+
+// LoFTR FineMatching (utils/fine_matching.py:46-70): centre token (WW // 2) of image 0's window
+// against the WW tokens of image 1's window; softmax / sqrt(C), expectation + std on the W x W grid
+// linspace(-1, 1, W) (x fastest); mkpts1_f = mkpts1_c + coords * (W // 2) * scale * scale1[b].
+// x32 fp32 [2][M][WW][128] (sequence-major).  One warp per match.
+__global__ void __launch_bounds__(128) fine_match_2d_kernel(
+    const float* __restrict__ x32, const float* __restrict__ mk1c, const long long* __restrict__ b_ids,
+    const float* __restrict__ scale1, float* __restrict__ expec_f, float* __restrict__ mk1f, int M, int W,
+    float fine_scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = blockIdx.x * 4 + warp;
+  if (m >= M) return;
+  const int WW = W * W;
+  const float4 a = reinterpret_cast<const float4*>(x32 + ((long long)m * WW + WW / 2) * 128)[lane];
+  const float* f1 = x32 + ((long long)M + m) * WW * 128;
+  float sim[3] = {-INFINITY, -INFINITY, -INFINITY};   // this lane owns tokens lane, lane + 32, lane + 64
+  for (int r = 0; r < WW; ++r) {
+    const float4 w = reinterpret_cast<const float4*>(f1 + (long long)r * 128)[lane];
+    float d = a.x * w.x + a.y * w.y + a.z * w.z + a.w * w.w;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((r & 31) == lane) sim[r >> 5] = d * 0.08838834764831845f;  // 1/sqrt(128)
+  }
+  float mx = fmaxf(sim[0], fmaxf(sim[1], sim[2]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float e[3], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    e[k] = (lane + 32 * k < WW) ? expf(sim[k] - mx) : 0.f;
+    sum += e[k];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float ex = 0.f, ey = 0.f, exx = 0.f, eyy = 0.f;
+  const float step = 2.f / (float)(W - 1);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int r = lane + 32 * k;
+    if (r < WW) {
+      const float p = e[k] / sum;
+      const float gx = -1.f + step * (float)(r % W), gy = -1.f + step * (float)(r / W);
+      ex += gx * p;
+      ey += gy * p;
+      exx += gx * gx * p;
+      eyy += gy * gy * p;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+    ey += __shfl_xor_sync(0xffffffffu, ey, o);
+    exx += __shfl_xor_sync(0xffffffffu, exx, o);
+    eyy += __shfl_xor_sync(0xffffffffu, eyy, o);
+  }
+  if (lane == 0) {
+    const float vx = exx - ex * ex, vy = eyy - ey * ey;
+    expec_f[m * 3 + 0] = ex;
+    expec_f[m * 3 + 1] = ey;
+    expec_f[m * 3 + 2] = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
+    float sx = fine_scale, sy = fine_scale;
+    if (scale1) {
+      const long long b = b_ids[m];
+      sx = fine_scale * scale1[b * 2];
+      sy = fine_scale * scale1[b * 2 + 1];
+    }
+    mk1f[m * 2 + 0] = mk1c[m * 2 + 0] + ex * (float)(W / 2) * sx;
+    mk1f[m * 2 + 1] = mk1c[m * 2 + 1] + ey * (float)(W / 2) * sy;
+  }
+}
+
 }  // namespace opp
 
 using namespace opp;
@@ -1087,8 +1382,7 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
 int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
                          int cols, const unsigned char* col_mask, opp_stream_t stream) {
   OPP_REQUIRE(col_m && col_s && lse && batches > 0 && groups > 0 && cols > 0, "bad lse_col_finalize arguments");
-  const long long n = (long long)batches * cols;
-  lse_col_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  lse_col_finalize_kernel<<<dim3((cols + 31) / 32, batches), 256, 0, (cudaStream_t)stream>>>(
       col_m, col_s, lse, batches, groups, cols, col_mask);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
@@ -1194,6 +1488,62 @@ int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_id
   OPP_REQUIRE(x32 && mkpts_c && b_ids && expec_f && mkpts_f, "null pointer");
   fine_match_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts_c, b_ids, img_scale,
                                                                    expec_f, mkpts_f, m, fine_scale, count_dev);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_match_select_2d(const float* pt_val, const int* pt_idx, const unsigned* colmax, const float* scale0,
+                        const float* scale1, int batch, int h0, int w0, int h1, int w1, float thr,
+                        int border, float cell, int* scratch, long long* b_ids, long long* i_ids,
+                        long long* j_ids, float* mconf, float* mkpts0_c, float* mkpts1_c, int* count_out,
+                        opp_stream_t stream) {
+  OPP_REQUIRE(pt_val && pt_idx && colmax && scratch && count_out, "null pointer");
+  const int l = h0 * w0, s = h1 * w1;
+  const long long rows = (long long)batch * l;
+  const int nblocks = (int)((rows + 1023) / 1024);
+  cudaStream_t st = (cudaStream_t)stream;
+  match_count_2d_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, rows, l, s, h0, w0, h1, w1, thr,
+                                                  border, scratch);
+  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
+  match_scatter_2d_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, scale0, scale1, rows, l, s, h0, w0,
+                                                    h1, w1, thr, border, cell, scratch, b_ids, i_ids, j_ids,
+                                                    mconf, mkpts0_c, mkpts1_c);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_fine_gather_2d(const void* fine0, const void* fine1, const long long* b_ids, const long long* i_ids,
+                       const long long* j_ids, void* x16, int m, int hf0, int wf0, int wc0, int hf1, int wf1,
+                       int wc1, int stride, int window, int split, opp_stream_t stream) {
+  if (m == 0) return OPP_OK;
+  OPP_REQUIRE(fine0 && fine1 && b_ids && i_ids && j_ids && x16, "null pointer");
+  OPP_REQUIRE(window % 2 == 1 && window >= 1 && window <= 9, "window %d unsupported (odd, <= 9)", window);
+  fine_gather_2d_kernel<<<dim3(m, 2), 128, 0, (cudaStream_t)stream>>>(
+      (const __half*)fine0, (const __half*)fine1, b_ids, i_ids, j_ids, (__half*)x16, m, hf0, wf0, wc0, hf1, wf1,
+      wc1, stride, window, split ? 128 : 0);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_seq_attention(const void* q, const void* kv, void* out, int groups, int l, int s, float eps, int split,
+                      opp_stream_t stream) {
+  if (groups == 0) return OPP_OK;
+  OPP_REQUIRE(q && kv && out && l > 0 && s > 0, "bad seq_attention arguments");
+  seq_attention_kernel<<<groups, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+                                                                 (__half*)out, l, s, eps, split ? 128 : 0,
+                                                                 split ? 256 : 0);
+  OPP_CHECK_CUDA(cudaGetLastError());
+  return OPP_OK;
+}
+
+int opp_fine_match_2d(const float* x32, const float* mkpts1_c, const long long* b_ids, const float* scale1,
+                      float* expec_f, float* mkpts1_f, int m, int window, float fine_scale,
+                      opp_stream_t stream) {
+  if (m == 0) return OPP_OK;
+  OPP_REQUIRE(x32 && mkpts1_c && b_ids && expec_f && mkpts1_f, "null pointer");
+  OPP_REQUIRE(window % 2 == 1 && window >= 3 && window <= 9, "window %d unsupported (odd, 3..9)", window);
+  fine_match_2d_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts1_c, b_ids, scale1, expec_f,
+                                                                      mkpts1_f, m, window, fine_scale);
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -212,107 +212,43 @@ def _pad16(c):
 # ---------------------------------------------------------------------------------------------
 # the model
 # ---------------------------------------------------------------------------------------------
-class OnePosePlus_model(nn.Module):
-    def __init__(self, config, profiler=None, debug=False, precision=None):
-        """`precision` (extension; default from $OPP_B200_PRECISION or "fp16x3"):
-        "fp16x3" = 2-term fp16 split operands, three tcgen05 MMAs per K-step (fp32-grade, the
-        parity mode); "fp16" = single fp16 operands (fast, ~1e-2 deviations on high-gain inputs)."""
-        super().__init__()
-        self.config = config
-        self.profiler = profiler
-        self.debug = debug
+class _Engine(nn.Module):
+    """What the 2D-3D matcher (OnePosePlus_model) and the 2D-2D matcher (loftr.LoFTR_for_OnePose_Plus)
+    share: weight preparation for the kernels, the name-keyed workspace, the ResNet-FPN backbone
+    and the d_model-256 encoder layer, all as sequences of C-ABI calls."""
+
+    def _init_engine(self, precision, coarse_attention="linear"):
         precision = precision or os.environ.get("OPP_B200_PRECISION", "fp16x3")
         if precision not in ("fp16x3", "fp16"):
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
-        self.backbone = build_backbone(config["loftr_backbone"])
-        if config["positional_encoding"]["enable"]:
-            self.dense_pos_encoding = PositionEncodingSine(
-                config["loftr_coarse"]["d_model"],
-                max_shape=config["positional_encoding"]["pos_emb_shape"])
-        else:
-            self.dense_pos_encoding = None
-        if config["keypoints_encoding"]["enable"]:
-            if config["keypoints_encoding"]["type"] != "mlp_linear":
-                raise NotImplementedError
-            self.kpt_3d_pos_encoding = KeypointEncoding_linear(
-                inp_dim=3, feature_dim=config["keypoints_encoding"]["descriptor_dim"],
-                layers=config["keypoints_encoding"]["keypoints_encoder"],
-                norm_method=config["keypoints_encoding"]["norm_method"])
-        else:
-            raise NotImplementedError("keypoints_encoding.enable=False is not built")
-        self.loftr_coarse = LocalFeatureTransformer(config["loftr_coarse"])
-        self.coarse_matching = CoarseMatching(config["coarse_matching"], profiler=profiler)
-        self.fine_preprocess = FinePreprocess(config["loftr_fine"],
-                                              cf_res=config["loftr_backbone"]["resolution"])
-        self.loftr_fine = LocalFeatureTransformer(config["loftr_fine"])
-        self.fine_matching = FineMatching(config["fine_matching"])
-        if config["loftr_coarse"]["d_model"] != 256 or config["loftr_coarse"]["nhead"] != 8:
-            raise NotImplementedError("coarse kernels are built for d_model 256, 8 heads")
-        if config["loftr_fine"]["d_model"] != 128 or config["loftr_fine"]["nhead"] != 8:
-            raise NotImplementedError("fine kernels are built for d_model 128, 8 heads")
-        if config["loftr_fine"]["attention"] != "linear":
-            raise NotImplementedError("the fine-level kernels implement attention='linear' (every shipped "
-                                      "config); 'full' is built for the coarse transformer only")
-        if config["loftr_fine"]["window_size"] != 5:
-            raise NotImplementedError("fine kernels are built for window_size 5")
-        b = config["loftr_backbone"]["resnetfpn"]
-        if list(b["block_dims"]) != [128, 196, 256] or b["initial_dim"] != 128 \
-                or list(b["output_layers"]) != [3, 1]:
-            raise NotImplementedError("backbone kernels are built for dims 128/[128,196,256], outputs [3,1]")
-
-        self.loftr_backbone_pretrained = config["loftr_backbone"]["pretrained"]
-        if self.loftr_backbone_pretrained is not None:
-            # OnePosePlusModel.py:79-94: initialise the backbone from a LoFTR checkpoint
-            ckpt = torch.load(self.loftr_backbone_pretrained, "cpu")["state_dict"]
-            for k in list(ckpt.keys()):
-                if "backbone" in k:
-                    ckpt[k[k.find("backbone") + len("backbone") + 1:]] = ckpt[k]
-                ckpt.pop(k)
-            self.backbone.load_state_dict(ckpt)
-            if config["loftr_backbone"]["pretrained_fix"]:
-                for p in self.backbone.parameters():
-                    p.requires_grad = False
+        self._coarse_attention = coarse_attention
         self._plan = None
         self._plan_sig = None
         self._sig_tensors = None
         self._apply_epoch = 0
         self._ws = {}
         self._ws_epoch = 0
-        self._bank = None
         self._graphs = {}
-        self._fwd_count = 0
-        self.use_cuda_graphs = os.environ.get("OPP_B200_GRAPHS", "0") == "1"
-        # data["conf_matrix"]: "eager" = fp32 [B, N, S] written every forward (reference contract,
-        # coarse_matching.py:119; what the training loss reads); "lazy" = a LazyConfMatrix handle
-        # that materialises on demand (no inference consumer reads the matrix:
-        # inference_OnePosePlus_worker.py:20-31); "skip" = key not written.
-        self.conf_matrix_mode = os.environ.get("OPP_B200_CONF", "eager")
-        # one-pass dual softmax: column statistics of sim / conf from the row passes (warp
-        # butterflies in the epilogue) instead of two more sim GEMM passes
-        self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "1") == "1"
-        self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "1") == "1"
         # K'/V rows of the coarse attention state stored as ONE fp16 plane: their only consumer sums
         # them over thousands of tokens, so the 2^-12 rounding averages out (oracle experiment: conf
         # changes by 1e-4; the whole GPU parity suite passes with it: profiles/r2_kv1_adoption.md)
         self.kv_single_plane = os.environ.get("OPP_B200_KV1", "1") == "1"
 
+    def _pe_module(self):
+        return getattr(self, "dense_pos_encoding", None)
+
+    def _ensure_plan(self, dev):
+        sig = self._signature()
+        if self._plan is None or self._plan_sig != sig or self._plan["device"] != dev:
+            self._plan = self._prepare(dev)
+            self._plan["device"] = dev
+            self._plan_sig = sig
+            self._graphs = {}
+
     @property
     def split(self):
         return self.precision == "fp16x3"
-
-    # pickling (Ray ships the module object): drop device-side caches
-    def __getstate__(self):
-        st = self.__dict__.copy()
-        st["_plan"], st["_plan_sig"], st["_ws"], st["_sig_tensors"] = None, None, {}, None
-        st["_bank"], st["_graphs"] = None, {}
-        return st
-
-    def __setstate__(self, st):
-        self.__dict__.update(st)
-        for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
-                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False)):
-            self.__dict__.setdefault(k, v)
 
     # ------------------------------------------------------------------ weight preparation
     def _apply(self, fn, *args, **kwargs):
@@ -383,8 +319,9 @@ class OnePosePlus_model(nn.Module):
         conv("layer1_outconv2.0", "layer1_outconv2.0", "layer1_outconv2.1")
         conv("layer1_outconv2.3", "layer1_outconv2.3", None)
 
-        P["kpt_mlp"] = [(sd[f"kpt_3d_pos_encoding.encoder.{i}.weight"].t().contiguous(),
-                         sd[f"kpt_3d_pos_encoding.encoder.{i}.bias"].contiguous()) for i in (0, 3, 6, 9)]
+        if "kpt_3d_pos_encoding.encoder.0.weight" in sd:
+            P["kpt_mlp"] = [(sd[f"kpt_3d_pos_encoding.encoder.{i}.weight"].t().contiguous(),
+                             sd[f"kpt_3d_pos_encoding.encoder.{i}.bias"].contiguous()) for i in (0, 3, 6, 9)]
 
         def layer(prefix):
             g = lambda k: sd[prefix + k]  # noqa: E731
@@ -409,10 +346,11 @@ class OnePosePlus_model(nn.Module):
     def _pe_tokens(self, hc, wc, device):
         key = (hc, wc)
         if key not in self._plan["pe"]:
-            if self.dense_pos_encoding is None:
+            pem = self._pe_module()
+            if pem is None:
                 pe = torch.zeros(hc * wc, 256, device=device)
             else:
-                pe = self.dense_pos_encoding.pe[0, :, :hc, :wc].to(device)
+                pe = pem.pe[0, :, :hc, :wc].to(device)
                 pe = pe.permute(1, 2, 0).reshape(hc * wc, -1).contiguous()
             self._plan["pe"][key] = pe
         return self._plan["pe"][key]
@@ -519,7 +457,7 @@ class OnePosePlus_model(nn.Module):
         split = self.split
         pl = 2 if split else 1
         msg = self._buf(tag + "msg", (B * lx, pl * 256), f16, dev)
-        if self.config["loftr_coarse"]["attention"] == "full":
+        if self._coarse_attention == "full":
             # FullAttention (linear_attention.py:64-95): q/k/v projections, softmax(QK^T/sqrt(D))V per
             # head, merge + LayerNorm (transformer.py:77-86).  Cold path (no shipped config).
             if x_mask is not None or src_mask is not None:
@@ -550,6 +488,91 @@ class OnePosePlus_model(nn.Module):
         else:
             ops.linear_act(x, msg, L["mlp0"], h, B * lx, 1, 512, split)
             ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, B * lx, split, resid=x, out16=out)
+
+
+class OnePosePlus_model(_Engine):
+    def __init__(self, config, profiler=None, debug=False, precision=None):
+        """`precision` (extension; default from $OPP_B200_PRECISION or "fp16x3"):
+        "fp16x3" = 2-term fp16 split operands, three tcgen05 MMAs per K-step (fp32-grade, the
+        parity mode); "fp16" = single fp16 operands (fast, ~1e-2 deviations on high-gain inputs)."""
+        super().__init__()
+        self.config = config
+        self.profiler = profiler
+        self.debug = debug
+        self._init_engine(precision, config["loftr_coarse"]["attention"])
+        self.backbone = build_backbone(config["loftr_backbone"])
+        if config["positional_encoding"]["enable"]:
+            self.dense_pos_encoding = PositionEncodingSine(
+                config["loftr_coarse"]["d_model"],
+                max_shape=config["positional_encoding"]["pos_emb_shape"])
+        else:
+            self.dense_pos_encoding = None
+        if config["keypoints_encoding"]["enable"]:
+            if config["keypoints_encoding"]["type"] != "mlp_linear":
+                raise NotImplementedError
+            self.kpt_3d_pos_encoding = KeypointEncoding_linear(
+                inp_dim=3, feature_dim=config["keypoints_encoding"]["descriptor_dim"],
+                layers=config["keypoints_encoding"]["keypoints_encoder"],
+                norm_method=config["keypoints_encoding"]["norm_method"])
+        else:
+            raise NotImplementedError("keypoints_encoding.enable=False is not built")
+        self.loftr_coarse = LocalFeatureTransformer(config["loftr_coarse"])
+        self.coarse_matching = CoarseMatching(config["coarse_matching"], profiler=profiler)
+        self.fine_preprocess = FinePreprocess(config["loftr_fine"],
+                                              cf_res=config["loftr_backbone"]["resolution"])
+        self.loftr_fine = LocalFeatureTransformer(config["loftr_fine"])
+        self.fine_matching = FineMatching(config["fine_matching"])
+        if config["loftr_coarse"]["d_model"] != 256 or config["loftr_coarse"]["nhead"] != 8:
+            raise NotImplementedError("coarse kernels are built for d_model 256, 8 heads")
+        if config["loftr_fine"]["d_model"] != 128 or config["loftr_fine"]["nhead"] != 8:
+            raise NotImplementedError("fine kernels are built for d_model 128, 8 heads")
+        if config["loftr_fine"]["attention"] != "linear":
+            raise NotImplementedError("the fine-level kernels implement attention='linear' (every shipped "
+                                      "config); 'full' is built for the coarse transformer only")
+        if config["loftr_fine"]["window_size"] != 5:
+            raise NotImplementedError("fine kernels are built for window_size 5")
+        b = config["loftr_backbone"]["resnetfpn"]
+        if list(b["block_dims"]) != [128, 196, 256] or b["initial_dim"] != 128 \
+                or list(b["output_layers"]) != [3, 1]:
+            raise NotImplementedError("backbone kernels are built for dims 128/[128,196,256], outputs [3,1]")
+
+        self.loftr_backbone_pretrained = config["loftr_backbone"]["pretrained"]
+        if self.loftr_backbone_pretrained is not None:
+            # OnePosePlusModel.py:79-94: initialise the backbone from a LoFTR checkpoint
+            ckpt = torch.load(self.loftr_backbone_pretrained, "cpu")["state_dict"]
+            for k in list(ckpt.keys()):
+                if "backbone" in k:
+                    ckpt[k[k.find("backbone") + len("backbone") + 1:]] = ckpt[k]
+                ckpt.pop(k)
+            self.backbone.load_state_dict(ckpt)
+            if config["loftr_backbone"]["pretrained_fix"]:
+                for p in self.backbone.parameters():
+                    p.requires_grad = False
+        self._bank = None
+        self._fwd_count = 0
+        self.use_cuda_graphs = os.environ.get("OPP_B200_GRAPHS", "0") == "1"
+        # data["conf_matrix"]: "eager" = fp32 [B, N, S] written every forward (reference contract,
+        # coarse_matching.py:119; what the training loss reads); "lazy" = a LazyConfMatrix handle
+        # that materialises on demand (no inference consumer reads the matrix:
+        # inference_OnePosePlus_worker.py:20-31); "skip" = key not written.
+        self.conf_matrix_mode = os.environ.get("OPP_B200_CONF", "eager")
+        # one-pass dual softmax: column statistics of sim / conf from the row passes (warp
+        # butterflies in the epilogue) instead of two more sim GEMM passes
+        self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "1") == "1"
+        self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "1") == "1"
+
+    # pickling (Ray ships the module object): drop device-side caches
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_plan"], st["_plan_sig"], st["_ws"], st["_sig_tensors"] = None, None, {}, None
+        st["_bank"], st["_graphs"] = None, {}
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
+                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False)):
+            self.__dict__.setdefault(k, v)
 
     # ------------------------------------------------------------------ descriptor bank
     def _encode_bank(self, kpts, dcoarse, dfine, persistent):
@@ -863,12 +886,7 @@ class OnePosePlus_model(nn.Module):
         # kernels are enqueued on the current stream of the tensors' device
         with torch.no_grad(), torch.cuda.device(img.device):
             dev = img.device
-            sig = self._signature()
-            if self._plan is None or self._plan_sig != sig or self._plan["device"] != dev:
-                self._plan = self._prepare(dev)
-                self._plan["device"] = dev
-                self._plan_sig = sig
-                self._graphs = {}
+            self._ensure_plan(dev)
             if img.dtype != torch.uint8 and img.dtype != torch.float32:
                 img = img.float()
             img = img.contiguous()

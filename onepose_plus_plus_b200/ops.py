@@ -222,3 +222,31 @@ def fine_attention(qkv, msg, m, cross, split, eps=1e-6, count=None):
 def fine_match(x32, mkpts_c, b_ids, img_scale, expec_f, mkpts_f, m, fine_scale, count=None):
     call("opp_fine_match", ptr(x32), ptr(mkpts_c), ptr(b_ids), ptr(img_scale), ptr(expec_f),
          ptr(mkpts_f), m, float(fine_scale), ptr(count), stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# LoFTR 2D-2D matcher
+# ---------------------------------------------------------------------------------------------
+def match_select_2d(pt_val, pt_idx, colmax, scale0, scale1, batch, h0, w0, h1, w1, thr, border, cell, scratch,
+                    b_ids, i_ids, j_ids, mconf, mkpts0_c, mkpts1_c, count):
+    call("opp_match_select_2d", ptr(pt_val), ptr(pt_idx), ptr(colmax), ptr(scale0), ptr(scale1), batch, h0, w0, h1,
+         w1, float(thr), int(border), float(cell), ptr(scratch), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(mconf),
+         ptr(mkpts0_c), ptr(mkpts1_c), ptr(count), stream())
+
+
+def fine_gather_2d(fine0, fine1, b_ids, i_ids, j_ids, x16, m, hf0, wf0, wc0, hf1, wf1, wc1, stride, window, split):
+    _chk(fine0, torch.float16, "fine0")
+    _chk(fine1, torch.float16, "fine1")
+    call("opp_fine_gather_2d", ptr(fine0), ptr(fine1), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x16), m, hf0, wf0,
+         wc0, hf1, wf1, wc1, stride, window, int(split), stream())
+
+
+def seq_attention(q, kv, out, groups, l, s, split, eps=1e-6):
+    _chk(q, torch.float16, "q")
+    _chk(kv, torch.float16, "kv")
+    call("opp_seq_attention", ptr(q), ptr(kv), ptr(out), groups, l, s, float(eps), int(split), stream())
+
+
+def fine_match_2d(x32, mkpts1_c, b_ids, scale1, expec_f, mkpts1_f, m, window, fine_scale):
+    call("opp_fine_match_2d", ptr(x32), ptr(mkpts1_c), ptr(b_ids), ptr(scale1), ptr(expec_f), ptr(mkpts1_f), m,
+         window, float(fine_scale), stream())

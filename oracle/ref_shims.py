@@ -85,6 +85,43 @@ def install():
         prof.PassThroughProfiler = PassThroughProfiler
 
 
+def build_reference_loftr(state_dict, config, enable_fine_matching=True):
+    """Instantiate the reference LoFTR_for_OnePose_Plus (src/KeypointFreeSfM/loftr_for_sfm/loftr.py;
+    its modules come from submodules/LoFTR/src) and load `state_dict` strictly.  `yacs` is absent
+    from this image: a dict-with-attributes stand-in is enough for the two config modules."""
+    install()
+    if "yacs" not in sys.modules:
+        yacs = _module("yacs")
+        ycfg = _module("yacs.config")
+
+        class CfgNode(dict):
+            def __getattr__(self, k):
+                try:
+                    return self[k]
+                except KeyError as e:
+                    raise AttributeError(k) from e
+
+            def __setattr__(self, k, v):
+                self[k] = v
+
+        ycfg.CfgNode = CfgNode
+        yacs.config = ycfg
+    lsrc = os.path.join(REFERENCE_ROOT, "submodules", "LoFTR", "src")
+    if lsrc not in sys.path:
+        sys.path.insert(0, lsrc)
+    # the package __init__ files pull in ray / hydra: register bare package objects and import the
+    # one module file (loftr.py) underneath them
+    import importlib
+    for name in ("src.KeypointFreeSfM", "src.KeypointFreeSfM.loftr_for_sfm", "src.KeypointFreeSfM.loftr_for_sfm.utils"):
+        if name not in sys.modules:
+            pkg = _module(name)
+            pkg.__path__ = [os.path.join(REFERENCE_ROOT, *name.split("."))]
+    LoFTR_for_OnePose_Plus = importlib.import_module("src.KeypointFreeSfM.loftr_for_sfm.loftr").LoFTR_for_OnePose_Plus
+    model = LoFTR_for_OnePose_Plus(copy.deepcopy(config), enable_fine_matching=enable_fine_matching)
+    model.load_state_dict(state_dict, strict=True)
+    return model.eval()
+
+
 def build_reference_model(state_dict, config):
     """Instantiate the reference OnePosePlus_model and load `state_dict` with strict=True — which
     also proves that our checkpoint layout is the reference's."""

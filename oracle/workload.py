@@ -24,6 +24,73 @@ def _xavier(g, shape):
     return (torch.rand(shape, generator=g) * 2 - 1) * bound
 
 
+def synthetic_loftr_state_dict(seed=0, gain=1.0):
+    """Seeded weights with the layout of LoFTR_for_OnePose_Plus (loftr.py:24-33): the backbone keys
+    of the 2D-3D matcher, 8 coarse layers, 2 fine layers.  `gain` scales the last coarse layer's
+    norm2 affine: with default-init weights the coarse tokens of different cells are almost
+    parallel and no confidence passes the 0.2 threshold; a synthetic checkpoint may as well be a
+    contrasty one."""
+    sd = {k: v for k, v in synthetic_state_dict(seed).items()
+          if k.startswith("backbone.") or k.startswith("loftr_fine.")}
+    g = torch.Generator().manual_seed(seed + 4242)
+    for i in range(8):
+        q = f"loftr_coarse.layers.{i}."
+        for proj in ("q_proj", "k_proj", "v_proj", "merge"):
+            sd[q + proj + ".weight"] = _xavier(g, (256, 256))
+        sd[q + "mlp.0.weight"] = _xavier(g, (512, 512))
+        sd[q + "mlp.2.weight"] = _xavier(g, (256, 512))
+        for nrm in ("norm1", "norm2"):
+            sd[q + nrm + ".weight"] = 1.0 + 0.05 * torch.randn(256, generator=g)
+            sd[q + nrm + ".bias"] = 0.05 * torch.randn(256, generator=g)
+    sd["loftr_coarse.layers.7.norm2.weight"] *= gain
+    sd["loftr_coarse.layers.7.norm2.bias"] *= gain
+    return sd
+
+
+def loftr_pair(h=256, w=320, batch=1, shift=(16, 24), seed=1, noise=0.01, with_scale=False):
+    """Image pair for the 2D-2D matcher: image1 is image0 translated by `shift` pixels (multiples
+    of 8 keep the coarse cells aligned, the remainder gives sub-cell fine offsets) plus noise."""
+    g = torch.Generator().manual_seed(seed)
+    dy, dx = shift
+    big = torch.rand(batch, 1, h + abs(dy), w + abs(dx), generator=g)
+    im0 = big[:, :, :h, :w].contiguous()
+    im1 = (big[:, :, dy:dy + h, dx:dx + w] + noise * torch.randn(batch, 1, h, w, generator=g)).clamp(0, 1).contiguous()
+    data = {"image0": im0, "image1": im1}
+    if with_scale:
+        data["scale0"] = torch.tensor([[1.25, 0.8]]).expand(batch, -1).contiguous()
+        data["scale1"] = torch.tensor([[0.9, 1.1]]).expand(batch, -1).contiguous()
+    return data
+
+
+@torch.no_grad()
+def planted_loftr(h=256, w=320, batch=1, shift=(16, 24), seed=0, backbone_gain=4.0, layer_gain=0.3,
+                  with_scale=False, noise=0.01):
+    """Checkpoint + image pair on which the 2D-2D matcher finds hundreds of geometrically consistent
+    matches (i - j = the planted shift in coarse cells).  A default-init LoFTR collapses all coarse
+    tokens onto one direction, so the synthetic checkpoint is made contrasty: the coarse layers'
+    second LayerNorm is damped (`layer_gain`), the coarse backbone head amplified (`backbone_gain`),
+    and minus the mean final token is folded into the last layer's norm2.bias (the dual softmax is
+    only discriminative on centred tokens).  Returns (state_dict, data)."""
+    from . import loftr_oracle
+    data = loftr_pair(h, w, batch=batch, shift=shift, seed=seed + 1, noise=noise, with_scale=with_scale)
+    sd = synthetic_loftr_state_dict(seed)
+    for i in range(8):
+        sd[f"loftr_coarse.layers.{i}.norm2.weight"] *= layer_gain
+        sd[f"loftr_coarse.layers.{i}.norm2.bias"] *= layer_gain
+    sd["backbone.layer3_outconv.weight"] = sd["backbone.layer3_outconv.weight"] * backbone_gain
+    cfg = loftr_oracle.DEFAULT_CONFIG
+    fc, _ = oracle.backbone(sd, torch.cat([data["image0"], data["image1"]], 0))
+    pe = loftr_oracle.position_encoding(256, *fc.shape[2:], cfg["coarse"]["temp_bug_fix"])
+    t = (fc + pe[None]).flatten(2).transpose(1, 2)
+    t0, t1 = loftr_oracle.transformer(sd, "loftr_coarse.", cfg["coarse"], t[:batch], t[batch:])
+    sd["loftr_coarse.layers.7.norm2.bias"] = sd["loftr_coarse.layers.7.norm2.bias"] - torch.cat([t0, t1], 1).mean((0, 1))
+    # the amplified coarse head also flows down the FPN: bring the fine map back to unit scale, else
+    # the fine correlation logits reach ~1e4 and amplify fp32 rounding itself to 1e-2
+    _, ff = oracle.backbone(sd, data["image0"][:1])
+    sd["backbone.layer1_outconv2.3.weight"] = sd["backbone.layer1_outconv2.3.weight"] * (3.0 / ff.std())
+    return sd, data
+
+
 def synthetic_state_dict(seed=0, bn_perturb=True):
     """Seeded weights with the reference layout.  Initialisers follow the
     reference (kaiming fan_out convs resnet.py:126-131, xavier transformer transformer.py:128-131);

@@ -509,6 +509,101 @@ def check_full_attention():
                    *_tol(split, (2e-3, 2e-3), (2e-5, 2e-5)))
 
 
+# ------------------------------------------------------------------------------ LoFTR 2D-2D kernels
+def check_loftr_kernels():
+    """opp_seq_attention / opp_fine_gather_2d / opp_fine_match_2d / opp_match_select_2d against torch
+    restatements of submodules/LoFTR/src/loftr (linear_attention.py, fine_preprocess.py:41-49,
+    fine_matching.py:46-70, coarse_matching.py:9-28,197-253)."""
+    g = torch.Generator().manual_seed(3)
+    for split in (0, 1):
+        pl = 2 if split else 1
+        # linear attention between token groups
+        for (G, L, S) in [(37, 81, 81), (5, 25, 25), (3, 81, 30)]:
+            qf = _rand(G * L, 128, seed=1).abs() + 0.05
+            kvf = torch.cat([_rand(G * S, 128, seed=2).abs() + 0.05, _rand(G * S, 128, seed=3)], 1)
+            out = torch.full((G * L, pl * 128), float("nan"), device=DEV, dtype=torch.half)
+            ops.seq_attention(_planes(qf, split), _planes(kvf, split), out, G, L, S, split)
+            torch.cuda.synchronize()
+            Q = _q(qf, split).double().view(G, L, 8, 16)
+            K = _q(kvf[:, :128], split).double().view(G, S, 8, 16)
+            V = _q(kvf[:, 128:], split).double().view(G, S, 8, 16)
+            kvm = torch.einsum("nshd,nshv->nhdv", K, V / S)
+            z = 1 / (torch.einsum("nlhd,nhd->nlh", Q, K.sum(1)) + 1e-6)
+            ref = (torch.einsum("nlhd,nhdv,nlh->nlhv", Q, kvm, z) * S).reshape(G * L, 128).float()
+            _close(f"seq_attention split={split} G={G} L={L} S={S}", _unplanes(out, split), ref,
+                   *_tol(split, (2e-3, 1e-3), (2e-5, 2e-6)))
+        # W x W windows of both fine maps, sequence-major
+        B, hf, wf, wc, W, M = 2, 48, 64, 16, 9, 150
+        f0f, f1f = _rand(B, hf, wf, 128, seed=4), _rand(B, hf, wf, 128, seed=5)
+        b_ids = torch.randint(0, B, (M,), generator=g).sort().values.to(DEV)
+        i_ids = torch.randint(0, (hf // 4) * wc, (M,), generator=g).to(DEV)
+        j_ids = torch.randint(0, (hf // 4) * wc, (M,), generator=g).to(DEV)
+        x16 = torch.full((2 * M * W * W, pl * 128), float("nan"), device=DEV, dtype=torch.half)
+        ops.fine_gather_2d(_planes(f0f, split), _planes(f1f, split), b_ids, i_ids, j_ids, x16, M, hf, wf, wc, hf, wf,
+                           wc, 4, W, split)
+        torch.cuda.synchronize()
+
+        def unfold(f):
+            u = F.unfold(_q(f, split).permute(0, 3, 1, 2), kernel_size=W, stride=4, padding=W // 2)
+            return u.view(B, 128, W * W, -1).permute(0, 3, 2, 1)
+
+        ref = torch.cat([unfold(f0f)[b_ids, i_ids], unfold(f1f)[b_ids, j_ids]], 0).reshape(2 * M * W * W, 128)
+        _close(f"fine_gather_2d split={split}", _unplanes(x16, split), ref, *_tol(split, (1e-3, 1e-3), (1e-6, 1e-6)))
+    # fine matching, W = 9 and 5
+    for W in (9, 5):
+        M, B = 211, 2
+        WW = W * W
+        xf = _rand(2 * M * WW, 128, seed=6)
+        mk1c = torch.rand(M, 2, device=DEV) * 300
+        b_ids = torch.randint(0, B, (M,), generator=g).sort().values.to(DEV)
+        scale1 = torch.rand(B, 2, device=DEV) + 0.5
+        ef, mf = torch.empty(M, 3, device=DEV), torch.empty(M, 2, device=DEV)
+        ops.fine_match_2d(xf, mk1c, b_ids, scale1, ef, mf, M, W, 2.0)
+        torch.cuda.synchronize()
+        x = xf.view(2, M, WW, 128)
+        hm = torch.softmax(torch.einsum("mc,mrc->mr", x[0][:, WW // 2], x[1]) / math.sqrt(128), 1)
+        lin = torch.linspace(-1, 1, W, device=DEV)
+        grid = torch.stack([lin.repeat(W), lin.repeat_interleave(W)], 1)
+        co = hm @ grid
+        std = torch.sqrt((hm @ grid ** 2 - co ** 2).clamp(min=1e-10)).sum(-1)
+        _close(f"fine_match_2d W={W} expec_f", ef, torch.cat([co, std[:, None]], 1), 1e-4, 2e-5)
+        _close(f"fine_match_2d W={W} mkpts1_f", mf, mk1c + co * (W // 2) * (2.0 * scale1[b_ids]), 1e-5, 2e-4)
+    # match selection on two image grids
+    B, h0, w0, h1, w1 = 2, 12, 16, 10, 20
+    L, S = h0 * w0, h1 * w1
+    conf = torch.rand(B, L, S, device=DEV) * 0.3
+    idx = torch.randperm(L, generator=g)[:90]
+    conf[0, idx, torch.randperm(S, generator=g)[:90]] = 0.5 + 0.4 * torch.rand(90, device=DEV)
+    conf[1, idx[:60], torch.randperm(S, generator=g)[:60]] = 0.5 + 0.4 * torch.rand(60, device=DEV)
+    pt_val, pt_idx = conf.max(2)
+    colmax = conf.max(1).values.contiguous().view(torch.int32)
+    cap = B * L
+    outs = [torch.empty(cap, dtype=torch.int64, device=DEV) for _ in range(3)]
+    mconf, mk0, mk1 = torch.empty(cap, device=DEV), torch.empty(cap, 2, device=DEV), torch.empty(cap, 2, device=DEV)
+    cnt = torch.zeros(1, device=DEV, dtype=torch.int32)
+    s0, s1 = torch.rand(B, 2, device=DEV) + 0.5, torch.rand(B, 2, device=DEV) + 0.5
+    ops.match_select_2d(pt_val.contiguous(), pt_idx.int().contiguous(), colmax, s0, s1, B, h0, w0, h1, w1, 0.2, 2, 8.0,
+                        torch.empty((cap + 1023) // 1024 + 2, device=DEV, dtype=torch.int32), *outs, mconf, mk0, mk1, cnt)
+    torch.cuda.synchronize()
+    M = int(cnt.item())
+    mask = (conf > 0.2).view(B, h0, w0, h1, w1).clone()
+    for d in (1, 2, 3, 4):
+        sl = [slice(None)] * 5
+        sl[d] = slice(0, 2)
+        mask[tuple(sl)] = False
+        sl[d] = slice(-2, None)
+        mask[tuple(sl)] = False
+    mask = mask.view(B, L, S) * (conf == conf.max(2, keepdim=True)[0]) * (conf == conf.max(1, keepdim=True)[0])
+    mv, aj = mask.max(2)
+    rb, ri = torch.where(mv)
+    rj = aj[rb, ri]
+    assert M == len(rb) and M > 40, (M, len(rb))
+    assert torch.equal(outs[0][:M], rb) and torch.equal(outs[1][:M], ri) and torch.equal(outs[2][:M], rj)
+    assert torch.equal(mconf[:M], conf[rb, ri, rj])
+    _close("match_select_2d mkpts0_c", mk0[:M], torch.stack([ri % w0, ri // w0], 1) * 8.0 * s0[rb], 1e-6, 1e-4)
+    _close("match_select_2d mkpts1_c", mk1[:M], torch.stack([rj % w1, rj // w1], 1) * 8.0 * s1[rb], 1e-6, 1e-4)
+
+
 # ------------------------------------------------------------------------------ one-pass dual softmax
 def check_sim_colmax():
     for split in (0, 1):
@@ -610,6 +705,7 @@ CHECKS = {
     "match_select": check_match_select,
     "fine": check_fine,
     "full_attention": check_full_attention,
+    "loftr_kernels": check_loftr_kernels,
     "sim_colmax": check_sim_colmax,
     "sim_lse_cols": check_sim_lse_cols,
     "kv_single_plane": check_kv_single_plane,

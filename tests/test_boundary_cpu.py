@@ -86,3 +86,22 @@ def test_reference_lightning_module_builds_around_the_drop_in(tmp_path):
     module.eval()
     assert not module.matcher.training
     assert sum(p.numel() for p in module.parameters()) == 10_226_480
+
+
+def test_loftr_drop_in_has_the_reference_layout():
+    """LoFTR_for_OnePose_Plus: same ctor, same state-dict keys / shapes as the reference
+    class built from submodules/LoFTR/src/loftr (strict load both ways), non-persistent pos-enc buffer."""
+    from oracle import loftr_oracle
+    from onepose_plus_plus_b200 import LoFTR_for_OnePose_Plus
+    sd = workload.synthetic_loftr_state_dict(0)
+    ref = ref_shims.build_reference_loftr(sd, dict(loftr_oracle.DEFAULT_CONFIG))
+    ours = LoFTR_for_OnePose_Plus(dict(loftr_oracle.DEFAULT_CONFIG), enable_fine_matching=True)
+    rs, os_ = ref.state_dict(), ours.state_dict()
+    assert set(rs) == set(os_) and all(rs[k].shape == os_[k].shape for k in rs)
+    ours.load_state_dict(rs, strict=True)
+    ref.load_state_dict(ours.state_dict(), strict=True)
+    assert torch.equal(ours.pos_encoding.pe, ref.pos_encoding.pe) and "pos_encoding.pe" not in os_
+    clone = pickle.loads(pickle.dumps(ours.eval()))
+    assert all(torch.equal(clone.state_dict()[k], rs[k]) for k in rs)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        clone({"image0": torch.rand(1, 1, 64, 64), "image1": torch.rand(1, 1, 64, 64)})

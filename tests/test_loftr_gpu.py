@@ -1,0 +1,68 @@
+"""pytest -m gpu: the 2D-2D matcher (onepose_plus_plus_b200.LoFTR_for_OnePose_Plus)
+against oracle/loftr_oracle.py (pinned to the unmodified reference LoFTR_for_OnePose_Plus) on planted
+image pairs: coarse matches exact, confidences / fine offsets / coordinates within the matcher's
+tolerances."""
+import pytest
+import torch
+
+from oracle import loftr_oracle, workload
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(sd, data, **kw):
+    from onepose_plus_plus_b200 import LoFTR_for_OnePose_Plus
+    m = LoFTR_for_OnePose_Plus(loftr_oracle.DEFAULT_CONFIG, **kw)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().cuda()
+    d = {k: v.cuda() for k, v in data.items()}
+    m(d)
+    torch.cuda.synchronize()
+    return d, m
+
+
+@pytest.mark.parametrize("case", [(256, 320, 1, False), (192, 256, 3, True), (384, 512, 1, True)])
+def test_loftr_parity_vs_oracle(case):
+    h, w, batch, with_scale = case
+    sd, data = workload.planted_loftr(h, w, batch=batch, with_scale=with_scale)
+    ref = loftr_oracle.forward(sd, {k: v.clone() for k, v in data.items()})
+    got, _ = _run(sd, data)
+    assert (got["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+    trip = lambda d: list(zip(d["b_ids"].tolist(), d["i_ids"].tolist(), d["j_ids"].tolist()))  # noqa: E731
+    g_list, r_list = trip({k: got[k].cpu() for k in ("b_ids", "i_ids", "j_ids")}), trip(ref)
+    g_conf, r_conf = dict(zip(g_list, got["mconf"].cpu().tolist())), dict(zip(r_list, ref["mconf"].tolist()))
+    only = set(g_list) ^ set(r_list)
+    for t in only:   # a strict `>` on a float both sides compute to ~4e-4 is undecidable within 1e-3 of thr
+        assert abs(g_conf.get(t, r_conf.get(t)) - 0.2) <= parity.THR_MARGIN, f"{t} present in only one implementation"
+    print(case, "M", len(r_list), "borderline", len(only))
+    assert len(only) <= 1 and len(r_list) > 80 * batch and g_list == sorted(g_list)
+    common = [t for t in r_list if t in g_conf]
+    gi = torch.tensor([g_list.index(t) for t in common])
+    ri = torch.tensor([r_list.index(t) for t in common])
+    off = torch.tensor([t[1] - t[2] for t in common])
+    assert (off == 2 * (w // 8) + 3).float().mean().item() > 0.9            # the planted (16, 24) px shift
+    err = lambda k, cols=slice(None): (got[k].cpu()[gi][:, cols] - ref[k][ri][:, cols]).abs().max().item()  # noqa: E731
+    assert (got["mconf"].cpu()[gi] - ref["mconf"][ri]).abs().max().item() <= 1e-3
+    assert err("mkpts0_c") <= 1e-3 and err("mkpts1_c") <= 1e-3
+    e_xy, e_std, e_px = err("expec_f", slice(0, 2)), err("expec_f", slice(2, 3)), err("mkpts1_f")
+    print("expec", e_xy, "std", e_std, "mkpts1_f", e_px)
+    assert e_xy <= 1e-3 and e_std <= 5e-3 and e_px <= 1e-2
+    assert torch.equal(got["mkpts0_f"], got["mkpts0_c"]) and got["W"] == 9 and got["bs"] == batch
+    assert tuple(got["hw0_c"]) == (h // 8, w // 8) and tuple(got["hw1_f"]) == (h // 2, w // 2)
+
+
+def test_loftr_coarse_only_and_no_match_path():
+    sd, data = workload.planted_loftr(192, 256, batch=1)
+    got, m = _run(sd, data, enable_fine_matching=False)
+    assert torch.equal(got["mkpts1_f"], got["mkpts1_c"]) and "expec_f" not in got and got["b_ids"].numel() > 50
+    # an unrelated pair with a default-init checkpoint: no confidence passes the threshold
+    sd0 = workload.synthetic_loftr_state_dict(3)
+    pair = {"image0": torch.rand(1, 1, 128, 160), "image1": torch.rand(1, 1, 128, 160)}
+    ref = loftr_oracle.forward(sd0, {k: v.clone() for k, v in pair.items()})
+    got0, _ = _run(sd0, pair)
+    assert got0["b_ids"].numel() == len(ref["b_ids"]) == 0
+    assert got0["expec_f"].shape == (0, 3) and got0["mkpts1_f"].shape == (0, 2)
+    assert (got0["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() <= 1e-3
+    with pytest.raises(NotImplementedError):
+        m({**{k: v.cuda() for k, v in pair.items()}, "mask0": torch.ones(1, 16, 20).cuda()})

@@ -116,3 +116,29 @@ def test_pnp_oracle_recovers_planted_poses():
         assert ok and homo.shape == (4, 4) and 0.6 * m.sum() < len(inl) < 0.8 * m.sum()
         ref = pnp.refined(K[i], p2[m], p3[m], pose, inl)
         assert np.abs(ref - gt[i]).max() < 5e-3 and np.abs(ref - pose).max() < 2e-3
+
+
+@pytest.mark.skipif(not ref_shims.available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("case", [(192, 256, 2, False), (256, 320, 1, True)], ids=["b2", "b1_scaled"])
+def test_loftr_oracle_matches_reference_live(case):
+    """oracle/loftr_oracle.py against the unmodified LoFTR_for_OnePose_Plus
+    (src/KeypointFreeSfM/loftr_for_sfm/loftr.py + submodules/LoFTR/src/loftr) on a planted pair."""
+    from oracle import loftr_oracle
+    h, w, batch, with_scale = case
+    sd, data = workload.planted_loftr(h, w, batch=batch, with_scale=with_scale)
+    cfg = dict(loftr_oracle.DEFAULT_CONFIG)
+    ref = ref_shims.build_reference_loftr(sd, cfg)
+    d_ref = {k: v.clone() for k, v in data.items()}
+    with torch.no_grad():
+        ref(d_ref)
+    d_or = loftr_oracle.forward(sd, {k: v.clone() for k, v in data.items()}, cfg)
+    assert len(d_ref["b_ids"]) > 100 * batch
+    off = (d_ref["i_ids"] - d_ref["j_ids"])
+    assert (off == 2 * (w // 8) + 3).float().mean().item() > 0.9      # the planted (16, 24) px shift
+    for k in ("b_ids", "i_ids", "j_ids", "mkpts0_c", "mkpts1_c"):
+        assert torch.equal(d_ref[k], d_or[k]), k
+    assert torch.allclose(d_ref["conf_matrix"], d_or["conf_matrix"], atol=1e-4)
+    assert torch.allclose(d_ref["mconf"], d_or["mconf"], atol=1e-4)
+    assert torch.allclose(d_ref["expec_f"][:, :2], d_or["expec_f"][:, :2], atol=2e-4)
+    assert torch.allclose(d_ref["mkpts1_f"], d_or["mkpts1_f"], atol=2e-3) and torch.equal(d_ref["mkpts0_f"], d_or["mkpts0_f"])
+    assert d_ref["W"] == 9
