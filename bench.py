@@ -236,6 +236,32 @@ def bench_c5(model, sd, dev, workload, peaks, steps=5, batch=8):
     return res
 
 
+def bench_loftr(dev, workload, steps=5, batch=8):
+    """the 2D-2D matcher (LoFTR_for_OnePose_Plus) on the same engine — image pairs/s at
+    batch 8 of 512x512 pairs (= 16 backbone images, 8 coarse layers on 2 x 4096 tokens, 9x9 fine
+    windows), planted pair so that hundreds of matches reach the fine level."""
+    from onepose_plus_plus_b200 import LoFTR_for_OnePose_Plus
+    from oracle import loftr_oracle
+    sd, data = workload.planted_loftr(512, 512, batch=1)
+    m = LoFTR_for_OnePose_Plus(loftr_oracle.DEFAULT_CONFIG)
+    m.load_state_dict(sd, strict=True)
+    m = m.eval().to(dev)
+    g = torch.Generator().manual_seed(9)
+    im0 = (data["image0"] + 0.005 * torch.randn(batch, 1, 512, 512, generator=g)).clamp(0, 1).to(dev)
+    im1 = (data["image1"] + 0.005 * torch.randn(batch, 1, 512, 512, generator=g)).clamp(0, 1).to(dev)
+    out = {}
+
+    def step():
+        d = {"image0": im0, "image1": im1}
+        m(d)
+        out["d"] = d
+
+    ms = cuda_time(step, steps)
+    return {"workload": f"batch {batch} pairs of 512x512 images, fine window 9 (loftr_for_onepose_plus_cfg.py)",
+            "pairs_per_s": batch / ms * 1e3, "ms_per_step": ms,
+            "matches_per_pair": out["d"]["b_ids"].numel() / batch}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -452,7 +478,7 @@ def main():
     # with CUDA events around the backbone on the launching stream
     conv_ms = attn_ms = l1_ms = None
     S_tok = (H // 8) * (W // 8)
-    c5 = None
+    c5 = loftr = None
     if rank == 0:
         conv_ms = cuda_time(lambda: model._backbone(imgs_dev), 3)
         # the dominant kernel launch: layer1 3x3 conv 128->128 at 1/2 resolution (4 identical launches
@@ -479,6 +505,11 @@ def main():
                 c5 = bench_c5(model, sd, dev, workload, peaks)
             except Exception as e:  # noqa: BLE001
                 c5 = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+            try:
+                model.clear_workspace()
+                loftr = bench_loftr(dev, workload)
+            except Exception as e:  # noqa: BLE001
+                loftr = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -552,7 +583,7 @@ def main():
                 "frac_of_peak_algorithmic": attn_tf / peak_tf, "frac_of_peak_issued": attn_tf * passes / peak_tf,
                 "flops_per_image": "(4096 + 5000) tokens x 6 layers x 10*d^2 MAC + KV/QKV contractions = 72.6 GFLOP",
                 "tensor_pipe_pct_ncu": "sm__pipe_tensor_cycles_active per launch at this batch: profiles/r2_ncu_xfmr_b64.md"},
-            "configs": {"c5": c5},
+            "configs": {"c5": c5, "loftr_2d2d": loftr},
             "pose_stage": pose,
             "latency_b1": b1,
             "kernel_options": {"lib": os.path.basename(_lib.LIB_PATH),
