@@ -234,7 +234,7 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
 // Linear-attention source state   (loftr_module/linear_attention.py:55-57)
 // part[b][chunk][h][d][v] = sum_{s in chunk} K'[s,h,d] V[s,h,v];  row d = 32 holds sum_s K'[s,h,:]
 // =============================================================================================
-constexpr int kKvChunk = 128;   // tokens per CTA
+constexpr int kKvChunk = 256;   // tokens per CTA (128 -> 256: half the partial-state traffic of kv_finalize)
 
 // ---------------------------------------------------------------------------------------------
 // Per head the state is a 32x32 GEMM over the tokens of the chunk, KV[d][v] = sum_t K'[t][d] V[t][v]:

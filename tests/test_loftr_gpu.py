@@ -10,7 +10,6 @@ import pytest
 import torch
 
 from oracle import loftr_oracle, workload
-from tests import parity
 
 pytestmark = pytest.mark.gpu
 CONF_TOL = 5e-3
