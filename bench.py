@@ -276,6 +276,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # started now so that nvidia-smi is already streaming when the (short) timed region begins
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     peaks = {}
@@ -374,7 +376,6 @@ def main():
     for _ in range(max(args.warmup, 3)):
         d = step_resident()
     _lib.LAUNCHES = 0
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ms, d, t0, t1 = timed(step_resident, args.steps)
     clocks = sampler.stop(t0, t1) if sampler else None
     launches = _lib.LAUNCHES

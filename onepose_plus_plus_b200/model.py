@@ -549,6 +549,7 @@ class OnePosePlus_model(_Engine):
                 for p in self.backbone.parameters():
                     p.requires_grad = False
         self._bank = None
+        self._side_stream = None
         self._fwd_count = 0
         self.use_cuda_graphs = os.environ.get("OPP_B200_GRAPHS", "0") == "1"
         # data["conf_matrix"]: "eager" = fp32 [B, N, S] written every forward (reference contract,
@@ -565,13 +566,14 @@ class OnePosePlus_model(_Engine):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_plan"], st["_plan_sig"], st["_ws"], st["_sig_tensors"] = None, None, {}, None
-        st["_bank"], st["_graphs"] = None, {}
+        st["_bank"], st["_graphs"], st["_side_stream"] = None, {}, None
+        st.pop("_aux", None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
-                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False)):
+                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False), ("_side_stream", None)):
             self.__dict__.setdefault(k, v)
 
     # ------------------------------------------------------------------ descriptor bank
@@ -656,7 +658,8 @@ class OnePosePlus_model(_Engine):
         shared = bank["Bb"] == 1 and B > 1
         cur2, cur3 = q2, bank["d3_in"]
         first = 0
-        if shared and "d3_l0" in bank:
+        both = self._both
+        if "d3_l0" in bank:
             # layer 0 (self): 2D side only; layer 1 (cross): the 2D side reads the cached 3D source
             # state, the 3D side reads the shared 3D tokens in place (no per-image copies)
             L0, L1 = self._plan["coarse"][0], self._plan["coarse"][1]
@@ -667,8 +670,9 @@ class OnePosePlus_model(_Engine):
             ksum_b.copy_(bank["l1_ksum"].expand(B, -1))
             o2b = self._buf("q2_0", (B, S, pl * 256), f16, dev)
             o3 = self._buf("d3_0", (B, N, pl * 256), f16, dev)
-            self._encoder_layer(L1, "c2_", o2, None, B, S, N, o2b, state=(bank["l1_mt"], ksum_b), x_mask=qmask)
-            self._encoder_layer(L1, "c3_", d3, o2, B, N, S, o3, x_shared=True, src_mask=qmask)
+            both(lambda: self._encoder_layer(L1, "c2_", o2, None, B, S, N, o2b, state=(bank["l1_mt"], ksum_b),
+                                             x_mask=qmask),
+                 lambda: self._encoder_layer(L1, "c3_", d3, o2, B, N, S, o3, x_shared=True, src_mask=qmask))
             cur2, cur3 = o2b, o3
             first = 2
         elif shared:
@@ -680,12 +684,30 @@ class OnePosePlus_model(_Engine):
             o2 = self._buf(f"q2_{nxt}", (B, S, pl * 256), f16, dev)
             o3 = self._buf(f"d3_{nxt}", (B, N, pl * 256), f16, dev)
             self_layer = names[i] == "self"
-            self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
-                                S if self_layer else N, o2, x_mask=qmask, src_mask=qmask if self_layer else None)
-            self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
-                                N if self_layer else S, o3, src_mask=None if self_layer else qmask)
+            both(lambda: self._encoder_layer(L, "c2_", cur2, cur2 if self_layer else cur3, B, S,
+                                             S if self_layer else N, o2, x_mask=qmask,
+                                             src_mask=qmask if self_layer else None),
+                 lambda: self._encoder_layer(L, "c3_", cur3, cur3 if self_layer else cur2, B, N,
+                                             N if self_layer else S, o3, src_mask=None if self_layer else qmask))
             cur2, cur3 = o2, o3
         return cur2, cur3
+
+    def _both(self, f2, f3):
+        """The 2D-side and the 3D-side update of a layer are independent (cross layers read the
+        pre-update tensors, transformer.py:154-159).  At small batches each persistent GEMM fills a
+        fraction of the 148 SMs, so in latency (CUDA-graph) mode the two sides are enqueued on two
+        streams and run side by side; otherwise one after the other."""
+        side = self._side_stream
+        if side is None:
+            f2()
+            f3()
+            return
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            f3()
+        f2()
+        cur.wait_stream(side)
 
     def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None):
         """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch.
@@ -927,7 +949,13 @@ class OnePosePlus_model(_Engine):
             bank = self._encode_bank(kp.float().contiguous(), dco.float().contiguous(),
                                      dfine.float().contiguous(), persistent=False)
         N = bank["N"]
-        q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N, qmask)
+        # latency mode at small batch: both sides of every layer run concurrently (see _both)
+        small = B * (max(hc * wc, N) // 256 + 1) <= 37
+        self._side_stream = self._aux_stream(img.device) if (dynamic and small) else None
+        try:
+            q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N, qmask)
+        finally:
+            self._side_stream = None
         out = {}
         count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask)
         ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
@@ -942,6 +970,12 @@ class OnePosePlus_model(_Engine):
                 self._fine(fine_map, bank, ids, M, img_scale, hc, wc, (H, W), out)
             out["M"] = M
         return out, count, cap
+
+    def _aux_stream(self, dev):
+        st = getattr(self, "_aux", None)
+        if st is None or st.device != dev:
+            st = self._aux = torch.cuda.Stream(device=dev)
+        return st
 
     # ------------------------------------------------------------------ CUDA graphs
     def enable_cuda_graphs(self, on=True):
