@@ -33,14 +33,6 @@ int opp_version(void);
 const char* opp_last_error(void);
 int opp_num_sms(void);
 
-/* Process-wide integer switches (no reference counterpart: the reference picks its kernels inside
- * PyTorch): selection between alternative kernels behind one entry point while a new variant is
- * validated.  Current names:
- *   "gemm_w_resident": 1 = token GEMMs whose W tile fits keep it in shared memory across M tiles
- *                      (initial value: $OPP_GEMM_W_RESIDENT, else 0)
- * opp_set_option returns 0, or non-zero for an unknown name; opp_get_option returns the value or -1. */
-int opp_set_option(const char* name, int value);
-int opp_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------
  * Backbone — ResNetFPN_8_2.forward (backbone/resnet.py:141-164), BatchNorm folded on the host;

@@ -58,8 +58,7 @@ SIGNATURES = {
 }
 PLAIN = {"opp_version": ([], c_int), "opp_num_sms": ([], c_int), "opp_sim_tiles": ([I], c_int),
          "opp_kv_chunks": ([I], c_int),
-         "opp_last_error": ([], ctypes.c_char_p),
-         "opp_set_option": ([ctypes.c_char_p, I], c_int), "opp_get_option": ([ctypes.c_char_p], c_int)}
+         "opp_last_error": ([], ctypes.c_char_p)}
 
 
 def load():
@@ -80,16 +79,6 @@ def load():
         fn.restype = restype
     _lib = lib
     return lib
-
-
-def set_option(name, value):
-    """Process-wide kernel selection switch (include/opp_b200.h: opp_set_option)."""
-    if load().opp_set_option(name.encode(), int(value)) != 0:
-        raise ValueError(f"unknown libopp_b200 option {name!r}")
-
-
-def get_option(name):
-    return load().opp_get_option(name.encode())
 
 
 def ptr(t):

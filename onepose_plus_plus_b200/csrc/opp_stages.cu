@@ -1293,47 +1293,6 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
 
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
 
-// Process-wide integer switches (opp_set_option / opp_get_option): selection between alternative
-// kernels behind one entry point while a new variant is being validated.  Unknown names fail.
-struct OppOption {
-  const char* name;
-  const char* env;
-  int value;   // -1 = not read yet
-  int dflt;
-};
-static OppOption g_options[] = {
-    {"gemm_w_resident", "OPP_GEMM_W_RESIDENT", -1, 0},
-};
-static OppOption* find_option(const char* name) {
-  if (!name) return nullptr;
-  for (auto& o : g_options)
-    if (strcmp(o.name, name) == 0) return &o;
-  return nullptr;
-}
-namespace opp {
-int option_value(const char* name) {
-  OppOption* o = find_option(name);
-  if (!o) return -1;
-  if (o->value < 0) {
-    const char* e = getenv(o->env);
-    o->value = e ? atoi(e) : o->dflt;
-  }
-  return o->value;
-}
-}  // namespace opp
-
-int opp_set_option(const char* name, int value) {
-  OppOption* o = find_option(name);
-  if (!o) {
-    set_last_error("unknown option '%s'", name ? name : "(null)");
-    return OPP_ERR_INVALID;
-  }
-  o->value = value < 0 ? 0 : value;
-  return OPP_OK;
-}
-
-int opp_get_option(const char* name) { return opp::option_value(name); }
-
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");

@@ -39,19 +39,6 @@ def test_version_and_tiles_without_gpu():
     assert lib.opp_kv_chunks(4096) * 256 >= 4096
 
 
-def test_runtime_options_roundtrip():
-    """opp_set_option / opp_get_option (include/opp_b200.h): known names toggle, unknown names fail."""
-    for name in ("gemm_w_resident",):
-        before = _lib.get_option(name)
-        assert before in (0, 1)
-        _lib.set_option(name, 1 - before)
-        assert _lib.get_option(name) == 1 - before
-        _lib.set_option(name, before)
-    with pytest.raises(ValueError):
-        _lib.set_option("no_such_option", 1)
-    assert _lib.get_option("no_such_option") == -1
-
-
 def test_state_dict_is_the_reference_layout():
     m = OnePosePlus_model(oracle.DEFAULT_CONFIG)
     sd = workload.synthetic_state_dict(0)
