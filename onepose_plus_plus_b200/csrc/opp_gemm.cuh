@@ -190,6 +190,7 @@ constexpr int kWarpStageBytes = 32 * kStageRowH;   // 2560 B
 
 // fp16 planes: v = this lane's 32 values for global columns [gcol, gcol+32); nvalid = valid
 // columns of the chunk (multiple of 8).  Writes hi (and lo when lo_off != 0).
+template <bool kBatch = true>
 __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCtx& c, __half* out,
                                                  long long ld, int lo_off, int gcol,
                                                  const float* v, int nvalid) {
@@ -222,12 +223,28 @@ __device__ __forceinline__ void staged_store_h32(const GemmShape& s, const EpiCt
     }
     __syncwarp();
     const int seg = lane & 3;
+    // all four shared loads first, then the four global stores: paired LDS -> STG serialised ~45 clk of
+    // shared-memory latency per store (short-scoreboard stalls were 28 % of the epilogue warps' samples
+    // in the source-level ncu of the K = 256 GEMMs, which are epilogue-bound)
+    // (kBatch = false: the conv epilogues sit at the 168-register cap and are MMA-bound; the paired
+    // form there avoids spills)
+    if constexpr (kBatch) {
+      uint4 t4[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rr = (lane >> 2) + 8 * i;
-      if (((c.svalid >> i) & 1u) && seg * 8 < nvalid)
-        *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + plane * lo_off + gcol + seg * 8) =
-            lds128(st + rr * kStageRowH + seg * 16);
+      for (int i = 0; i < 4; ++i) t4[i] = lds128(st + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (((c.svalid >> i) & 1u) && seg * 8 < nvalid)
+          *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + plane * lo_off + gcol + seg * 8) = t4[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int rr = (lane >> 2) + 8 * i;
+        if (((c.svalid >> i) & 1u) && seg * 8 < nvalid)
+          *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + plane * lo_off + gcol + seg * 8) =
+              lds128(st + rr * kStageRowH + seg * 16);
+      }
     }
     __syncwarp();
   }
@@ -298,12 +315,13 @@ __device__ __forceinline__ void staged_store_f32(const EpiCtx& c, float* out, lo
              make_uint4(__float_as_uint(v[16 * half + 4 * g]), __float_as_uint(v[16 * half + 4 * g + 1]),
                         __float_as_uint(v[16 * half + 4 * g + 2]), __float_as_uint(v[16 * half + 4 * g + 3])));
     __syncwarp();
+    uint4 t4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) t4[i] = lds128(st + ((lane >> 2) + 8 * i) * kStageRowH + seg * 16);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int rr = (lane >> 2) + 8 * i;
       if (((c.svalid >> i) & 1u) && 16 * half + seg * 4 < nvalid)
-        *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + gcol + 16 * half + seg * 4) =
-            lds128(st + rr * kStageRowH + seg * 16);
+        *reinterpret_cast<uint4*>(out + c.sgrow[i] * ld + gcol + 16 * half + seg * 4) = t4[i];
     }
     __syncwarp();
   }
@@ -632,7 +650,7 @@ struct EpiConv {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
       }
-      if (p.out) staged_store_h32(s, c, p.out, p.ld, p.out_lo, g0, v, nvalid);
+      if (p.out) staged_store_h32<false>(s, c, p.out, p.ld, p.out_lo, g0, v, nvalid);
       if (p.tok) {
         if (c.valid) {
 #if OPP_PE_VEC
@@ -654,7 +672,7 @@ struct EpiConv {
             if (j < nvalid) v[j] += pe[j];
 #endif
         }
-        staged_store_h32(s, c, p.tok, p.ld, p.out_lo, g0, v, nvalid);
+        staged_store_h32<false>(s, c, p.tok, p.ld, p.out_lo, g0, v, nvalid);
       }
     });
   }
@@ -708,9 +726,10 @@ struct EpiConvUp {
     for (int o = c.group * 128; o < bytes; o += 128 * kGroups) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + o));
   }
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    epi_sync(c);
-    for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
-    epi_sync(c);
+    if (c.it == 0) {
+      for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
+      epi_sync(c);
+    }
     const int lane = threadIdx.x & 31;
     const int seg = lane & 3;
     // this lane's output pixel and its interpolation weights / neighbour slots
@@ -812,7 +831,7 @@ struct EpiConvUp {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
       }
-      staged_store_h32(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, c.ncols - col);
+      staged_store_h32<false>(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, c.ncols - col);
     }
   }
 };
