@@ -140,13 +140,15 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
   cfg.blockDim = dim3(gemm_threads(Epi::kGroups));
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = s.cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // see pdl_wait() in opp_common.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   void* kargs[5] = {(void*)&maps, (void*)&s, (void*)&ep, (void*)&rows_dev, (void*)&rows_mult};
   cudaError_t le = cudaLaunchKernelExC(&cfg, kern, kargs);
   if (le != cudaSuccess) {
@@ -206,11 +208,30 @@ static int pick_block_n(int n) {
   return 256;
 }
 
+// Latency shapes (batch 1-2: a GEMM has fewer super tiles than half the SMs, e.g. 16 CTA pairs
+// for 4096 tokens): halve the N tile, down to 64 columns, so that 2-4x as many SMs share the MMAs
+// and the epilogue of the same output.  A is re-read once per N tile — a few hundred KB from L2.
+// Call after pick_grouping() and before the W map is built.  $OPP_NSPLIT=0 disables it.
+static void split_n_for_latency(GemmShape& s) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("OPP_NSPLIT");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on) return;
+  const int max_clusters = num_sms() / s.cluster;
+  while (s.block_n >= 128 && s.block_n % 64 == 0 && s.n_total % (s.block_n / 2) == 0 &&
+         (long long)s.batches * s.msup * s.n_tiles * 2 <= max_clusters) {
+    s.block_n /= 2;
+    s.n_tiles = s.n_total / s.block_n;
+  }
+}
+
 // common shape / map setup for token-row GEMMs.  With split, every operand row holds two planes:
 // A_i rows are [hi(k_i) | lo(k_i)], W rows are [hi(k0+k1) | lo(k0+k1)].
 static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, const void* a1,
                       int k1, const void* w, int w_batched, int batches, long long rows, int n,
-                      int split, int n_align = 16, int a0_shared = 0) {
+                      int split, int n_align = 16, int a0_shared = 0, int nsplit_ok = 0) {
   OPP_REQUIRE(a0 && w, "null operand");
   OPP_REQUIRE(k0 > 0 && k0 % 64 == 0 && k1 % 64 == 0, "K (%d,%d) must be multiples of 64", k0,
               k1);
@@ -246,6 +267,7 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   maps.a[2] = maps.a[0];
   maps.a[3] = maps.a[0];
   pick_grouping(s);
+  if (nsplit_ok) split_n_for_latency(s);
   const long long kt = (long long)planes * (k0 + k1);
   return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt,
                   s.block_n / s.cluster);
@@ -270,7 +292,7 @@ int opp_linear_act_f16_b(const void* a0, int k0, int a0_shared, const void* a1, 
                          int split, const unsigned char* row_mask, opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, batches, rows, n, split, 16, a0_shared);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, batches, rows, n, split, 16, a0_shared, 1);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
@@ -288,7 +310,7 @@ int opp_linear_act_f16_out1(const void* a0, int k0, const void* a1, int k1, cons
                             opp_stream_t stream) {
   TensorMaps maps;
   GemmShape s;
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, 1);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, 0, 1, rows, n, 1, 16, 0, 1);
   if (rc) return rc;
   OPP_REQUIRE(out, "null output");
   OPP_REQUIRE(act_cols % 32 == 0, "act_cols=%d must be a multiple of 32", act_cols);
@@ -335,7 +357,7 @@ int opp_linear_q_f16(const void* x, const void* wq, const float* ksum, void* out
   GemmShape s;
   OPP_REQUIRE(d_model == 256, "opp_linear_q_f16 supports d_model 256 (8 heads x 32), got %d",
               d_model);
-  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model, split, 16, x_shared);
+  int rc = setup_rows(maps, s, x, d_model, nullptr, 0, wq, 0, batches, rows, d_model, split, 16, x_shared, 1);
   if (rc) return rc;
   OPP_REQUIRE(ksum && out, "null pointer");
   EpiQ::Params ep{(__half*)out, (long long)d_model * (split ? 2 : 1), split ? d_model : 0, ksum,
@@ -424,6 +446,7 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   s.b_lo = (int)kplane;
   const long long kt = kplane * planes;
   pick_grouping(s);
+  split_n_for_latency(s);   // the 1/8-resolution layers at batch 1: 16 CTA pairs -> 64
   rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n / s.cluster);
   if (rc) return rc;
   OPP_REQUIRE(!up || (out_h % 2 == 0 && out_w % 2 == 0 && out_h >= 4 && out_w >= 4),

@@ -1177,6 +1177,10 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
   if (csize > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above overlapped with the previous kernel's tail;
+  // from here on we read what it wrote.  Our own successor may be scheduled right away (it parks
+  // in its prologue until this grid has completed).
+  pdl_sync();
 
   // Producer and MMA warps run their loops warp-uniformly (all 32 lanes evaluate the same
   // addresses, coordinates and descriptors, so they live in uniform registers) and only the
@@ -1438,6 +1442,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
     }
   }
 
+  pdl_done();
   tc_fence_before();
   // a CTA must outlive every multicast write / remote barrier arrival aimed at it
   if (csize > 1) cluster_sync_all(); else __syncthreads();
@@ -1461,6 +1466,7 @@ __global__ void __launch_bounds__(gemm_threads(Epi::kGroups), 1)
 gemm_kernel_dyn(const __grid_constant__ TensorMaps maps, const GemmShape s_in,
                 const typename Epi::Params ep, const int* rows_dev, int rows_mult) {
   GemmShape s = s_in;
+  pdl_wait();   // rows_dev is written by the previous kernels of the stream
   const int r = *rows_dev * rows_mult;
   s.rows = r < s_in.rows ? r : s_in.rows;
   s.m_tiles = (s.rows + kBlockM - 1) / kBlockM;

@@ -244,6 +244,7 @@ pnp_ransac_kernel(const float* __restrict__ pts3d, const float* __restrict__ pts
                   float scale, float thr, int n_hyp, unsigned seed, int refine_rounds,
                   float* __restrict__ pose_out, int* __restrict__ n_inl_out,
                   unsigned char* __restrict__ inl_mask, int* __restrict__ status_out) {
+  pdl_sync();
   __shared__ int seg[2];
   __shared__ unsigned long long best_key[kPnpThreads / 32];
   __shared__ Pose best_pose;
@@ -521,9 +522,9 @@ extern "C" int opp_pnp_ransac(const float* pts3d, const float* pts2d, const long
   OPP_REQUIRE(m == 0 || (pts3d && pts2d && m_bids && inlier_mask), "null match lists");
   OPP_REQUIRE(batch > 0 && hypotheses > 0 && scale > 0.f && reproj_thr > 0.f && refine_rounds >= 0,
               "bad pnp arguments");
-  pnp_ransac_kernel<<<batch, kPnpThreads, 0, (cudaStream_t)stream>>>(
+  OPP_CHECK_CUDA(opp::launch_pdl(pnp_ransac_kernel, dim3(batch), dim3(kPnpThreads), 0, (cudaStream_t)stream, 
       pts3d, pts2d, m_bids, m, intrinsics, scale, reproj_thr, hypotheses, seed, refine_rounds, poses,
-      n_inliers, inlier_mask, status);
+      n_inliers, inlier_mask, status));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -29,6 +29,7 @@ template <bool IMG_U8>
 __global__ void __launch_bounds__(256) conv1_im2col_kernel(const void* __restrict__ img_v,
                                                            __half* __restrict__ a_out, int H, int W,
                                                            int lo_off) {
+  pdl_sync();
   constexpr int P = 2 * kC1Tile + 5;   // 37 x 37 input patch of a 16 x 16 output tile
   __shared__ float p_s[P * P];
   const int b = blockIdx.z;
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(256) conv1_im2col_kernel(const void* __restric
 // =============================================================================================
 __global__ void __launch_bounds__(256) kpt_stats_kernel(const float* __restrict__ kpts,
                                                         float* __restrict__ stats, int n) {
+  pdl_sync();
   __shared__ float red[9][256];
   const int b = blockIdx.x;
   const float* k0 = kpts;                        // batch element 0 for the extents
@@ -174,6 +176,7 @@ kpt_encode_kernel(const float* __restrict__ kpts, const float* __restrict__ stat
                   const float* __restrict__ b2, const float* __restrict__ w3_t,
                   const float* __restrict__ b3, const float* __restrict__ w4_t,
                   const float* __restrict__ b4, __half* __restrict__ tok, int n, int lo_off) {
+  pdl_sync();
   __shared__ float buf_a[kKeP * 129];   // holds [P][3], [P][64+1] ... reused
   __shared__ float buf_b[kKeP * 257];
   const int b = blockIdx.y;
@@ -281,6 +284,7 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const __half* __restrict__ kv16,
                                                              float* __restrict__ part, int S) {
+  pdl_sync();
   extern __shared__ __align__(16) uint8_t kvm_smem[];
   constexpr int kRowB = SPLIT ? 2048 : 1024;      // [K'(256) V(256)] fp16, x2 planes when split
   constexpr int kStride = kRowB + 16;
@@ -391,6 +395,7 @@ __global__ void __launch_bounds__(1024) kv_finalize_kernel(const float* __restri
                                                           __half* __restrict__ mt,
                                                           float* __restrict__ ksum, int chunks,
                                                           int d, float inv_vlen, int lo_off) {
+  pdl_sync();
   __shared__ float kv_s[33][33];
   const int h = blockIdx.x, b = blockIdx.y, H = gridDim.x;
   // chunk partials are 33.8 KB apart: keep 8 loads in flight per element (a plain loop serialised
@@ -441,6 +446,7 @@ __global__ void __launch_bounds__(1024) kv_finalize_kernel(const float* __restri
 // =============================================================================================
 __global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* __restrict__ ps,
                                     float* __restrict__ lse, long long rows, int tiles) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float m = -INFINITY;
@@ -459,6 +465,7 @@ __global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __re
                                                                float* __restrict__ lse, int batches,
                                                                int groups, int cols,
                                                                const unsigned char* __restrict__ col_mask) {
+  pdl_sync();
   __shared__ float m_s[8][32], s_s[8][32];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
@@ -504,6 +511,7 @@ __global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __re
 __global__ void best_finalize_kernel(const float* __restrict__ pv, const int* __restrict__ pi,
                                      float* __restrict__ bv, int* __restrict__ bi, long long rows,
                                      int tiles) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= rows) return;
   float best = pv[r * tiles];
@@ -560,6 +568,7 @@ __global__ void __launch_bounds__(1024) match_count_colmax_kernel(const float* p
                                                                   long long rows, int l, int s, int wc,
                                                                   float thr, int border,
                                                                   int* block_counts) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag_colmax(pt_val, pt_idx, colmax, r, l, s, wc, thr, border);
   const int c = __syncthreads_count(f);
@@ -570,6 +579,7 @@ __global__ void __launch_bounds__(1024) match_count_kernel(const float* pt_val, 
                                                            const int* px_idx, long long rows,
                                                            int l, int s, int wc, float thr,
                                                            int border, int* block_counts) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
   const int c = __syncthreads_count(f);
@@ -579,6 +589,7 @@ __global__ void __launch_bounds__(1024) match_count_kernel(const float* pt_val, 
 // single block: exclusive scan of block_counts in place; total -> counts[nblocks] and count_out
 __global__ void __launch_bounds__(1024) match_scan_kernel(int* counts, int nblocks,
                                                           int* count_out) {
+  pdl_sync();
   __shared__ int warp_sums[32];
   __shared__ int carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -623,6 +634,7 @@ match_scatter_kernel(const float* pt_val, const int* pt_idx, const int* px_idx, 
                      int border, float cell, const int* block_offsets, long long* b_ids,
                      long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
                      float* mkpts_c, int kpts_shared) {
+  pdl_sync();
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
@@ -670,6 +682,7 @@ match_scatter_colmax_kernel(const float* pt_val, const int* pt_idx, const unsign
                      int border, float cell, const int* block_offsets, long long* b_ids,
                      long long* i_ids, long long* j_ids, float* mconf, float* mkpts3d,
                      float* mkpts_c, int kpts_shared) {
+  pdl_sync();
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag_colmax(pt_val, pt_idx, px_idx, r, l, s, wc, thr, border);
@@ -719,6 +732,7 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
     const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
     int wf, int wc, int stride, int n, int lo_off, int desc_shared, const int* __restrict__ count_dev) {
+  pdl_sync();
   const int m = blockIdx.x, c = threadIdx.x;
   if (count_dev && m >= *count_dev) return;   // launched at capacity, match count on the device
   const long long b = b_ids[m], i = i_ids[m], j = j_ids[m];
@@ -747,6 +761,7 @@ __global__ void __launch_bounds__(128) fine_attention_kernel(const __half* __res
                                                              float eps, int lo_off_in,
                                                              int lo_off_out,
                                                              const int* __restrict__ count_dev) {
+  pdl_sync();
   if (count_dev && (int)blockIdx.x >= *count_dev) return;
   // ncu (batch 64, 24 k matches): the first version was bound by shared-memory instructions — 32-bit
   // loads of values every lane of a head shares, and the per-head state re-read from shared memory
@@ -859,6 +874,7 @@ __global__ void __launch_bounds__(128) full_attention_kernel(const __half* __res
                                                              const __half* __restrict__ kv,
                                                              __half* __restrict__ out, int L, int S,
                                                              int heads, int lo_q, int lo_kv) {
+  pdl_sync();
   __shared__ __align__(16) float k_s[kFaKeys][D];
   __shared__ __align__(16) float v_s[kFaKeys][D];
   const int b = blockIdx.z, h = blockIdx.y;
@@ -923,6 +939,7 @@ __global__ void __launch_bounds__(128) fine_match_kernel(
     const long long* __restrict__ b_ids, const float* __restrict__ img_scale,
     float* __restrict__ expec_f, float* __restrict__ mkpts_f, int M, float fine_scale,
     const int* __restrict__ count_dev) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
   if (m >= M || (count_dev && m >= *count_dev)) return;
@@ -1003,6 +1020,7 @@ __global__ void __launch_bounds__(1024) match_count_2d_kernel(const float* pt_va
                                                               int l, int s, int h0, int w0, int h1,
                                                               int w1, float thr, int border,
                                                               int* block_counts) {
+  pdl_sync();
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag_2d(pt_val, pt_idx, colmax, r, l, s, h0, w0, h1, w1, thr, border);
   const int c = __syncthreads_count(f);
@@ -1015,6 +1033,7 @@ match_scatter_2d_kernel(const float* pt_val, const int* pt_idx, const unsigned* 
                         int w0, int h1, int w1, float thr, int border, float cell,
                         const int* block_offsets, long long* b_ids, long long* i_ids, long long* j_ids,
                         float* mconf, float* mk0, float* mk1) {
+  pdl_sync();
   __shared__ int warp_sums[32];
   const long long r = (long long)blockIdx.x * 1024 + threadIdx.x;
   const bool f = r < rows && match_flag_2d(pt_val, pt_idx, colmax, r, l, s, h0, w0, h1, w1, thr, border);
@@ -1057,6 +1076,7 @@ __global__ void __launch_bounds__(128) fine_gather_2d_kernel(
     const __half* __restrict__ f0, const __half* __restrict__ f1, const long long* __restrict__ b_ids,
     const long long* __restrict__ i_ids, const long long* __restrict__ j_ids, __half* __restrict__ x16,
     int M, int hf0, int wf0, int wc0, int hf1, int wf1, int wc1, int stride, int W, int lo_off) {
+  pdl_sync();
   const int m = blockIdx.x, seq = blockIdx.y, c = threadIdx.x;
   const long long b = b_ids[m];
   const long long cell = seq ? j_ids[m] : i_ids[m];
@@ -1082,6 +1102,7 @@ __global__ void __launch_bounds__(128) seq_attention_kernel(const __half* __rest
                                                             const __half* __restrict__ kv,
                                                             __half* __restrict__ out, int L, int S,
                                                             float eps, int lo_q, int lo_kv) {
+  pdl_sync();
   __shared__ __align__(16) float a_s[kSaSlab][128];
   __shared__ __align__(16) float b_s[kSaSlab][128];
   __shared__ __align__(16) float ks2[128];
@@ -1181,6 +1202,7 @@ __global__ void __launch_bounds__(128) fine_match_2d_kernel(
     const float* __restrict__ x32, const float* __restrict__ mk1c, const long long* __restrict__ b_ids,
     const float* __restrict__ scale1, float* __restrict__ expec_f, float* __restrict__ mk1f, int M, int W,
     float fine_scale) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m = blockIdx.x * 4 + warp;
   if (m >= M) return;
@@ -1264,16 +1286,16 @@ int opp_conv1_im2col(const void* image, int image_u8, void* a_out, int batch, in
   OPP_REQUIRE(h % 2 == 0 && w % 2 == 0 && batch > 0, "bad conv1 shape");
   dim3 grid((w / 2 + kC1Tile - 1) / kC1Tile, (h / 2 + kC1Tile - 1) / kC1Tile, batch);
   if (image_u8)
-    conv1_im2col_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
+    OPP_CHECK_CUDA(opp::launch_pdl(conv1_im2col_kernel<true>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, image, (__half*)a_out, h, w, split ? 64 : 0));
   else
-    conv1_im2col_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(image, (__half*)a_out, h, w, split ? 64 : 0);
+    OPP_CHECK_CUDA(opp::launch_pdl(conv1_im2col_kernel<false>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, image, (__half*)a_out, h, w, split ? 64 : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
 
 int opp_kpt_stats(const float* kpts, float* stats, int batch, int n, opp_stream_t stream) {
   OPP_REQUIRE(kpts && stats && batch > 0 && n > 0, "bad kpt_stats arguments");
-  kpt_stats_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(kpts, stats, n);
+  OPP_CHECK_CUDA(opp::launch_pdl(kpt_stats_kernel, dim3(batch), dim3(256), 0, (cudaStream_t)stream, kpts, stats, n));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1284,9 +1306,9 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
                    int split, opp_stream_t stream) {
   OPP_REQUIRE(kpts && stats && desc && tok, "null pointer");
   dim3 grid((n + kKeP - 1) / kKeP, batch);
-  kpt_encode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(kpts, stats, desc, w1_t, b1, w2_t, b2,
+  OPP_CHECK_CUDA(opp::launch_pdl(kpt_encode_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, kpts, stats, desc, w1_t, b1, w2_t, b2,
                                                             w3_t, b3, w4_t, b4, (__half*)tok, n,
-                                                            split ? 256 : 0);
+                                                            split ? 256 : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1310,9 +1332,9 @@ int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int s
     attr_done |= 1ull << dev;
   }
   if (split)
-    kv_partial_mma_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16, part, s);
+    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<true>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s));
   else
-    kv_partial_mma_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>((const __half*)kv16, part, s);
+    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1322,9 +1344,9 @@ int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ks
   OPP_REQUIRE(part && merge_w && mt && ksum, "null pointer");
   OPP_REQUIRE(d % 32 == 0 && d <= 256, "d=%d must be a multiple of the head size 32, <= 256", d);
   dim3 grid(d / 32, batch);
-  kv_finalize_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(part, merge_w, (__half*)mt, ksum,
+  OPP_CHECK_CUDA(opp::launch_pdl(kv_finalize_kernel, dim3(grid), dim3(1024), 0, (cudaStream_t)stream, part, merge_w, (__half*)mt, ksum,
                                                              chunks, d, 1.f / v_len,
-                                                             split ? d : 0);
+                                                             split ? d : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1332,8 +1354,8 @@ int opp_kv_finalize(const float* part, const float* merge_w, void* mt, float* ks
 int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long long rows,
                      int tiles, opp_stream_t stream) {
   OPP_REQUIRE(part_m && part_s && lse, "null pointer");
-  lse_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      part_m, part_s, lse, rows, tiles);
+  OPP_CHECK_CUDA(opp::launch_pdl(lse_finalize_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      part_m, part_s, lse, rows, tiles));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1341,8 +1363,8 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
 int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
                          int cols, const unsigned char* col_mask, opp_stream_t stream) {
   OPP_REQUIRE(col_m && col_s && lse && batches > 0 && groups > 0 && cols > 0, "bad lse_col_finalize arguments");
-  lse_col_finalize_kernel<<<dim3((cols + 31) / 32, batches), 256, 0, (cudaStream_t)stream>>>(
-      col_m, col_s, lse, batches, groups, cols, col_mask);
+  OPP_CHECK_CUDA(opp::launch_pdl(lse_col_finalize_kernel, dim3(dim3((cols + 31) / 32, batches)), dim3(256), 0, (cudaStream_t)stream, 
+      col_m, col_s, lse, batches, groups, cols, col_mask));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1350,8 +1372,8 @@ int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int
 int opp_best_finalize(const float* part_val, const int* part_idx, float* best_val, int* best_idx,
                       long long rows, int tiles, opp_stream_t stream) {
   OPP_REQUIRE(part_val && part_idx && best_val && best_idx, "null pointer");
-  best_finalize_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      part_val, part_idx, best_val, best_idx, rows, tiles);
+  OPP_CHECK_CUDA(opp::launch_pdl(best_finalize_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+      part_val, part_idx, best_val, best_idx, rows, tiles));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1366,12 +1388,12 @@ int opp_match_select(const float* pt_val, const int* pt_idx, const int* px_idx, 
   const int nblocks = (int)((rows + 1023) / 1024);
   const int s = hc * wc;
   cudaStream_t st = (cudaStream_t)stream;
-  match_count_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, rows, l, s, wc, thr, border,
-                                               scratch);
-  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
-  match_scatter_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, px_idx, kpts, img_scale, rows, l,
+  OPP_CHECK_CUDA(opp::launch_pdl(match_count_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, px_idx, rows, l, s, wc, thr, border,
+                                               scratch));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scan_kernel, dim3(1), dim3(1024), 0, st, scratch, nblocks, count_out));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scatter_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, px_idx, kpts, img_scale, rows, l,
                                                  s, wc, thr, border, cell, scratch, b_ids, i_ids,
-                                                 j_ids, mconf, mkpts3d, mkpts_c, bank_shared);
+                                                 j_ids, mconf, mkpts3d, mkpts_c, bank_shared));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1387,12 +1409,12 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
   const int nblocks = (int)((rows + 1023) / 1024);
   const int s = hc * wc;
   cudaStream_t st = (cudaStream_t)stream;
-  match_count_colmax_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, rows, l, s, wc, thr,
-                                                      border, scratch);
-  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
-  match_scatter_colmax_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, kpts, img_scale, rows,
+  OPP_CHECK_CUDA(opp::launch_pdl(match_count_colmax_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, colmax, rows, l, s, wc, thr,
+                                                      border, scratch));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scan_kernel, dim3(1), dim3(1024), 0, st, scratch, nblocks, count_out));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scatter_colmax_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, colmax, kpts, img_scale, rows,
                                                         l, s, wc, thr, border, cell, scratch, b_ids,
-                                                        i_ids, j_ids, mconf, mkpts3d, mkpts_c, bank_shared);
+                                                        i_ids, j_ids, mconf, mkpts3d, mkpts_c, bank_shared));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1403,10 +1425,10 @@ int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_id
                     const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x16, "null pointer");
-  fine_gather_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)fine, desc3d, b_ids,
+  OPP_CHECK_CUDA(opp::launch_pdl(fine_gather_kernel, dim3(m), dim3(128), 0, (cudaStream_t)stream, (const __half*)fine, desc3d, b_ids,
                                                           i_ids, j_ids, x32, (__half*)x16, hf, wf,
                                                           wc, stride, n, split ? 128 : 0, bank_shared,
-                                                          count_dev);
+                                                          count_dev));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1415,8 +1437,8 @@ int opp_fine_attention(const void* qkv, void* msg, int m, int cross, float eps, 
                        const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(qkv && msg, "null pointer");
-  fine_attention_kernel<<<m, 128, 0, (cudaStream_t)stream>>>((const __half*)qkv, (__half*)msg, cross, eps,
-                                                             split ? 384 : 0, split ? 128 : 0, count_dev);
+  OPP_CHECK_CUDA(opp::launch_pdl(fine_attention_kernel, dim3(m), dim3(128), 0, (cudaStream_t)stream, (const __half*)qkv, (__half*)msg, cross, eps,
+                                                             split ? 384 : 0, split ? 128 : 0, count_dev));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1429,13 +1451,13 @@ int opp_full_attention(const void* q, const void* kv, void* out, int batch, int 
   dim3 grid((l + 127) / 128, heads, batch);
   const int dm = heads * head_dim;
   if (head_dim == 32)
-    full_attention_kernel<32><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+    OPP_CHECK_CUDA(opp::launch_pdl(full_attention_kernel<32>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const __half*)q, (const __half*)kv,
                                                                      (__half*)out, l, s, heads, split ? dm : 0,
-                                                                     split ? 2 * dm : 0);
+                                                                     split ? 2 * dm : 0));
   else
-    full_attention_kernel<16><<<grid, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+    OPP_CHECK_CUDA(opp::launch_pdl(full_attention_kernel<16>, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const __half*)q, (const __half*)kv,
                                                                      (__half*)out, l, s, heads, split ? dm : 0,
-                                                                     split ? 2 * dm : 0);
+                                                                     split ? 2 * dm : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1445,8 +1467,8 @@ int opp_fine_match(const float* x32, const float* mkpts_c, const long long* b_id
                    const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(x32 && mkpts_c && b_ids && expec_f && mkpts_f, "null pointer");
-  fine_match_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts_c, b_ids, img_scale,
-                                                                   expec_f, mkpts_f, m, fine_scale, count_dev);
+  OPP_CHECK_CUDA(opp::launch_pdl(fine_match_kernel, dim3((m + 3) / 4), dim3(128), 0, (cudaStream_t)stream, x32, mkpts_c, b_ids, img_scale,
+                                                                   expec_f, mkpts_f, m, fine_scale, count_dev));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1461,12 +1483,12 @@ int opp_match_select_2d(const float* pt_val, const int* pt_idx, const unsigned* 
   const long long rows = (long long)batch * l;
   const int nblocks = (int)((rows + 1023) / 1024);
   cudaStream_t st = (cudaStream_t)stream;
-  match_count_2d_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, rows, l, s, h0, w0, h1, w1, thr,
-                                                  border, scratch);
-  match_scan_kernel<<<1, 1024, 0, st>>>(scratch, nblocks, count_out);
-  match_scatter_2d_kernel<<<nblocks, 1024, 0, st>>>(pt_val, pt_idx, colmax, scale0, scale1, rows, l, s, h0, w0,
+  OPP_CHECK_CUDA(opp::launch_pdl(match_count_2d_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, colmax, rows, l, s, h0, w0, h1, w1, thr,
+                                                  border, scratch));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scan_kernel, dim3(1), dim3(1024), 0, st, scratch, nblocks, count_out));
+  OPP_CHECK_CUDA(opp::launch_pdl(match_scatter_2d_kernel, dim3(nblocks), dim3(1024), 0, st, pt_val, pt_idx, colmax, scale0, scale1, rows, l, s, h0, w0,
                                                     h1, w1, thr, border, cell, scratch, b_ids, i_ids, j_ids,
-                                                    mconf, mkpts0_c, mkpts1_c);
+                                                    mconf, mkpts0_c, mkpts1_c));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1477,9 +1499,9 @@ int opp_fine_gather_2d(const void* fine0, const void* fine1, const long long* b_
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(fine0 && fine1 && b_ids && i_ids && j_ids && x16, "null pointer");
   OPP_REQUIRE(window % 2 == 1 && window >= 1 && window <= 9, "window %d unsupported (odd, <= 9)", window);
-  fine_gather_2d_kernel<<<dim3(m, 2), 128, 0, (cudaStream_t)stream>>>(
+  OPP_CHECK_CUDA(opp::launch_pdl(fine_gather_2d_kernel, dim3(dim3(m, 2)), dim3(128), 0, (cudaStream_t)stream, 
       (const __half*)fine0, (const __half*)fine1, b_ids, i_ids, j_ids, (__half*)x16, m, hf0, wf0, wc0, hf1, wf1,
-      wc1, stride, window, split ? 128 : 0);
+      wc1, stride, window, split ? 128 : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1488,9 +1510,9 @@ int opp_seq_attention(const void* q, const void* kv, void* out, int groups, int 
                       opp_stream_t stream) {
   if (groups == 0) return OPP_OK;
   OPP_REQUIRE(q && kv && out && l > 0 && s > 0, "bad seq_attention arguments");
-  seq_attention_kernel<<<groups, 128, 0, (cudaStream_t)stream>>>((const __half*)q, (const __half*)kv,
+  OPP_CHECK_CUDA(opp::launch_pdl(seq_attention_kernel, dim3(groups), dim3(128), 0, (cudaStream_t)stream, (const __half*)q, (const __half*)kv,
                                                                  (__half*)out, l, s, eps, split ? 128 : 0,
-                                                                 split ? 256 : 0);
+                                                                 split ? 256 : 0));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1501,8 +1523,8 @@ int opp_fine_match_2d(const float* x32, const float* mkpts1_c, const long long* 
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(x32 && mkpts1_c && b_ids && expec_f && mkpts1_f, "null pointer");
   OPP_REQUIRE(window % 2 == 1 && window >= 3 && window <= 9, "window %d unsupported (odd, 3..9)", window);
-  fine_match_2d_kernel<<<(m + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x32, mkpts1_c, b_ids, scale1, expec_f,
-                                                                      mkpts1_f, m, window, fine_scale);
+  OPP_CHECK_CUDA(opp::launch_pdl(fine_match_2d_kernel, dim3((m + 3) / 4), dim3(128), 0, (cudaStream_t)stream, x32, mkpts1_c, b_ids, scale1, expec_f,
+                                                                      mkpts1_f, m, window, fine_scale));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -212,6 +212,35 @@ def _pad16(c):
 # ---------------------------------------------------------------------------------------------
 # the model
 # ---------------------------------------------------------------------------------------------
+class _OutPack:
+    """The per-match outputs of a forward carved out of ONE byte buffer.  In CUDA-graph mode the
+    graph owns the buffers it writes, so the caller gets copies: one clone of the pack (one
+    kernel) instead of one per output tensor."""
+
+    def __init__(self, nbytes, dev):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.fields = []
+        self._off = 0
+
+    @staticmethod
+    def nbytes(cap, fcap):
+        # b_ids, i_ids, j_ids (int64), mconf, mkpts_3d_db [.,3], mkpts_query_c [.,2]; expec_f [.,3],
+        # mkpts_query_f [.,2]; 16 B alignment slack per field
+        return cap * (3 * 8 + 4 + 12 + 8) + fcap * (12 + 8) + 16 * 8
+
+    def new(self, key, shape, dtype):
+        n = dtype.itemsize
+        for d in shape:
+            n *= d
+        off = (self._off + 15) & ~15
+        self.fields.append((key, off, n, dtype, tuple(shape)))
+        self._off = off + n
+        return self.buf[off:off + n].view(dtype).view(shape)
+
+    def views(self, buf):
+        return {k: buf[off:off + n].view(dt).view(shape) for k, off, n, dt, shape in self.fields}
+
+
 class _Engine(nn.Module):
     """What the 2D-3D matcher (OnePosePlus_model) and the 2D-2D matcher (loftr.LoFTR_for_OnePose_Plus)
     share: weight preparation for the kernels, the name-keyed workspace, the ResNet-FPN backbone
@@ -709,7 +738,7 @@ class OnePosePlus_model(_Engine):
         f2()
         cur.wait_stream(side)
 
-    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None):
+    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None, pack=None):
         """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch.
         Enqueues everything up to the ordered match lists (capacity B*min(N,S)) and the device-side
         match count; nothing here synchronises.  Fills `out` with the full-capacity tensors."""
@@ -749,12 +778,14 @@ class OnePosePlus_model(_Engine):
         cap = B * N if self.coarse_colmax else B * min(N, S)
         scratch = self._buf("match_scratch", ((B * N + 1023) // 1024 + 2,), i32, dev)
         count = self._buf("match_count", (1,), i32, dev)
-        b_ids = torch.empty(cap, dtype=torch.int64, device=dev)
-        i_ids = torch.empty(cap, dtype=torch.int64, device=dev)
-        j_ids = torch.empty(cap, dtype=torch.int64, device=dev)
-        mconf = torch.empty(cap, dtype=f32, device=dev)
-        mk3 = torch.empty((cap, 3), dtype=f32, device=dev)
-        mkc = torch.empty((cap, 2), dtype=f32, device=dev)
+        new = pack.new if pack is not None else (
+            lambda key, shape, dtype: torch.empty(shape, dtype=dtype, device=dev))
+        b_ids = new("b_ids", (cap,), torch.int64)
+        i_ids = new("i_ids", (cap,), torch.int64)
+        j_ids = new("j_ids", (cap,), torch.int64)
+        mconf = new("mconf", (cap,), f32)
+        mk3 = new("mkpts_3d_db", (cap, 3), f32)
+        mkc = new("mkpts_query_c", (cap, 2), f32)
         kshared = bank["Bb"] == 1
         if self.coarse_colmax:
             colmax = self._buf("colmax", (B, S), i32, dev)
@@ -793,7 +824,7 @@ class OnePosePlus_model(_Engine):
                      self._buf("lz_bi", (B, N), torch.int32, dev), self.split)
         return conf
 
-    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, count=None):
+    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, count=None, pack=None):
         """FinePreprocess (fine_preprocess.py:32-55) -> loftr_fine -> FineMatching
         (fine_matching.py:28-110) on the first M entries of the match lists.  With `count` (the
         device-side match counter) M is only the CAPACITY: every kernel reads the real number of
@@ -829,8 +860,11 @@ class OnePosePlus_model(_Engine):
                 ops.linear_ln(h, None, L["mlp2"], False, *L["n2"], 1, rows, split, resid=x[cur],
                               out16=None if last else x[1 - cur], out32=x32 if last else None, **dyn26)
                 cur = 1 - cur
-        expec_f = torch.empty((M, 3), dtype=f32, device=dev)
-        mkpts_f = torch.empty((M, 2), dtype=f32, device=dev)
+        if pack is not None:
+            expec_f, mkpts_f = pack.new("expec_f", (M, 3), f32), pack.new("mkpts_query_f", (M, 2), f32)
+        else:
+            expec_f = torch.empty((M, 3), dtype=f32, device=dev)
+            mkpts_f = torch.empty((M, 2), dtype=f32, device=dev)
         fine_scale = float(q_hw_i[0] / hf)
         ops.fine_match(x32, mkc, b_ids, img_scale, expec_f, mkpts_f, M, fine_scale, **dyn)
         out.update({"expec_f": expec_f, "mkpts_query_f": mkpts_f})
@@ -951,19 +985,28 @@ class OnePosePlus_model(_Engine):
         N = bank["N"]
         # latency mode at small batch: both sides of every layer run concurrently (see _both)
         small = B * (max(hc * wc, N) // 256 + 1) <= 37
+        if os.environ.get("OPP_B200_TWO_STREAMS") == "0":   # A/B switch for the latency probe
+            small = False
         self._side_stream = self._aux_stream(img.device) if (dynamic and small) else None
         try:
             q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N, qmask)
         finally:
             self._side_stream = None
         out = {}
-        count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask)
+        pack = None
+        if dynamic:
+            S = hc * wc
+            cap = B * N if self.coarse_colmax else B * min(N, S)
+            fcap = min(cap, B * min(N, S))
+            pack = _OutPack(_OutPack.nbytes(cap, fcap), img.device)
+        count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask,
+                                           pack=pack)
         ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
         if dynamic:
-            fcap = min(cap, B * min(N, hc * wc))
             if fine_on:
-                self._fine(fine_map, bank, ids, fcap, img_scale, hc, wc, (H, W), out, count=count)
+                self._fine(fine_map, bank, ids, fcap, img_scale, hc, wc, (H, W), out, count=count, pack=pack)
             out["fcap"] = fcap
+            out["pack"] = pack
         else:
             M = int(count.item())  # the one host sync of the forward
             if fine_on and M > 0:
@@ -1023,9 +1066,11 @@ class OnePosePlus_model(_Engine):
             self._enqueue(s_img, s_scale, s_bank, fine_on, dynamic=True)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
+            count_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
             with torch.cuda.graph(g):
                 out, count, cap = self._enqueue(s_img, s_scale, s_bank, fine_on, dynamic=True)
-            ent = {"graph": g, "out": out, "count": count, "ws_epoch": self._ws_epoch,
+                count_host.copy_(count, non_blocking=True)   # last node of the graph: M lands in pinned memory
+            ent = {"graph": g, "out": out, "count": count_host, "ws_epoch": self._ws_epoch,
                    "inputs": (s_img, s_scale, s_bank)}
             self._graphs[key] = ent
         s_img, s_scale, s_bank = ent["inputs"]
@@ -1037,8 +1082,11 @@ class OnePosePlus_model(_Engine):
                 d.copy_(t)
         ent["graph"].replay()
         src = ent["out"]
-        M = min(int(ent["count"].item()), src["fcap"])   # the only host sync, after everything is queued
-        out = {k: (v[:M].clone() if torch.is_tensor(v) and k != "conf_matrix" else v) for k, v in src.items()}
+        torch.cuda.current_stream().synchronize()        # the only host sync, after everything is queued
+        M = min(int(ent["count"][0]), src["fcap"])
+        pack = src["pack"]
+        out = {k: v[:M] for k, v in pack.views(pack.buf.clone()).items()}   # one copy kernel
+        out["conf_matrix"] = None
         if torch.is_tensor(src["conf_matrix"]):
             out["conf_matrix"] = src["conf_matrix"].clone()
         elif src["conf_matrix"] is not None:     # lazy handle: re-issue it for this forward
