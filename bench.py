@@ -152,16 +152,19 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
-def conv_flops_table(B, h=H, w=W):
+def conv_flops_table(B, h=H, w=W, head=True):
     """Algorithmic MACs of the tcgen05 conv launches of one backbone pass (true channel counts;
-    the 7x7 conv1 — 0.41 GMAC/image — is listed separately)."""
+    the 7x7 conv1 — 0.41 GMAC/image — is listed separately).  head=False: without
+    layer1_outconv2, which the forward evaluates on the match windows only."""
     h2, h4, h8 = (h // 2) * (w // 2), (h // 4) * (w // 4), (h // 8) * (w // 8)
     macs = 0
     macs += 4 * h2 * 128 * 128 * 9                                   # layer1
     macs += h4 * 196 * 128 * 9 + 3 * h4 * 196 * 196 * 9 + h4 * 196 * 128   # layer2 (+downsample)
     macs += h8 * 256 * 196 * 9 + 3 * h8 * 256 * 256 * 9 + h8 * 256 * 196   # layer3
     macs += h8 * 256 * 256 + h4 * 256 * 196 + h4 * 256 * 256 * 9 + h4 * 196 * 256 * 9   # fpn 1/4
-    macs += h2 * 196 * 128 + h2 * 196 * 196 * 9 + h2 * 128 * 196 * 9                   # fpn 1/2
+    macs += h2 * 196 * 128                                                             # fpn 1/2 lateral
+    if head:
+        macs += h2 * 196 * 196 * 9 + h2 * 128 * 196 * 9                                # layer1_outconv2
     return 2.0 * macs * B
 
 
@@ -481,7 +484,22 @@ def main():
     S_tok = (H // 8) * (W // 8)
     c5 = loftr = None
     if rank == 0:
-        conv_ms = cuda_time(lambda: model._backbone(imgs_dev), 3)
+        # the backbone as the forward runs it: everything up to layer1_outconv2, whose two 3x3
+        # convolutions are evaluated afterwards on the 5x5 windows of the matches only
+        conv_ms = cuda_time(lambda: model._backbone(imgs_dev, defer_fine=True), 3)
+        x1_lat = model._backbone(imgs_dev, defer_fine=True)[1]
+        head_dense_ms = cuda_time(lambda: model._fine_head_dense(x1_lat), 3)
+        dm = {"query_image": imgs_dev, "query_image_scale": scale_dev, **bank}
+        model(dm)
+        x1_lat = model._backbone(imgs_dev, defer_fine=True)[1]
+        Mh = int(dm["b_ids"].numel())
+        head_win_ms = cuda_time(lambda: model._fine_head_windows(x1_lat, dm["b_ids"], dm["j_ids"], Mh,
+                                                                 W // 8, 4), 3) if Mh else None
+        fine_head = {"what": "layer1_outconv2 (3x3 208->208 + 3x3 208->128 at 1/2 resolution)",
+                     "dense_ms": head_dense_ms, "windows_ms": head_win_ms, "matches": Mh,
+                     "mode": model.fine_windows,
+                     "note": "windows = the same convolutions on the 7x7 / 5x5 neighbourhood of each coarse match "
+                             "(what fine_preprocess.py:40-47 reads); bit-equal outputs (tests)"}
         # the dominant kernel launch: layer1 3x3 conv 128->128 at 1/2 resolution (4 identical launches
         # per forward = 30 % of the conv flops), timed alone on the launching stream.  Its input
         # (batch x 256 x 256 x 2 planes x 128 ch fp16 = 2.1 GB at batch 64) exceeds L2.
@@ -493,7 +511,7 @@ def main():
         # coarse attention (BASELINE.json "coarse-attn tensor-pipe %"): the 6-layer linear-attention
         # transformer on both sequences (tcgen05 GEMM launches + the KV-state kernels), one object
         # per image so that nothing is served from the per-object cache
-        q2, _, (hc, wc) = model._backbone(imgs_dev)
+        q2, _, (hc, wc) = model._backbone(imgs_dev, defer_fine=True)
         S_tok = hc * wc
         bstate = {"Bb": B, "N": N_POINTS,
                   "d3_in": ops.to_planes(torch.randn(B, N_POINTS, 256, device=dev), model.split)}
@@ -526,7 +544,7 @@ def main():
 
     if rank == 0:
         total_imgs = B * world * args.steps
-        flops = conv_flops_table(B)
+        flops = conv_flops_table(B, head=False)
         ach = flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None
         passes = 3 if model.split else 1
         l1_flops = 2.0 * B * (H // 2) * (W // 2) * 128 * 128 * 9
@@ -574,8 +592,8 @@ def main():
                                  "time of the launch; the fp32-grade mode issues mma_passes x that on the tensor pipe; "
                                  "traffic = dram read+write of this launch from the committed ncu --set full capture at "
                                  "this batch (profiles/r2_ncu_b64_traffic.json), null when absent",
-                         "backbone": {"kernels": "conv1 im2col + 22 tcgen05 GEMM launches (FPN upsample-adds fused)",
-                                      "ms": conv_ms,
+                         "backbone": {"kernels": "conv1 im2col + 20 tcgen05 GEMM launches (FPN upsample-adds fused), without layer1_outconv2",
+                                      "ms": conv_ms, "fine_head": fine_head,
                                       "algorithmic_tflops": ach, "frac": ach / peak_tf if ach else None,
                                       "issued_frac": ach * passes / peak_tf if ach else None}},
             "coarse_attention": {

@@ -69,6 +69,24 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
                     int ksize, int stride, int act, float slope, void* tok, const float* pe,
                     const void* up, int split, opp_stream_t stream);
 
+/* The same 3x3 / stride 1 / pad 1 convolution evaluated only on a win x win window around each
+ * coarse match (win = 7 or 5).  The fine branch of the FPN (resnet.py:155-157 layer1_outconv2) is
+ * read only inside the 5x5 window of each match (fine_preprocess.py:40-47: unfold, then keep the
+ * matched cells), so for few matches the two half-resolution convolutions run on those windows
+ * alone: conv A on 7x7 (what conv B's 5x5 outputs need), conv B on 5x5; values are those of the
+ * dense convolution at the same positions.
+ *   out   fp16 [matches][win][8][planes*c_out_pad] (compact windows; column 7 of a row is padding;
+ *         positions outside the image are written as zeros = the padding the next conv must see)
+ *   j_ids != NULL (with b_ids): `in` is the dense NHWC map [batch][in_h][in_w][planes*c_in_pad];
+ *         window m starts at (x, y) = (stride * cx + org, stride * cy + org), (cy, cx) = divmod(j_ids[m], wc)
+ *   j_ids == NULL: `in` is the compact output [matches][win + 2][8][planes*c_in_pad] of a previous
+ *         call; output (ly, lx) reads input rows ly..ly+2, columns lx..lx+2
+ *   count: NULL = `matches` is exact; else the capacity, the real count is read on the device */
+int opp_conv_win(const void* in, const void* w, const float* bias, void* out, const long long* b_ids,
+                 const long long* j_ids, int matches, const int* count, int batch, int in_h, int in_w,
+                 int c_in_pad, int c_out_pad, int win, int wc, int stride, int org, int act,
+                 float slope, int split, opp_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * 3D keypoint encoding — normalize_3d_keypoints (utils/normalize.py:16-26) +
  * KeypointEncoding_linear.forward (utils/position_encoding.py:54-60)
@@ -248,11 +266,13 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
  * of the fine map centred on fine pixel (stride*jy, stride*jx), zero outside the map.
  * fine NHWC fp16 [B][hf][wf][planes*128]; desc3d fp32 [B][128][n];
  * x32 fp32 [26 M][128] (may be NULL) / x16 fp16 [26 M][planes*128];
- * bank_shared != 0: desc3d is [1][128][n], shared by every batch element */
+ * bank_shared != 0: desc3d is [1][128][n], shared by every batch element;
+ * windows != 0: `fine` is not the dense map but the compact per-match windows written by
+ * opp_conv_win (win = 5): fp16 [M][5][8][planes*128] */
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
                     int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
-                    const int* count_dev, opp_stream_t stream);
+                    int windows, const int* count_dev, opp_stream_t stream);
 
 /* Linear attention for the 1 + 25 tokens of each match (linear_attention.py:29-61 with
  * L,S in {1,25}).  qkv fp16 [26 M][planes*384] = (elu(q)+1 | elu(k)+1 | v), 8 heads of 16.

@@ -45,7 +45,8 @@ SIGNATURES = {
     "opp_best_finalize": [P, P, P, P, L, I, P],
     "opp_match_select": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, I, P],
     "opp_match_select_colmax": [P, P, P, P, P, I, I, I, I, F, I, F, P, P, P, P, P, P, P, P, I, P],
-    "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P],
+    "opp_fine_gather": [P, P, P, P, P, P, P, I, I, I, I, I, I, I, I, I, P, P],
+    "opp_conv_win": [P, P, P, P, P, P, I, P, I, I, I, I, I, I, I, I, I, I, F, I, P],
     "opp_fine_attention": [P, P, I, I, F, I, P, P],
     "opp_fine_match": [P, P, P, P, P, P, I, F, P, P],
     "opp_linear_act_f16_dyn": [P, I, P, I, P, P, L, P, I, I, I, I, I, P],

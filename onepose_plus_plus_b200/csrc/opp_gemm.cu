@@ -460,6 +460,62 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   return launch<A_CONV, EpiConv>(maps, s, ep, (cudaStream_t)stream);
 }
 
+int opp_conv_win(const void* in, const void* w, const float* bias, void* out, const long long* b_ids,
+                 const long long* j_ids, int matches, const int* count, int batch, int in_h, int in_w,
+                 int c_in_pad, int c_out_pad, int win, int wc, int stride, int org, int act,
+                 float slope, int split, opp_stream_t stream) {
+  OPP_REQUIRE(in && w && bias && out, "null operand");
+  OPP_REQUIRE(win == 5 || win == 7, "window side %d unsupported (5 or 7)", win);
+  OPP_REQUIRE(c_in_pad % 16 == 0 && c_out_pad % 16 == 0 && c_out_pad <= 256,
+              "channel counts must be padded to multiples of 16 (got %d -> %d)", c_in_pad, c_out_pad);
+  OPP_REQUIRE(matches >= 0 && (j_ids == nullptr) == (b_ids == nullptr), "bad match list");
+  if (matches == 0) return OPP_OK;
+  const int planes = split ? 2 : 1;
+  TensorMaps maps;
+  GemmShape s;
+  memset(&s, 0, sizeof(s));
+  s.batches = 1;
+  s.tile_w = 8;
+  s.tile_h = win;
+  s.tiles_x = 128 / (8 * win);   // windows per M tile: 2 (7x7) or 3 (5x5)
+  s.tiles_y = 1;
+  s.rows = matches * 8 * win;
+  s.m_tiles = (matches + s.tiles_x - 1) / s.tiles_x;
+  s.block_n = c_out_pad;
+  s.n_tiles = 1;
+  s.n_total = c_out_pad;
+  s.conv_c = c_in_pad;
+  s.conv_cchunks = (c_in_pad + 63) / 64;
+  s.k_chunks = 9 * s.conv_cchunks;
+  s.conv_kw = 3;
+  s.conv_pad = 1;
+  s.conv_stride = 1;
+  s.out_w = 8;
+  s.out_h = win;
+  s.split = split ? 1 : 0;
+  const long long C = (long long)planes * c_in_pad;
+  int rc;
+  {
+    const uint64_t iw = j_ids ? in_w : 8, ih = j_ids ? in_h : win + 2, ib = j_ids ? batch : matches;
+    uint64_t dims[4] = {(uint64_t)C, iw, ih, ib};
+    uint64_t str[3] = {(uint64_t)C, (uint64_t)(iw * C), (uint64_t)(ih * iw * C)};
+    uint32_t box[4] = {64, 8, (uint32_t)win, 1};
+    rc = make_map(&maps.a[0], in, 4, dims, str, box);
+    if (rc) return rc;
+    maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
+  }
+  const long long kplane = 9LL * c_in_pad;
+  s.b_lo = (int)kplane;
+  const long long kt = kplane * planes;
+  pick_grouping(s);
+  rc = map_rows(&maps.b, w, kt, c_out_pad, 1, kt, (long long)c_out_pad * kt, s.block_n / s.cluster);
+  if (rc) return rc;
+  EpiWin::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias, act, slope,
+                    b_ids, j_ids, wc, stride, org, in_h, in_w};
+  if (count) return launch<A_WIN, EpiWin, true>(maps, s, ep, (cudaStream_t)stream, count, 8 * win);
+  return launch<A_WIN, EpiWin>(maps, s, ep, (cudaStream_t)stream);
+}
+
 int opp_sim_lse(const void* a, const void* b, float* part_m, float* part_s, int batches, int rows,
                 int cols, int k, float scale, int split, opp_stream_t stream) {
   TensorMaps maps;

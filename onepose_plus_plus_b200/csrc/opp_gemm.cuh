@@ -72,7 +72,7 @@ constexpr int kEpiSmemBytes = kEpiParamBytes + kMaxEpiWarps * 2560;   // + trans
 // 64 threads (producer + MMA warps) + 128 per epilogue warp group (Epi::kGroups = 1 or 2)
 constexpr int gemm_threads(int groups) { return 64 + 128 * groups; }
 
-enum AMode : int { A_ROWS = 0, A_CONV = 1 };
+enum AMode : int { A_ROWS = 0, A_CONV = 1, A_WIN = 2 };
 
 struct TensorMaps {
   CUtensorMap a[4];
@@ -110,6 +110,10 @@ struct GemmShape {
   int tile_w, tile_h;    // output tile, tile_w*tile_h == 128
   int tiles_x, tiles_y;  // tiles per image
   int out_w, out_h;
+  // A_WIN (sparse 3x3 convolution on per-match windows) reuses the conv fields: tile_w = 8 (window
+  // row pitch), tile_h = window rows (7 or 5), tiles_x = windows per M tile (2 or 3; they occupy
+  // tiles_x * tile_w * tile_h <= 128 accumulator rows), rows = matches * tile_w * tile_h,
+  // m_tiles = ceil(matches / tiles_x), batches = 1.
 };
 
 struct EpiCtx {
@@ -167,6 +171,10 @@ __device__ __forceinline__ bool epi_row_info(const GemmShape& s, const EpiCtx& c
   if (c.a_mode == A_ROWS) {
     row = c.m_tile * kBlockM + rit;
     ok = row < s.rows;
+  } else if (c.a_mode == A_WIN) {
+    const int wrows = s.tiles_x * s.tile_w * s.tile_h;   // accumulator rows in use
+    row = c.m_tile * wrows + rit;
+    ok = rit < wrows && row < s.rows;
   } else {
     const int ty = c.m_tile / s.tiles_x;
     const int tx = c.m_tile - ty * s.tiles_x;
@@ -674,6 +682,74 @@ struct EpiConv {
         }
         staged_store_h32<false>(s, c, p.tok, p.ld, p.out_lo, g0, v, nvalid);
       }
+    });
+  }
+};
+
+// Sparse 3x3 convolution on per-match windows (A_WIN): the fine branch of the FPN
+// (resnet.py:155-157, layer1_outconv2) is only ever read inside the W x W window of each coarse
+// match (fine_preprocess.py:40-47 unfolds the map and keeps the matched cells), so the two
+// half-resolution 3x3 convolutions are evaluated on those windows alone: conv A on the 7x7
+// neighbourhood of a match (what conv B's 5x5 outputs need), conv B on the 5x5 window.
+// Output rows are compact: window m, position (ly, lx) -> row (m * tile_h + ly) * 8 + lx.
+// j_ids != null: the input is the dense NHWC map and the window origin comes from the match's
+// coarse cell: x = stride * cx + org + lx, y likewise; rows whose position lies outside the image
+// are written as ZERO (they are the zero padding conv B must see).  j_ids == null: the input is a
+// compact window tensor [matches][tile_h + 2][8][C] of a previous A_WIN launch.
+struct EpiWin {
+  static constexpr int kGroups = OPP_CONV_GROUPS;
+  struct Params {
+    __half* out;
+    long long ld;
+    int out_lo;
+    const float* bias;
+    int act;
+    float slope;
+    const long long* b_ids;   // [matches] image of the match (dense input only)
+    const long long* j_ids;   // [matches] coarse cell of the match, or null: compact input
+    int wc;                   // coarse cells per row
+    int stride;               // input pixels per coarse cell (4)
+    int org;                  // first output position relative to stride * cell (-3 / -2)
+    int in_h, in_w;           // dense map size
+  };
+  __device__ static void prefetch(const Params&, const GemmShape&, const EpiCtx&) {}
+  __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
+    epi_sync(c);
+    for (int i = c.etid; i < c.ncols; i += 128) sts32f(c.smem_s + 4 * i, p.bias[c.n0 + i]);
+    epi_sync(c);
+    bool inside = true;
+    if (p.j_ids && c.valid) {
+      const int rpm = s.tile_w * s.tile_h;
+      const int m = (int)(c.grow / rpm);
+      const int local = (int)(c.grow - (long long)m * rpm);
+      const int ly = local / s.tile_w, lx = local - ly * s.tile_w;
+      const int j = (int)p.j_ids[m];
+      const int cy = j / p.wc;
+      const int y = p.stride * cy + p.org + ly, x = p.stride * (j - cy * p.wc) + p.org + lx;
+      inside = y >= 0 && y < p.in_h && x >= 0 && x < p.in_w;
+    }
+    tmem_foreach32_sel<kGroups == 1>(c.tmem, c.ncols, c.col_first, c.col_step, [&](int col, float* v) {
+      const int nvalid = c.ncols - col;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 bq = lds128(c.smem_s + 4 * ((col + 4 * g) & 255));
+        v[4 * g + 0] += __uint_as_float(bq.x);
+        v[4 * g + 1] += __uint_as_float(bq.y);
+        v[4 * g + 2] += __uint_as_float(bq.z);
+        v[4 * g + 3] += __uint_as_float(bq.w);
+      }
+      if (p.act == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+      }
+      if (!inside) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      staged_store_h32<false>(s, c, p.out, p.ld, p.out_lo, c.n0 + col, v, nvalid);
     });
   }
 };
@@ -1192,7 +1268,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
     uint32_t phase = 0;
     const bool skip_b = (s.debug_skip & 1) != 0, skip_a = (s.debug_skip & 2) != 0;
     // pair: both CTAs' loads are credited to the leader's barrier, which expects twice the bytes
-    const uint32_t tx_bytes = ((skip_a ? 0 : a_stage) + (skip_b ? 0 : b_stage)) * (pair ? 2 : 1);
+    const int a_tx = A_MODE == A_WIN ? s.tiles_x * s.tile_w * s.tile_h * (kBlockK * 2) * planes : a_stage;
+    const uint32_t tx_bytes = ((skip_a ? 0 : a_tx) + (skip_b ? 0 : b_stage)) * (pair ? 2 : 1);
     for (int t = cluster_id; t < total_tiles; t += n_clusters) {
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
@@ -1207,6 +1284,24 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       }
       const int bb = s.b_batched ? b : 0;
       const int nrow0 = n_tile * s.block_n;
+      // A_WIN: input coordinates of the (up to three) windows of this tile, once per tile
+      int win_x[3] = {0, 0, 0}, win_y[3] = {0, 0, 0}, win_z[3] = {0, 0, 0};
+      if constexpr (A_MODE == A_WIN) {
+        const int cnt = s.rows / (s.tile_w * s.tile_h);
+#pragma unroll
+        for (int wi = 0; wi < 3; ++wi) {
+          int m = m_tile * s.tiles_x + wi;
+          m = m < cnt ? m : cnt - 1;
+          win_z[wi] = m;
+          if (ep.j_ids) {
+            const int j = (int)ep.j_ids[m];
+            const int cy = j / ep.wc;
+            win_z[wi] = (int)ep.b_ids[m];
+            win_x[wi] = ep.stride * (j - cy * ep.wc) + ep.org - s.conv_pad;
+            win_y[wi] = ep.stride * cy + ep.org - s.conv_pad;
+          }
+        }
+      }
       // incremental (tap, channel-chunk) counters instead of per-chunk divisions
       int cc = 0, ky = 0, kx = 0, kb_tap = 0;
       for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
@@ -1232,6 +1327,40 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
                 tma_load_3d(am, &full[stage], sa, kc, m_tile * kBlockM, ba);
                 if (s.split) tma_load_3d(am, &full[stage], sa + kABytes, kc + lo, m_tile * kBlockM, ba);
               }
+            }
+          }
+        } else if constexpr (A_MODE == A_WIN) {
+          // one TMA box (64 channels x 8 x tile_h) per window and plane; windows past the match
+          // count re-read the last one (their rows are never stored)
+          kb = kb_tap + cc * kBlockK;
+          const int wbytes = s.tile_w * s.tile_h * (kBlockK * 2);
+#pragma unroll
+          for (int wi = 0; wi < 3; ++wi) {
+            if (wi >= s.tiles_x) break;
+            const int bx = win_x[wi] + kx, by = win_y[wi] + ky, bz = win_z[wi];
+            if (elect_one()) {
+              if (wi == 0 && (!pair || leader)) mbar_expect_tx(&full[stage], tx_bytes);
+              if (!skip_a) {
+                if (pair) {
+                  tma_load_4d_2sm(&maps.a[0], &full[stage], sa + wi * wbytes, cc * kBlockK, bx, by, bz);
+                  if (s.split)
+                    tma_load_4d_2sm(&maps.a[0], &full[stage], sa + kABytes + wi * wbytes,
+                                    s.conv_c + cc * kBlockK, bx, by, bz);
+                } else {
+                  tma_load_4d(&maps.a[0], &full[stage], sa + wi * wbytes, cc * kBlockK, bx, by, bz);
+                  if (s.split)
+                    tma_load_4d(&maps.a[0], &full[stage], sa + kABytes + wi * wbytes,
+                                s.conv_c + cc * kBlockK, bx, by, bz);
+                }
+              }
+            }
+          }
+          if (++cc == s.conv_cchunks) {
+            cc = 0;
+            kb_tap += s.conv_c;
+            if (++kx == s.conv_kw) {
+              kx = 0;
+              ++ky;
             }
           }
         } else {
@@ -1319,7 +1448,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       int cc = 0;
       for (int chunk = 0; chunk < s.k_chunks; ++chunk) {
         int ksteps = 4;
-        if (A_MODE == A_CONV) {
+        if (A_MODE != A_ROWS) {
           const int rem = (s.conv_c - cc * kBlockK) >> 4;
           ksteps = rem < 4 ? rem : 4;
           if (++cc == s.conv_cchunks) cc = 0;
@@ -1469,7 +1598,8 @@ gemm_kernel_dyn(const __grid_constant__ TensorMaps maps, const GemmShape s_in,
   pdl_wait();   // rows_dev is written by the previous kernels of the stream
   const int r = *rows_dev * rows_mult;
   s.rows = r < s_in.rows ? r : s_in.rows;
-  s.m_tiles = (s.rows + kBlockM - 1) / kBlockM;
+  const int tile_rows = A_MODE == A_WIN ? s_in.tiles_x * s_in.tile_w * s_in.tile_h : kBlockM;
+  s.m_tiles = (s.rows + tile_rows - 1) / tile_rows;
   s.msup = (s.m_tiles + s_in.cluster - 1) / s_in.cluster;
   gemm_body<A_MODE, Epi>(maps, s, ep);
 }

@@ -731,7 +731,8 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const __half* __restrict__ fine, const float* __restrict__ desc3d,
     const long long* __restrict__ b_ids, const long long* __restrict__ i_ids,
     const long long* __restrict__ j_ids, float* __restrict__ x32, __half* __restrict__ x16, int hf,
-    int wf, int wc, int stride, int n, int lo_off, int desc_shared, const int* __restrict__ count_dev) {
+    int wf, int wc, int stride, int n, int lo_off, int desc_shared, int windows,
+    const int* __restrict__ count_dev) {
   pdl_sync();
   const int m = blockIdx.x, c = threadIdx.x;
   if (count_dev && m >= *count_dev) return;   // launched at capacity, match count on the device
@@ -742,11 +743,13 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
   const float d = desc3d[((desc_shared ? 0 : b) * 128 + c) * n + i];
   if (x32) x32[row0 * 128 + c] = d;
   store_split1(x16 + row0 * ld, c, d, lo_off);
-  const __half* fb = fine + b * hf * wf * ld;
+  // windows: `fine` holds the compact per-match windows of opp_conv_win, [m][5][8][ld]
+  const __half* fb = windows ? fine + (long long)m * 40 * ld : fine + b * hf * wf * ld;
   for (int ww = 0; ww < 25; ++ww) {
     const int y = jy * stride + ww / 5 - 2, x = jx * stride + ww % 5 - 2;
     float v = 0.f;
-    if (y >= 0 && y < hf && x >= 0 && x < wf) v = load_split1(fb + ((long long)y * wf + x) * ld, c, lo_off);
+    if (y >= 0 && y < hf && x >= 0 && x < wf)
+      v = load_split1(fb + (windows ? (long long)((ww / 5) * 8 + ww % 5) : (long long)y * wf + x) * ld, c, lo_off);
     if (x32) x32[(row0 + 1 + ww) * 128 + c] = v;
     store_split1(x16 + (row0 + 1 + ww) * ld, c, v, lo_off);
   }
@@ -1422,13 +1425,13 @@ int opp_match_select_colmax(const float* pt_val, const int* pt_idx, const unsign
 int opp_fine_gather(const void* fine, const float* desc3d, const long long* b_ids,
                     const long long* i_ids, const long long* j_ids, float* x32, void* x16, int m,
                     int hf, int wf, int wc, int stride, int n, int split, int bank_shared,
-                    const int* count_dev, opp_stream_t stream) {
+                    int windows, const int* count_dev, opp_stream_t stream) {
   if (m == 0) return OPP_OK;
   OPP_REQUIRE(fine && desc3d && b_ids && i_ids && j_ids && x16, "null pointer");
   OPP_CHECK_CUDA(opp::launch_pdl(fine_gather_kernel, dim3(m), dim3(128), 0, (cudaStream_t)stream, (const __half*)fine, desc3d, b_ids,
                                                           i_ids, j_ids, x32, (__half*)x16, hf, wf,
                                                           wc, stride, n, split ? 128 : 0, bank_shared,
-                                                          count_dev));
+                                                          windows, count_dev));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }

@@ -226,7 +226,8 @@ class _OutPack:
     def nbytes(cap, fcap):
         # b_ids, i_ids, j_ids (int64), mconf, mkpts_3d_db [.,3], mkpts_query_c [.,2]; expec_f [.,3],
         # mkpts_query_f [.,2]; 16 B alignment slack per field
-        return cap * (3 * 8 + 4 + 12 + 8) + fcap * (12 + 8) + 16 * 8
+        # + gt_mask (bool, all False at inference: coarse_matching.py:233 with no GT)
+        return cap * (3 * 8 + 4 + 12 + 8 + 1) + fcap * (12 + 8) + 16 * 9
 
     def new(self, key, shape, dtype):
         n = dtype.itemsize
@@ -415,8 +416,13 @@ class _Engine(nn.Module):
         return sum(e[0].numel() for e in self._ws.values())
 
     # ------------------------------------------------------------------ stages
-    def _backbone(self, img):
-        """ResNetFPN_8_2.forward (backbone/resnet.py:141-164) -> coarse tokens (+pe), fine map."""
+    def _backbone(self, img, defer_fine=False, fpn_stream=None):
+        """ResNetFPN_8_2.forward (backbone/resnet.py:141-164) -> coarse tokens (+pe), fine map.
+        defer_fine: stop before layer1_outconv2 and return its input (the merged 1/2-resolution
+        map) instead of the fine map; the caller finishes with _fine_head_dense or, when the
+        matches are few, _fine_head_windows.  fpn_stream (latency mode): the top-down path below
+        the coarse output — which nothing needs before the fine stage — is enqueued on that stream
+        so that it runs beside the coarse transformer; the caller joins it before the fine head."""
         P = self._plan
         dev = img.device
         B, _, H, W = img.shape
@@ -446,14 +452,53 @@ class _Engine(nn.Module):
         S = hc * wc
         tok = self._buf("q2_0", (B, S, pl * 256), f16, dev)
         x3_out = cv("layer3_outconv", x3, "x3_out", 1, 1, tok=tok, pe=self._pe_tokens(hc, wc, dev))
-        # FPN top-down merge fused into the lateral 1x1 conv epilogue (resnet.py:149-157)
-        x2_lat = cv("layer2_outconv", x2, "x2_lat", 1, 1, up=x3_out)
-        t = cv("layer2_outconv2.0", x2_lat, "x2_h", 3, 1, act=2)
-        x2_out = cv("layer2_outconv2.3", t, "x2_out", 3, 1)
-        x1_lat = cv("layer1_outconv", x1, "x1_lat", 1, 1, up=x2_out)
-        t = cv("layer1_outconv2.0", x1_lat, "x1_h", 3, 1, act=2)
-        x1_out = cv("layer1_outconv2.3", t, "x1_out", 3, 1)
-        return tok, x1_out, (hc, wc)
+        def top_down():
+            # FPN top-down merge fused into the lateral 1x1 conv epilogue (resnet.py:149-157)
+            x2_lat = cv("layer2_outconv", x2, "x2_lat", 1, 1, up=x3_out)
+            t = cv("layer2_outconv2.0", x2_lat, "x2_h", 3, 1, act=2)
+            x2_out = cv("layer2_outconv2.3", t, "x2_out", 3, 1)
+            return cv("layer1_outconv", x1, "x1_lat", 1, 1, up=x2_out)
+
+        if fpn_stream is not None:
+            fpn_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(fpn_stream):
+                x1_lat = top_down()
+        else:
+            x1_lat = top_down()
+        if defer_fine:
+            return tok, x1_lat, (hc, wc)
+        return tok, self._fine_head_dense(x1_lat), (hc, wc)
+
+    def _fine_head_dense(self, x1_lat):
+        """layer1_outconv2 (resnet.py:155-157) on the whole 1/2-resolution map."""
+        P, split = self._plan, self.split
+        pl = 2 if split else 1
+        B, h, w, _ = x1_lat.shape
+        (w0, b0), (w1, b1) = P["layer1_outconv2.0"], P["layer1_outconv2.3"]
+        t = self._buf("x1_h", (B, h, w, pl * w0.shape[0]), torch.float16, x1_lat.device)
+        ops.conv2d_nhwc(x1_lat, w0, b0, t, 3, 1, split, 2)
+        out = self._buf("x1_out", (B, h, w, pl * w1.shape[0]), torch.float16, x1_lat.device)
+        return ops.conv2d_nhwc(t, w1, b1, out, 3, 1, split, 0)
+
+    def _fine_head_windows(self, x1_lat, b_ids, j_ids, M, wc, stride, count=None):
+        """The same two convolutions evaluated only where fine_preprocess.py:40-47 reads them: the
+        5x5 window of each coarse match (conv A on its 7x7 neighbourhood, conv B on the window).
+        Returns the compact window tensor [M, 5, 8, pl*128] (values identical to the dense map's at
+        those positions).  M is the capacity when `count` (device-side match count) is given."""
+        P, split = self._plan, self.split
+        pl = 2 if split else 1
+        dev = x1_lat.device
+        (w0, b0), (w1, b1) = P["layer1_outconv2.0"], P["layer1_outconv2.3"]
+        t = self._buf("x1_h_win", (M, 7, 8, pl * w0.shape[0]), torch.float16, dev)
+        ops.conv_win(x1_lat, w0, b0, t, 7, split, M, act=2, b_ids=b_ids, j_ids=j_ids, wc=wc, stride=stride,
+                     org=-3, count=count)
+        out = self._buf("x1_out_win", (M, 5, 8, pl * w1.shape[0]), torch.float16, dev)
+        return ops.conv_win(t, w1, b1, out, 5, split, M, count=count)
+
+    def _windows_pay(self, M, B, hf, wf):
+        """Sparse vs dense layer1_outconv2: M-tile counts weighted by the output widths (208 / 128):
+        2 (3) windows per 128-row tile against hf*wf/128 tiles per image."""
+        return M * (208 / 2 + 128 / 3) < 0.85 * B * (hf * wf / 128) * (208 + 128)
 
     def _src_state(self, L, tag, src, B, ls, src_mask=None):
         """Source side of linear attention for one layer (linear_attention.py:46,55-57 +
@@ -590,6 +635,10 @@ class OnePosePlus_model(_Engine):
         # butterflies in the epilogue) instead of two more sim GEMM passes
         self.coarse_colmax = os.environ.get("OPP_B200_COLMAX", "1") == "1"
         self.coarse_lse_cols = os.environ.get("OPP_B200_LSECOLS", "1") == "1"
+        # layer1_outconv2 (the last two 3x3 convolutions of the FPN, 1/2 resolution) evaluated only on
+        # the 5x5 windows the fine stage reads: "auto" = when cheaper than the dense map (by the
+        # match count), "sparse" / "dense" = always / never
+        self.fine_windows = os.environ.get("OPP_B200_FINE_WINDOWS", "auto")
 
     # pickling (Ray ships the module object): drop device-side caches
     def __getstate__(self):
@@ -597,12 +646,14 @@ class OnePosePlus_model(_Engine):
         st["_plan"], st["_plan_sig"], st["_ws"], st["_sig_tensors"] = None, None, {}, None
         st["_bank"], st["_graphs"], st["_side_stream"] = None, {}, None
         st.pop("_aux", None)
+        st.pop("_aux_fpn", None)
         return st
 
     def __setstate__(self, st):
         self.__dict__.update(st)
         for k, v in (("_sig_tensors", None), ("_apply_epoch", 0), ("_ws_epoch", 0), ("_bank", None),
-                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False), ("_side_stream", None)):
+                     ("_graphs", {}), ("_fwd_count", 0), ("use_cuda_graphs", False), ("_side_stream", None),
+                     ("fine_windows", "auto")):
             self.__dict__.setdefault(k, v)
 
     # ------------------------------------------------------------------ descriptor bank
@@ -824,7 +875,7 @@ class OnePosePlus_model(_Engine):
                      self._buf("lz_bi", (B, N), torch.int32, dev), self.split)
         return conf
 
-    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, count=None, pack=None):
+    def _fine(self, fine_map, bank, ids, M, img_scale, hc, wc, q_hw_i, out, count=None, pack=None, windows_hw=None):
         """FinePreprocess (fine_preprocess.py:32-55) -> loftr_fine -> FineMatching
         (fine_matching.py:28-110) on the first M entries of the match lists.  With `count` (the
         device-side match counter) M is only the CAPACITY: every kernel reads the real number of
@@ -833,7 +884,10 @@ class OnePosePlus_model(_Engine):
         f16, f32 = torch.float16, torch.float32
         split = self.split
         pl = 2 if split else 1
-        B, hf, wf, _ = fine_map.shape
+        if windows_hw is None:
+            B, hf, wf, _ = fine_map.shape
+        else:
+            hf, wf = windows_hw     # fine_map = compact windows of _fine_head_windows
         stride = hf // hc
         rows = 26 * M
         x = [self._buf(f"fx{k}", (rows, pl * 128), f16, dev) for k in range(2)]
@@ -843,7 +897,8 @@ class OnePosePlus_model(_Engine):
         dyn = {} if count is None else {"count": count}
         dyn26 = {} if count is None else {"count": count, "rows_per_count": 26}
         ops.fine_gather(fine_map, bank["fine"], b_ids, i_ids, j_ids, None if fine_layers else x32, x[0], M,
-                        hf, wf, wc, stride, bank["N"], split, bank_shared=bank["Bb"] == 1, **dyn)
+                        hf, wf, wc, stride, bank["N"], split, bank_shared=bank["Bb"] == 1,
+                        windows=windows_hw is not None, **dyn)
         cur = 0
         if fine_layers:
             qkv = self._buf("f_qkv", (rows, pl * 384), f16, dev)
@@ -970,7 +1025,17 @@ class OnePosePlus_model(_Engine):
         dynamic=True: no sync at all — the fine stage is launched at its capacity
         (B * min(N, S) matches) and reads M on the device; this is the capturable form."""
         B, _, H, W = img.shape
-        q2, fine_map, (hc, wc) = self._backbone(img)
+        # layer1_outconv2 is deferred: after the coarse stage it runs on the match windows only
+        # (fine_windows "auto": when that is cheaper; "sparse" / "dense" force one path), and not
+        # at all when fine matching is disabled
+        win_ok = fine_on and self.fine_windows != "dense" and self.fine_preprocess.W == 5
+        # latency mode (CUDA-graph capture at small batch): FPN top-down path on its own stream
+        fpn_stream = None
+        if dynamic and B <= 2 and os.environ.get("OPP_B200_TWO_STREAMS") != "0":
+            fpn_stream = self._aux_stream(img.device, "_aux_fpn")
+        q2, fine_in, (hc, wc) = self._backbone(img, defer_fine=True, fpn_stream=fpn_stream)
+        fstride = fine_in.shape[1] // hc
+        win_ok = win_ok and fstride == 4
         if bank_raw is None:
             bank = self._resident_bank_state()
         else:
@@ -999,25 +1064,42 @@ class OnePosePlus_model(_Engine):
             cap = B * N if self.coarse_colmax else B * min(N, S)
             fcap = min(cap, B * min(N, S))
             pack = _OutPack(_OutPack.nbytes(cap, fcap), img.device)
+            out["gt_mask"] = pack.new("gt_mask", (cap,), torch.bool)   # zeroed once by _replay, never written
         count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask,
                                            pack=pack)
         ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
+        hf, wf = fine_in.shape[1:3]
+        if fpn_stream is not None:
+            torch.cuda.current_stream().wait_stream(fpn_stream)
         if dynamic:
             if fine_on:
-                self._fine(fine_map, bank, ids, fcap, img_scale, hc, wc, (H, W), out, count=count, pack=pack)
+                # the host does not know M: windows at capacity (the kernels read M on the device)
+                # for the small batches this mode is meant for, else the dense map
+                if win_ok and (self.fine_windows == "sparse" or B <= 8):
+                    fw = self._fine_head_windows(fine_in, out["b_ids"], out["j_ids"], fcap, wc, fstride, count=count)
+                    self._fine(fw, bank, ids, fcap, img_scale, hc, wc, (H, W), out, count=count, pack=pack,
+                               windows_hw=(hf, wf))
+                else:
+                    self._fine(self._fine_head_dense(fine_in), bank, ids, fcap, img_scale, hc, wc, (H, W), out,
+                               count=count, pack=pack)
             out["fcap"] = fcap
             out["pack"] = pack
         else:
             M = int(count.item())  # the one host sync of the forward
             if fine_on and M > 0:
-                self._fine(fine_map, bank, ids, M, img_scale, hc, wc, (H, W), out)
+                if win_ok and (self.fine_windows == "sparse" or self._windows_pay(M, B, hf, wf)):
+                    fw = self._fine_head_windows(fine_in, out["b_ids"], out["j_ids"], M, wc, fstride)
+                    self._fine(fw, bank, ids, M, img_scale, hc, wc, (H, W), out, windows_hw=(hf, wf))
+                else:
+                    self._fine(self._fine_head_dense(fine_in), bank, ids, M, img_scale, hc, wc, (H, W), out)
             out["M"] = M
         return out, count, cap
 
-    def _aux_stream(self, dev):
-        st = getattr(self, "_aux", None)
+    def _aux_stream(self, dev, name="_aux"):
+        st = getattr(self, name, None)
         if st is None or st.device != dev:
-            st = self._aux = torch.cuda.Stream(device=dev)
+            st = torch.cuda.Stream(device=dev)
+            setattr(self, name, st)
         return st
 
     # ------------------------------------------------------------------ CUDA graphs
@@ -1043,7 +1125,7 @@ class OnePosePlus_model(_Engine):
                 bank_raw = tuple(t[:1] for t in bank_raw)
             bkey = tuple((tuple(t.shape), t.dtype) for t in bank_raw)
         key = (tuple(img.shape), img.dtype, img_scale is not None, bkey, fine_on, self.conf_matrix_mode,
-               self.coarse_colmax, self.coarse_lse_cols, self.kv_single_plane)
+               self.coarse_colmax, self.coarse_lse_cols, self.kv_single_plane, self.fine_windows)
         ent = self._graphs.get(key)
         if ent is not None and ent["ws_epoch"] != self._ws_epoch:
             ent = None            # a workspace buffer was re-allocated: the captured pointers are stale
@@ -1070,6 +1152,7 @@ class OnePosePlus_model(_Engine):
             with torch.cuda.graph(g):
                 out, count, cap = self._enqueue(s_img, s_scale, s_bank, fine_on, dynamic=True)
                 count_host.copy_(count, non_blocking=True)   # last node of the graph: M lands in pinned memory
+            out["gt_mask"].zero_()
             ent = {"graph": g, "out": out, "count": count_host, "ws_epoch": self._ws_epoch,
                    "inputs": (s_img, s_scale, s_bank)}
             self._graphs[key] = ent
@@ -1100,7 +1183,7 @@ class OnePosePlus_model(_Engine):
         b_ids = out["b_ids"][:M]
         data.update({
             "b_ids": b_ids, "i_ids": out["i_ids"][:M], "j_ids": out["j_ids"][:M],
-            "gt_mask": torch.zeros(M, dtype=torch.bool, device=dev),
+            "gt_mask": out["gt_mask"][:M] if "gt_mask" in out else torch.zeros(M, dtype=torch.bool, device=dev),
             "m_bids": b_ids, "mkpts_3d_db": out["mkpts_3d_db"][:M], "mkpts_query_c": out["mkpts_query_c"][:M],
             "mconf": out["mconf"][:M],
         })

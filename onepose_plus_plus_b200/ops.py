@@ -209,10 +209,28 @@ def match_select(pt_val, pt_idx, px_idx, kpts, img_scale, batch, l, hc, wc, thr,
 
 
 def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stride, n, split,
-                bank_shared=False, count=None):
+                bank_shared=False, count=None, windows=False):
+    """windows: `fine` is the compact [m, 5, 8, planes*128] window tensor of conv_win."""
     _chk(desc3d, torch.float32, "descriptors3d_db")
     call("opp_fine_gather", ptr(fine), ptr(desc3d), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x32),
-         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), ptr(count), stream())
+         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), int(windows), ptr(count), stream())
+
+
+def conv_win(x, w, bias, out, win, split, m, act=0, slope=0.01, b_ids=None, j_ids=None, wc=0, stride=4,
+             org=0, count=None):
+    """3x3 convolution on per-match windows (opp_conv_win).  With j_ids: x is the dense NHWC map
+    [B, H, W, planes*Cin_pad]; without: the compact output [m, win+2, 8, planes*Cin_pad] of the
+    previous call.  out: [m, win, 8, planes*Cout_pad]."""
+    _chk(x, torch.float16, "x")
+    _chk(w, torch.float16, "w")
+    planes = 2 if split else 1
+    if j_ids is not None:
+        B, H, W, C = x.shape
+    else:
+        B, H, W, C = 1, 0, 0, x.shape[-1]
+    call("opp_conv_win", ptr(x), ptr(w), ptr(bias), ptr(out), ptr(b_ids), ptr(j_ids), m, ptr(count), B, H, W,
+         C // planes, w.shape[0], win, wc, stride, org, act, float(slope), int(split), stream())
+    return out
 
 
 def fine_attention(qkv, msg, m, cross, split, eps=1e-6, count=None):

@@ -47,7 +47,7 @@ def timed(name, fn):
 
 
 with torch.no_grad():
-    (q2, fine_map, (hc, wc)), g_bb = timed("backbone", lambda: m._backbone(img))
+    (q2, x1_lat, (hc, wc)), g_bb = timed("backbone_trunk", lambda: m._backbone(img, defer_fine=True))
     bank = m._resident_bank_state()
     S, N = hc * wc, bank["N"]
 
@@ -69,7 +69,18 @@ with torch.no_grad():
     (count, cap), g_cm = timed("coarse_matching", cm)
     ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
     fcap = min(cap, min(N, S))
-    _, g_f = timed("fine", lambda: m._fine(fine_map, bank, ids, fcap, scale, hc, wc, (512, 512), {}, count=count))
+    # run the real coarse stage once so that the device-side match count is the real one
+    g_bb.replay()        # (the transformer ping-pongs through its own input buffer)
+    g_xf.replay()
+    g_cm.replay()
+    torch.cuda.synchronize()
+    hf, wf = x1_lat.shape[1:3]
+    fw, _g = timed("fine_head_windows", lambda: m._fine_head_windows(x1_lat, out["b_ids"], out["j_ids"], fcap, wc, 4,
+                                                                  count=count))
+    _, _g = timed("fine_head_dense", lambda: m._fine_head_dense(x1_lat))
+    _, g_f = timed("fine", lambda: m._fine(fw, bank, ids, fcap, scale, hc, wc, (512, 512), {}, count=count,
+                                           windows_hw=(hf, wf)))
 res["matches"] = int(count.item())
-res["sum_us"] = round(res["backbone"] + res["transformer_two_streams"] + res["coarse_matching"] + res["fine"], 1)
+res["sum_us"] = round(res["backbone_trunk"] + res["transformer_two_streams"] + res["coarse_matching"]
+                      + res["fine_head_windows"] + res["fine"], 1)
 print(json.dumps(res))

@@ -221,6 +221,77 @@ def check_conv():
         _conv_case(split, 1, 8, 16, 128, 128, 196, 208, 1, 1, 0, False, False, up=True)
 
 
+def check_conv_win():
+    """opp_conv_win (3x3 convolutions on per-match windows, the sparse form of layer1_outconv2)
+    against the dense convolutions of the same engine (bit-equal at the window positions: same K
+    order, same MMA sequence) and against fp64 torch; matches on the image border (zero padding of
+    both convolutions, windows reaching outside the map) and ragged tile counts included."""
+    from onepose_plus_plus_b200 import ops
+    for split in (0, 1):
+        pl = 2 if split else 1
+        for (B, H, W, M, dyn) in [(2, 64, 96, 37, False), (1, 32, 32, 64, True), (3, 40, 72, 1, False),
+                                  (1, 64, 64, 200, True)]:
+            hc, wc = H // 4, W // 4
+            cin, cin_pad, cmid, cmid_pad, cout = 196, 208, 196, 208, 128
+            xf = torch.zeros(B, H, W, cin_pad, device=DEV)
+            xf[..., :cin] = _rand(B, H, W, cin, seed=1)
+            w0f = torch.zeros(cmid_pad, 3, 3, cin_pad, device=DEV)
+            w0f[:cmid, :, :, :cin] = _rand(cmid, 3, 3, cin, scale=1.0 / math.sqrt(9 * cin), seed=2)
+            b0 = torch.zeros(cmid_pad, device=DEV)
+            b0[:cmid] = _rand(cmid, seed=3) * 0.1
+            w1f = torch.zeros(cout, 3, 3, cmid_pad, device=DEV)
+            w1f[:, :, :, :cmid] = _rand(cout, 3, 3, cmid, scale=1.0 / math.sqrt(9 * cmid), seed=4)
+            b1 = _rand(cout, seed=5) * 0.1
+            x16 = _planes(xf, split)
+            w0, w1 = _planes(w0f.reshape(cmid_pad, -1), split), _planes(w1f.reshape(cout, -1), split)
+            g = torch.Generator().manual_seed(7)
+            b_ids = torch.randint(0, B, (M,), generator=g).sort().values
+            j_ids = torch.randint(0, hc * wc, (M,), generator=g)
+            j_ids[: min(M, 4)] = torch.tensor([0, wc - 1, (hc - 1) * wc, hc * wc - 1])[: min(M, 4)]   # corners
+            b_ids, j_ids = b_ids.to(DEV), j_ids.to(DEV)
+            # dense reference on the same engine
+            t_d = torch.empty(B, H, W, pl * cmid_pad, device=DEV, dtype=torch.half)
+            o_d = torch.empty(B, H, W, pl * cout, device=DEV, dtype=torch.half)
+            ops.conv2d_nhwc(x16, w0, b0, t_d, 3, 1, split, 2)
+            ops.conv2d_nhwc(t_d, w1, b1, o_d, 3, 1, split, 0)
+            cap = M + 5 if dyn else M
+            count = torch.tensor([M], dtype=torch.int32, device=DEV) if dyn else None
+            bi = torch.cat([b_ids, b_ids.new_zeros(cap - M)]) if dyn else b_ids
+            ji = torch.cat([j_ids, j_ids.new_zeros(cap - M)]) if dyn else j_ids
+            t_w = torch.full((cap, 7, 8, pl * cmid_pad), float("nan"), device=DEV, dtype=torch.half)
+            o_w = torch.full((cap, 5, 8, pl * cout), float("nan"), device=DEV, dtype=torch.half)
+            ops.conv_win(x16, w0, b0, t_w, 7, split, cap, act=2, b_ids=bi, j_ids=ji, wc=wc, stride=4, org=-3,
+                         count=count)
+            ops.conv_win(t_w, w1, b1, o_w, 5, split, cap, count=count)
+            torch.cuda.synchronize()
+            cy, cx = (j_ids // wc).cpu(), (j_ids % wc).cpu()
+            bad_t = bad_o = 0
+            for m in range(M):
+                for (win, org, got, dense) in ((7, -3, t_w, t_d), (5, -2, o_w, o_d)):
+                    for ly in range(win):
+                        for lx in range(win):
+                            y, x = 4 * int(cy[m]) + org + ly, 4 * int(cx[m]) + org + lx
+                            inside = 0 <= y < H and 0 <= x < W
+                            if win == 5 and not inside:
+                                continue      # the gather never reads these
+                            want = dense[int(b_ids[m]), y, x] if inside else torch.zeros_like(got[m, ly, lx])
+                            if not torch.equal(got[m, ly, lx], want):
+                                if win == 7:
+                                    bad_t += 1
+                                else:
+                                    bad_o += 1
+            assert bad_t == 0 and bad_o == 0, (f"conv_win split={split} B={B} {H}x{W} M={M} dyn={dyn}: {bad_t} window "
+                                               f"positions of conv A and {bad_o} of conv B differ from the dense conv")
+            if dyn:
+                assert torch.isnan(o_w[M:].float()).all(), "rows past the device-side match count were written"
+            # and the dense engine result itself against fp64 torch (layer1_outconv2 shape)
+            ref = F.leaky_relu(F.conv2d(_q(xf, split).double().permute(0, 3, 1, 2),
+                                        _q(w0f, split).double().permute(0, 3, 1, 2), b0.double(), padding=1), 0.01)
+            _close(f"conv_win dense-ref split={split}", _unplanes(t_d, split), ref.permute(0, 2, 3, 1).float(),
+                   *_tol(split, (2e-3, 3e-3), (2e-5, 2e-5)))
+            print(f"conv_win split={split} B={B} {H}x{W} M={M} dyn={dyn}: windows bit-equal to the dense conv")
+
+
 def check_sim():
     for split in (0, 1):
         for (B, L, S, K) in [(2, 700, 520, 256), (1, 300, 100, 256), (1, 5000, 4096, 256)]:
@@ -429,7 +500,7 @@ def check_fine():
         x32 = torch.empty(M * 26, 128, device=DEV)
         x16 = torch.empty(M * 26, pl * 128, device=DEV, dtype=torch.half)
         _lib.call("opp_fine_gather", _lib.ptr(fine), _lib.ptr(desc), _lib.ptr(b_ids), _lib.ptr(i_ids),
-                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, 0, None, _lib.stream())
+                  _lib.ptr(j_ids), _lib.ptr(x32), _lib.ptr(x16), M, hf, wf, wc, 4, N, split, 0, 0, None, _lib.stream())
         torch.cuda.synchronize()
         unf = F.unfold(_q(finef, split).permute(0, 3, 1, 2), kernel_size=5, stride=4, padding=2)
         unf = unf.view(B, 128, 25, -1).permute(0, 3, 2, 1)  # n l ww c
@@ -698,6 +769,7 @@ CHECKS = {
     "linear_q": check_linear_q,
     "linear_act_shared": check_linear_act_shared,
     "conv": check_conv,
+    "conv_win": check_conv_win,
     "sim": check_sim,
     "conv1_gemm": check_conv1_gemm,
     "kpt_encode": check_kpt_encode,

@@ -226,6 +226,38 @@ def test_cuda_graph_mode_is_bit_identical():
         m.clear_bank()
 
 
+def test_fine_windows_path_equals_dense_map():
+    """layer1_outconv2 evaluated on the match windows only (fine_windows "sparse") returns the same
+    bits as the dense fine map ("dense"), eager and under CUDA graphs; "auto" picks by match count.
+    (border_rm keeps matches two cells away from the border, so the zero-padding branch of the
+    window kernels is exercised by kernel_checks.check_conv_win, not here.)"""
+    sd = _sd()
+    m = parity.cuda_model()
+    keys = ("b_ids", "i_ids", "j_ids", "mconf", "expec_f", "mkpts_query_f")
+    cases = [workload.planted_workload(sd, 512, 512, 5000, 3000, batch=2)[0],
+             workload.planted_workload(sd, 480, 640, 3000, 2500, batch=1)[0],
+             workload.planted_workload(sd, 64, 96, 900, 60, batch=3)[0]]
+    try:
+        for d in cases:
+            m.fine_windows = "dense"
+            dense = parity.run_cuda(d)
+            assert dense["b_ids"].numel() > 0
+            m.fine_windows = "sparse"
+            sparse = parity.run_cuda(d)
+            m.enable_cuda_graphs(True)
+            graph = parity.run_cuda(d)
+            m.enable_cuda_graphs(False)
+            m.fine_windows = "auto"
+            auto = parity.run_cuda(d)
+            for k in keys:
+                assert torch.equal(dense[k], sparse[k]), f"sparse windows: {k} differs from the dense map"
+                assert torch.equal(dense[k], graph[k]), f"sparse windows under graphs: {k} differs"
+                assert torch.equal(dense[k], auto[k]), f"auto: {k} differs"
+    finally:
+        m.fine_windows = "auto"
+        m.enable_cuda_graphs(False)
+
+
 def test_workspace_is_bounded_across_shapes():
     """Different point counts / image sizes reuse one allocation per buffer name (high-water mark)."""
     m = parity.cuda_model()
