@@ -218,7 +218,7 @@ class _OutPack:
     kernel) instead of one per output tensor."""
 
     def __init__(self, nbytes, dev):
-        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.buf = torch.empty((nbytes + 15) & ~15, dtype=torch.uint8, device=dev)
         self.fields = []
         self._off = 0
 
@@ -238,8 +238,19 @@ class _OutPack:
         self._off = off + n
         return self.buf[off:off + n].view(dtype).view(shape)
 
-    def views(self, buf):
-        return {k: buf[off:off + n].view(dt).view(shape) for k, off, n, dt, shape in self.fields}
+    def views(self, buf, M):
+        """The first M rows of every field of `buf` (a clone of self.buf): one typed alias of the
+        buffer per dtype + one as_strided per field (this runs on the host after the forward's only
+        sync, so every tensor op here is latency)."""
+        bases, out = {}, {}
+        for k, off, n, dt, shape in self.fields:
+            base = bases.get(dt)
+            if base is None:
+                base = bases[dt] = buf.view(dt)
+            tail = shape[1:]
+            stride = (tail[0], 1) if tail else (1,)
+            out[k] = torch.as_strided(base, (M,) + tail, stride, off // dt.itemsize)
+        return out
 
 
 class _Engine(nn.Module):
@@ -789,7 +800,7 @@ class OnePosePlus_model(_Engine):
         f2()
         cur.wait_stream(side)
 
-    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None, pack=None):
+    def _coarse_matching(self, q2, d3, bank, img_scale, B, N, hc, wc, cell, out, qmask=None, pack=None, side=None):
         """CoarseMatching.forward + get_coarse_match (coarse_matching.py:76-242), inference branch.
         Enqueues everything up to the ordered match lists (capacity B*min(N,S)) and the device-side
         match count; nothing here synchronises.  Fills `out` with the full-capacity tensors."""
@@ -812,7 +823,7 @@ class OnePosePlus_model(_Engine):
             col_m = self._buf("lse_col_m", (B, groups, S), f32, dev)
             col_s = self._buf("lse_col_s", (B, groups, S), f32, dev)
             ops.sim_lse_cols(d3, q2, B, N, S, 256, scale, pm_pt, ps_pt, lse_pt, col_m, col_s, lse_px, split,
-                             col_mask=qmask)
+                             col_mask=qmask, side_stream=side)
         else:
             pm_px = self._buf("pm_px", (B * S, tl), f32, dev)
             ps_px = self._buf("ps_px", (B * S, tl), f32, dev)
@@ -1052,7 +1063,8 @@ class OnePosePlus_model(_Engine):
         small = B * (max(hc * wc, N) // 256 + 1) <= 37
         if os.environ.get("OPP_B200_TWO_STREAMS") == "0":   # A/B switch for the latency probe
             small = False
-        self._side_stream = self._aux_stream(img.device) if (dynamic and small) else None
+        side = self._aux_stream(img.device) if (dynamic and small) else None
+        self._side_stream = side
         try:
             q2, d3 = self._coarse_transformer(q2, bank, B, hc * wc, N, qmask)
         finally:
@@ -1066,7 +1078,7 @@ class OnePosePlus_model(_Engine):
             pack = _OutPack(_OutPack.nbytes(cap, fcap), img.device)
             out["gt_mask"] = pack.new("gt_mask", (cap,), torch.bool)   # zeroed once by _replay, never written
         count, cap = self._coarse_matching(q2, d3, bank, img_scale, B, N, hc, wc, float(H / hc), out, qmask,
-                                           pack=pack)
+                                           pack=pack, side=side)
         ids = (out["b_ids"], out["i_ids"], out["j_ids"], out["mkpts_query_c"])
         hf, wf = fine_in.shape[1:3]
         if fpn_stream is not None:
@@ -1168,7 +1180,8 @@ class OnePosePlus_model(_Engine):
         torch.cuda.current_stream().synchronize()        # the only host sync, after everything is queued
         M = min(int(ent["count"][0]), src["fcap"])
         pack = src["pack"]
-        out = {k: v[:M] for k, v in pack.views(pack.buf.clone()).items()}   # one copy kernel
+        out = pack.views(pack.buf.clone(), M)    # one copy kernel
+        out["sized"] = True
         out["conf_matrix"] = None
         if torch.is_tensor(src["conf_matrix"]):
             out["conf_matrix"] = src["conf_matrix"].clone()
@@ -1180,19 +1193,21 @@ class OnePosePlus_model(_Engine):
         """Write the reference's output keys (coarse_matching.py:231-241, fine_matching.py:46-55,107-110)."""
         if out["conf_matrix"] is not None:
             data["conf_matrix"] = out["conf_matrix"]
-        b_ids = out["b_ids"][:M]
+        # graph mode hands in tensors that are already M rows long (sized=True)
+        cut = (lambda t: t) if out.get("sized") else (lambda t: t[:M])
+        b_ids = cut(out["b_ids"])
         data.update({
-            "b_ids": b_ids, "i_ids": out["i_ids"][:M], "j_ids": out["j_ids"][:M],
-            "gt_mask": out["gt_mask"][:M] if "gt_mask" in out else torch.zeros(M, dtype=torch.bool, device=dev),
-            "m_bids": b_ids, "mkpts_3d_db": out["mkpts_3d_db"][:M], "mkpts_query_c": out["mkpts_query_c"][:M],
-            "mconf": out["mconf"][:M],
+            "b_ids": b_ids, "i_ids": cut(out["i_ids"]), "j_ids": cut(out["j_ids"]),
+            "gt_mask": cut(out["gt_mask"]) if "gt_mask" in out else torch.zeros(M, dtype=torch.bool, device=dev),
+            "m_bids": b_ids, "mkpts_3d_db": cut(out["mkpts_3d_db"]), "mkpts_query_c": cut(out["mkpts_query_c"]),
+            "mconf": cut(out["mconf"]),
         })
         if not fine_on:
             data["mkpts_query_f"] = data["mkpts_query_c"]
         elif M == 0:
             data.update({"expec_f": torch.empty(0, 3, device=dev), "mkpts_query_f": data["mkpts_query_c"]})
         else:
-            data.update({"expec_f": out["expec_f"][:M], "mkpts_query_f": out["mkpts_query_f"][:M]})
+            data.update({"expec_f": cut(out["expec_f"]), "mkpts_query_f": cut(out["mkpts_query_f"])})
 
 
 class LazyConfMatrix:

@@ -171,17 +171,26 @@ def sim_conf(a, b, lse_own, lse_other, own_is_pt, conf, batches, rows, cols, k, 
 
 
 def sim_lse_cols(a, b, batches, rows, cols, k, scale, part_m, part_s, lse_rows, col_m, col_s, lse_cols,
-                 split, col_mask=None):
+                 split, col_mask=None, side_stream=None):
     """lse over columns for every row (as sim_lse) AND lse over rows for every column, one GEMM pass.
-    col_mask uint8 [batches, cols]: masked columns (0) get sim - 1e9 and lse_cols = +inf (conf = 0)."""
+    col_mask uint8 [batches, cols]: masked columns (0) get sim - 1e9 and lse_cols = +inf (conf = 0).
+    side_stream (latency mode): the two independent finalisers run side by side."""
     _chk(col_mask, torch.uint8, "col_mask")
     tiles = sim_tiles(cols)
     groups = (rows + 31) // 32
     call("opp_sim_lse_cols", ptr(a), ptr(b), ptr(part_m), ptr(part_s), ptr(col_m), ptr(col_s), batches,
          rows, cols, k, float(scale), int(split), ptr(col_mask), stream())
-    call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse_rows), batches * rows, tiles, stream())
+    if side_stream is not None:
+        cur = torch.cuda.current_stream()
+        side_stream.wait_stream(cur)
+        with torch.cuda.stream(side_stream):
+            call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse_rows), batches * rows, tiles, stream())
+    else:
+        call("opp_lse_finalize", ptr(part_m), ptr(part_s), ptr(lse_rows), batches * rows, tiles, stream())
     call("opp_lse_col_finalize", ptr(col_m), ptr(col_s), ptr(lse_cols), batches, groups, cols, ptr(col_mask),
          stream())
+    if side_stream is not None:
+        cur.wait_stream(side_stream)
 
 
 def sim_conf_colmax(a, b, lse_own, lse_other, conf, batches, rows, cols, k, scale, part_val, part_idx,
