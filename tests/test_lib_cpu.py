@@ -253,3 +253,35 @@ def test_input_validation_raises_like_the_reference_would():
     d = {k: v for k, v in good.items() if k not in ("keypoints3d",)}
     with pytest.raises(KeyError, match="set_bank"):
         m._check_inputs(d)
+
+
+def test_out_pack_views_and_window_policy():
+    """Host logic of the latency mode and of the sparse fine head: the per-match outputs carved out
+    of one byte buffer come back as contiguous M-row tensors of the right dtype from a clone, and
+    the windows-vs-dense policy switches at the match count where the tile counts cross."""
+    from onepose_plus_plus_b200.model import OnePosePlus_model, _OutPack
+    cap, fcap = 50, 40
+    p = _OutPack(_OutPack.nbytes(cap, fcap), "cpu")
+    spec = (("gt_mask", (cap,), torch.bool), ("b_ids", (cap,), torch.int64), ("i_ids", (cap,), torch.int64),
+            ("j_ids", (cap,), torch.int64), ("mconf", (cap,), torch.float32), ("mkpts_3d_db", (cap, 3), torch.float32),
+            ("mkpts_query_c", (cap, 2), torch.float32), ("expec_f", (fcap, 3), torch.float32),
+            ("mkpts_query_f", (fcap, 2), torch.float32))
+    t = {k: p.new(k, sh, dt) for k, sh, dt in spec}
+    assert p._off <= p.buf.numel()
+    g = torch.Generator().manual_seed(0)
+    for k, sh, dt in spec:
+        if dt == torch.bool:
+            t[k].zero_()
+        elif dt == torch.int64:
+            t[k].copy_(torch.randint(0, 1 << 40, sh, generator=g))
+        else:
+            t[k].copy_(torch.randn(sh, generator=g))
+    for M in (0, 1, 17, 40):
+        v = p.views(p.buf.clone(), M)
+        for k, sh, dt in spec:
+            assert v[k].dtype == dt and v[k].shape == (M,) + tuple(sh[1:]) and v[k].is_contiguous()
+            assert torch.equal(v[k], t[k][:M])
+    pay = OnePosePlus_model._windows_pay
+    # 256x256 fine map: 512 dense M tiles per image and conv; windows: 2 (3) matches per tile
+    assert pay(None, 372 * 64, 64, 256, 256) and pay(None, 900, 1, 256, 256)
+    assert not pay(None, 1300, 1, 256, 256) and not pay(None, 4096, 1, 256, 256)
