@@ -105,7 +105,7 @@ def timing(label):
         "ops_ms": {k: round(v[1], 3) for k, v in sorted(rows.items(), key=lambda kv_: -kv_[1][1])}}
 
 
-# options: C-ABI switches (opp_set_option) except "colmax" / "lse_cols", host-flow switches of the
+# options: (historic: C-ABI switches, since removed) except "colmax" / "lse_cols", host-flow switches of the
 # model (column maxima of conf / column log-sum-exp from the first pass instead of a second GEMM).  Every config
 # starts from the defaults; its label lists the options it turns on.
 EXPERIMENTAL_CHECK = {}
