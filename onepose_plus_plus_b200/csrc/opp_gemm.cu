@@ -469,6 +469,8 @@ int opp_conv_win(const void* in, const void* w, const float* bias, void* out, co
   OPP_REQUIRE(c_in_pad % 16 == 0 && c_out_pad % 16 == 0 && c_out_pad <= 256,
               "channel counts must be padded to multiples of 16 (got %d -> %d)", c_in_pad, c_out_pad);
   OPP_REQUIRE(matches >= 0 && (j_ids == nullptr) == (b_ids == nullptr), "bad match list");
+  OPP_REQUIRE(!j_ids || (wc > 0 && stride > 0 && batch > 0 && in_h > 0 && in_w > 0),
+              "dense-input window convolution needs the map size, wc and stride");
   if (matches == 0) return OPP_OK;
   const int planes = split ? 2 : 1;
   TensorMaps maps;
