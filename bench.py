@@ -584,7 +584,7 @@ def main():
             "roofline": {"bound": "tensor",
                          "kernel": "gemm_kernel<A_CONV,EpiConv>: layer1 3x3 conv 128->128 @256x256 (one launch, whole batch)",
                          "achieved": l1_tf, "peak": peak_burst, "unit": "TFLOP/s", "frac": l1_tf / peak_burst,
-                         "traffic": ncu_traffic("EpiConv", 1),
+                         "traffic": ncu_traffic("EpiConv", 0),   # launch 0 = layer1.0.conv1, the launch timed here
                          "peak_source": peak_src.replace("bf16_tflops_sustained", "bf16_tflops (burst: kernel timed alone)"), "ms_per_launch": l1_ms,
                          "algorithmic_flops_per_launch": l1_flops, "mma_passes": passes,
                          "issued_tensor_tflops": l1_tf * passes, "issued_frac": l1_tf * passes / peak_burst,
