@@ -258,6 +258,47 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_
       "r"(cta_rank)
       : "memory");
 }
+// the same with release semantics at cluster scope: data written to the peer's shared memory
+// (st_cluster_f32x2) before the arrive is visible to a peer thread that acquires the phase
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint64_t* bar, uint32_t cta_rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta_rank)
+      : "memory");
+}
+// two floats into CTA `cta_rank`'s shared memory, at the offset `local` has in this CTA
+__device__ __forceinline__ void st_cluster_f32x2(void* local, uint32_t cta_rank, float a, float b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.v2.f32 [ra], {%2, %3};\n\t"
+      "}\n" ::"r"(smem_u32(local)),
+      "r"(cta_rank), "f"(a), "f"(b)
+      : "memory");
+}
+// bounded wait with acquire at cluster scope (pairs with mbar_arrive_cluster_release)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

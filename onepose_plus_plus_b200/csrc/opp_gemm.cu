@@ -103,7 +103,7 @@ template <int A_MODE, class Epi, bool DYN = false>
 static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Params& ep,
                   cudaStream_t stream, const int* rows_dev = nullptr, int rows_mult = 1) {
   constexpr int kEpiBytes = epi_smem_bytes<Epi>();
-  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair, kEpiBytes);
+  s.stages = gemm_pick_stages(s.block_n, s.k_chunks, s.split, s.pair == 1, kEpiBytes);
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -118,7 +118,7 @@ static int launch(const TensorMaps& maps, GemmShape s, const typename Epi::Param
     }
     if (cap > 1 && s.stages > cap) s.stages = cap;
   }
-  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair, kEpiBytes);
+  const int smem = gemm_smem_bytes(s.stages, s.block_n, s.split, s.pair == 1, kEpiBytes);
   const void* kern;
   if constexpr (DYN) kern = (const void*)gemm_kernel_dyn<A_MODE, Epi>;
   else kern = (const void*)gemm_kernel<A_MODE, Epi>;
@@ -227,6 +227,25 @@ static void split_n_for_latency(GemmShape& s) {
   }
 }
 
+// Latency shapes of the LayerNorm GEMMs (N = 256 must stay in one row for the statistics): when
+// every 128-row M tile can have a 2-CTA cluster of its own, the two CTAs take one 128-column half
+// each (GemmShape.pair = 2) and exchange the row statistics through distributed shared memory —
+// half the MMA and epilogue time per CTA; A is read twice (L2).  $OPP_LN_NSPLIT=0 disables it.
+static void ln_nsplit_cluster(GemmShape& s) {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("OPP_LN_NSPLIT");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on || s.n_total != 256 || s.block_n != 256) return;
+  if ((long long)s.batches * s.m_tiles > num_sms() / 2) return;
+  s.pair = 2;
+  s.cluster = 2;
+  s.msup = s.m_tiles;
+  s.block_n = 128;
+  s.n_tiles = 1;
+}
+
 // common shape / map setup for token-row GEMMs.  With split, every operand row holds two planes:
 // A_i rows are [hi(k_i) | lo(k_i)], W rows are [hi(k0+k1) | lo(k0+k1)].
 static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, const void* a1,
@@ -267,10 +286,11 @@ static int setup_rows(TensorMaps& maps, GemmShape& s, const void* a0, int k0, co
   maps.a[2] = maps.a[0];
   maps.a[3] = maps.a[0];
   pick_grouping(s);
-  if (nsplit_ok) split_n_for_latency(s);
+  if (nsplit_ok == 1) split_n_for_latency(s);
+  if (nsplit_ok == 2) ln_nsplit_cluster(s);
   const long long kt = (long long)planes * (k0 + k1);
   return map_rows(&maps.b, w, kt, n, w_batched ? batches : 1, kt, (long long)n * kt,
-                  s.block_n / s.cluster);
+                  s.pair == 2 ? s.block_n : s.block_n / s.cluster);
 }
 
 }  // namespace opp
@@ -372,7 +392,7 @@ int opp_linear_ln(const void* a0, int k0, const void* a1, int k1, const void* w,
   TensorMaps maps;
   GemmShape s;
   OPP_REQUIRE(n == 128 || n == 256, "LayerNorm epilogue needs N in {128,256}, got %d", n);
-  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, w_batched, batches, rows, n, split);
+  int rc = setup_rows(maps, s, a0, k0, a1, k1, w, w_batched, batches, rows, n, split, 16, 0, 2);
   if (rc) return rc;
   OPP_REQUIRE(gamma && beta, "null LayerNorm parameters");
   OPP_REQUIRE(out16 || out32, "no output requested");

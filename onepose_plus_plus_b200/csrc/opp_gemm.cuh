@@ -92,7 +92,10 @@ struct GemmShape {
   int cluster;      // CTAs per cluster (1, 2, 4): they work on adjacent M tiles of the same
                     // (batch, n_tile) in lockstep and share the W tile through TMA multicast
   int msup;         // ceil(m_tiles / cluster)
-  int pair;         // 1: the two CTAs of the cluster form ONE cta_group::2 MMA: 256 x N tile, each
+  int pair;         // 2: "N-split cluster" (latency shapes of the LayerNorm GEMMs): the two CTAs of the
+                    // cluster work on the SAME 128-row M tile, CTA r on columns [r*block_n, +block_n),
+                    // independent pipelines, row statistics exchanged through DSMEM (EpiLN);
+                    // 1: the two CTAs of the cluster form ONE cta_group::2 MMA: 256 x N tile, each
                     // CTA holds 128 rows of A, N/2 rows of W and 128 rows of the accumulator
   int debug_skip;   // TIMING EXPERIMENTS ONLY ($OPP_DEBUG_SKIP): 1 = skip W loads, 2 = skip A loads
   int split;        // operands are (hi|lo) plane pairs; 3 MMAs per K-step
@@ -137,6 +140,7 @@ struct EpiCtx {
   long long sgrow[4];
   unsigned svalid;
   int next_b, next_m_tile;   // the (batch, M tile) this CTA processes next, or next_b = -1
+  uint8_t* extra;            // EpiExtraSmem<Epi>::value bytes (EpiLN: DSMEM exchange slots + 2 mbarriers)
   int it;                    // how many tiles this CTA has processed before this one
 };
 
@@ -152,9 +156,18 @@ template <class E>
 struct EpiWarpStage<E, std::void_t<decltype(E::kWarpStage)>> {
   static constexpr int value = E::kWarpStage;
 };
+// bytes of extra shared memory behind the warp stages: epilogues declare `static constexpr int kExtraSmem`
+template <class E, class = void>
+struct EpiExtraSmem {
+  static constexpr int value = 0;
+};
+template <class E>
+struct EpiExtraSmem<E, std::void_t<decltype(E::kExtraSmem)>> {
+  static constexpr int value = E::kExtraSmem;
+};
 template <class E>
 constexpr int epi_smem_bytes() {
-  return 4096 + 8 * EpiWarpStage<E>::value;   // kEpiParamBytes + kMaxEpiWarps * stage
+  return 4096 + 8 * EpiWarpStage<E>::value + EpiExtraSmem<E>::value;   // kEpiParamBytes + kMaxEpiWarps * stage
 }
 
 // epilogues that look one tile ahead declare `static constexpr bool kNeedsNext`
@@ -423,6 +436,8 @@ struct EpiQ {
 // (transformer.py:86-94: norm1 after merge; norm2 then x + msg).
 struct EpiLN {
   static constexpr int kGroups = OPP_LN_GROUPS;
+  // N-split cluster (GemmShape.pair == 2): 2 x 128 (mean, M2) slots the peer CTA writes into + 2 mbarriers
+  static constexpr int kExtraSmem = 2 * 128 * 8 + 64;
   struct Params {
     const float* gamma;
     const float* beta;
@@ -436,7 +451,7 @@ struct EpiLN {
   };
   __device__ static void prefetch(const Params& p, const GemmShape& s, const EpiCtx& c) {
     if (!p.resid || !c.valid) return;
-    const char* row = reinterpret_cast<const char*>(p.resid + (p.resid_shared ? (long long)c.row : c.grow) * p.ld);
+    const char* row = reinterpret_cast<const char*>(p.resid + (p.resid_shared ? (long long)c.row : c.grow) * p.ld + c.n0);
     for (int o = c.group * 128; o < c.ncols * 2; o += 256) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(row + o));
       if (p.out_lo) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 2 * p.out_lo + o));
@@ -450,10 +465,10 @@ struct EpiLN {
   // instruction = 32 L1 wavefronts at ~2 clk each, which made this epilogue wavefront-bound
   // (28-34 k clk per tile against 6-12 k clk of MMA work).
   __device__ static void run(const Params& p, const GemmShape& s, const EpiCtx& c) {
-    if (c.it == 0) {   // gamma / beta are the same for every tile (single N tile): staged once per CTA
+    if (c.it == 0) {   // gamma / beta of this CTA's columns (the same for every tile): staged once per CTA
       for (int i = c.etid; i < c.ncols; i += 128) {
-        sts32f(c.smem_s + 4 * i, p.gamma[i]);
-        sts32f(c.smem_s + 4 * (256 + i), p.beta[i]);
+        sts32f(c.smem_s + 4 * i, p.gamma[c.n0 + i]);
+        sts32f(c.smem_s + 4 * (256 + i), p.beta[c.n0 + i]);
       }
       epi_sync(c);
     }
@@ -501,7 +516,32 @@ struct EpiLN {
       mean = mean_a + delta * (nb / n);
       m2 = m2a + m2b + delta * delta * (na * nb / n);
     }
-    const float rstd = 1.f / sqrtf(m2 / (float)c.ncols + p.eps);
+    if (s.pair == 2) {
+      // N-split cluster: the other half of every row is in the peer CTA of the cluster (same M tile,
+      // same iteration).  Group 0 writes (mean, M2) of this half into the PEER's slot of this tile
+      // parity and arrives (release.cluster) on the peer's mbarrier; everybody waits on the local
+      // one (acquire.cluster) and merges "columns 0..127 first", so both CTAs get bit-identical
+      // statistics.  Two slots / barriers alternate by tile parity: the peer can be one publish
+      // ahead, never two (its next publish needs ours; the 256-thread barrier that ends run()
+      // keeps our group 1 from still reading the slot by then).
+      const int lane = threadIdx.x & 31;
+      const int par = c.it & 1;
+      float2* slot = reinterpret_cast<float2*>(c.extra) + par * 128 + c.q * 32 + lane;
+      uint64_t* xbar = reinterpret_cast<uint64_t*>(c.extra + 2 * 128 * 8) + par;
+      const uint32_t peer = (uint32_t)(c.n_tile ^ 1);
+      if (c.group == 0) {
+        st_cluster_f32x2(slot, peer, mean, m2);
+        mbar_arrive_cluster_release(xbar, peer);
+      }
+      mbar_wait_cluster(xbar, (uint32_t)((c.it >> 1) & 1));
+      const float2 o = *slot;
+      const float mean_a = c.n_tile == 0 ? mean : o.x, m2a = c.n_tile == 0 ? m2 : o.y;
+      const float mean_b = c.n_tile == 0 ? o.x : mean, m2b = c.n_tile == 0 ? o.y : m2;
+      const float delta = mean_b - mean_a;
+      mean = mean_a + delta * 0.5f;                       // both halves have c.ncols columns
+      m2 = m2a + m2b + delta * delta * (0.5f * (float)c.ncols);
+    }
+    const float rstd = 1.f / sqrtf(m2 / (float)s.n_total + p.eps);
     // a shared residual is indexed by the row inside the batch: rebase the pointer once per tile
     const __half* resid = p.resid;
     if (resid && p.resid_shared) resid -= (long long)c.b * s.rows * p.ld;
@@ -523,7 +563,7 @@ struct EpiLN {
       // every lane takes part in the warp-staged transposes; row validity is per staged row
       if (resid) staged_load_add(c, p.out_lo, pre, v);
       if (p.out32 && c.valid) {
-        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + col);
+        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + c.n0 + col);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           o4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -542,7 +582,7 @@ struct EpiLN {
         }
       }
       if (p.out32) {
-        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + col);
+        float4* o4 = reinterpret_cast<float4*>(p.out32 + c.grow * (long long)s.n_total + c.n0 + col);
 #pragma unroll
         for (int g = 0; g < 8; ++g)
           o4[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
@@ -1184,7 +1224,8 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
   uint8_t* smem = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int planes = s.split ? 2 : 1;
-  const bool pair = s.pair != 0;
+  const bool pair = s.pair == 1;
+  const bool nsc = s.pair == 2;   // N-split cluster: two independent CTAs, same M tile, N half = cluster rank
   const int b_rows = pair ? s.block_n / 2 : s.block_n;   // W rows resident in THIS CTA
   const int b_bytes = b_rows * kBlockK * 2;              // one plane of the (local) W tile
   const int a_stage = kABytes * planes;
@@ -1214,12 +1255,16 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
   const uint32_t tmem_cols = 2 * acc_stride;
   // tile schedule: "super tiles" of `cluster` adjacent M tiles; every CTA of a cluster walks the
   // same sequence, so the multicast W loads and the cross-CTA stage releases stay in lockstep.
-  const int csize = s.cluster;
-  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  // N-split cluster: logically two single-CTA GEMMs (csize 1: no multicast, no shared barriers) that
+  // walk the same tile sequence; `nrank` selects the N half.
+  const int csize = nsc ? 1 : s.cluster;
+  const int prank = s.cluster > 1 ? (int)cluster_ctarank() : 0;   // physical rank in the cluster
+  const int crank = nsc ? 0 : prank;
+  const int nrank = nsc ? prank : 0;
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const bool leader = crank == 0;
-  const int cluster_id = blockIdx.x / csize;
-  const int n_clusters = gridDim.x / csize;
+  const int cluster_id = blockIdx.x / s.cluster;
+  const int n_clusters = gridDim.x / s.cluster;
   const int tiles_per_batch = s.msup * s.n_tiles;
   const int total_tiles = s.batches * tiles_per_batch;
 
@@ -1238,6 +1283,13 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       // every epilogue thread arrives; pair: the threads of both CTAs arrive on the leader's barrier
       mbar_init(&tempty[i], 128 * Epi::kGroups * (pair ? 2 : 1));
     }
+    if constexpr (EpiExtraSmem<Epi>::value > 0) {
+      // EpiLN's DSMEM exchange: the 128 group-0 threads of the peer CTA arrive once per tile
+      uint64_t* xbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(epi_smem) + epi_smem_bytes<Epi>() -
+                                                   EpiExtraSmem<Epi>::value + 2 * 128 * 8);
+      mbar_init(&xbar[0], 128);
+      mbar_init(&xbar[1], 128);
+    }
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -1250,7 +1302,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
     }
   }
   tc_fence_before();
-  if (csize > 1) cluster_sync_all(); else __syncthreads();
+  if (s.cluster > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // programmatic dependent launch: everything above overlapped with the previous kernel's tail;
@@ -1274,7 +1326,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       const int b = t / tiles_per_batch;
       const int r = t - b * tiles_per_batch;
       const int msi = r / s.n_tiles;
-      const int n_tile = r - msi * s.n_tiles;
+      const int n_tile = nsc ? nrank : r - msi * s.n_tiles;
       const int m_tile = msi * csize + crank;
       int ox0 = 0, oy0 = 0;
       if (A_MODE == A_CONV) {
@@ -1521,6 +1573,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
     c.col_step = 32 * Epi::kGroups;
     c.smem = epi_smem + c.group * (kEpiParamBytes / 8);   // 2 KB (512 floats) per group
     c.wstage = reinterpret_cast<uint8_t*>(epi_smem) + kEpiParamBytes + warp * EpiWarpStage<Epi>::value;
+    c.extra = reinterpret_cast<uint8_t*>(epi_smem) + epi_smem_bytes<Epi>() - EpiExtraSmem<Epi>::value;
     c.smem_s = smem_u32(c.smem);
     c.wstage_s = smem_u32(c.wstage);
     int it = 0;
@@ -1530,7 +1583,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       c.b = t / tiles_per_batch;
       const int r = t - c.b * tiles_per_batch;
       const int msi = r / s.n_tiles;
-      c.n_tile = r - msi * s.n_tiles;
+      c.n_tile = nsc ? nrank : r - msi * s.n_tiles;
       c.m_tile = msi * csize + crank;   // may lie past the last M tile: rows are then invalid
       c.n0 = c.n_tile * s.block_n;
       const int rem = s.n_total - c.n0;
@@ -1574,7 +1627,7 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
   pdl_done();
   tc_fence_before();
   // a CTA must outlive every multicast write / remote barrier arrival aimed at it
-  if (csize > 1) cluster_sync_all(); else __syncthreads();
+  if (s.cluster > 1) cluster_sync_all(); else __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     if (pair) tmem_dealloc2(tmem_base, tmem_cols); else tmem_dealloc(tmem_base, tmem_cols);

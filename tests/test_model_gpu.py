@@ -300,13 +300,17 @@ def test_properties_at_baseline_size():
     assert (jy >= 2).all() and (jx >= 2).all(), "top/left border cells are masked"
     conf = a["conf_matrix"]
     assert conf.min().item() >= 0 and conf.max().item() <= 1.0 + 1e-5
-    # image 0 alone gives the same matches as image 0 inside the batch
+    # image 0 alone gives the same matches as image 0 inside the batch.  Not the same bits: at batch 1
+    # the latency tilings are chosen (N-split GEMMs; LayerNorm statistics merged from two column halves
+    # across a CTA cluster), so the fp32 rounding of the statistics differs — a tenth of the parity bar
     single = {k: v[:1].clone() for k, v in data.items()}
     s = parity.run_cuda(single)
     m0 = a["b_ids"] == 0
     assert torch.equal(s["i_ids"], a["i_ids"][m0]) and torch.equal(s["j_ids"], a["j_ids"][m0])
-    assert torch.allclose(s["mconf"], a["mconf"][m0], atol=1e-5)
-    assert torch.allclose(s["mkpts_query_f"], a["mkpts_query_f"][m0], atol=1e-3)
+    d_conf = (s["mconf"] - a["mconf"][m0]).abs().max().item()
+    d_px = (s["mkpts_query_f"] - a["mkpts_query_f"][m0]).abs().max().item()
+    print(f"batch independence: |d mconf| {d_conf:.2e}, |d mkpts_query_f| {d_px:.2e} px")
+    assert d_conf <= 1e-4 and d_px <= 1e-3
 
 
 def test_weights_reload_invalidates_plan():
