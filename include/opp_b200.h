@@ -172,6 +172,9 @@ int opp_full_attention(const void* q, const void* kv, void* out, int batch, int 
  * part fp32 [B][chunks][H][33][32], chunks = opp_kv_chunks(S): per-chunk sum_s K'^T V (rows 0..31)
  * and sum_s K' (row 32) for each of the H = d/32 heads. */
 int opp_kv_chunks(int s);
+/* chunks per batch element as opp_kv_partial / opp_kv_finalize use them for this (S, batch): at
+ * small batches the chunks are shorter so that more CTAs share the stream (size `part` with this) */
+int opp_kv_chunks_b(int s, int batch);
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream);
 

@@ -283,7 +283,8 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const __half* __restrict__ kv16,
-                                                             float* __restrict__ part, int S) {
+                                                             float* __restrict__ part, int S,
+                                                             int kv_chunk) {
   pdl_sync();
   extern __shared__ __align__(16) uint8_t kvm_smem[];
   constexpr int kRowB = SPLIT ? 2048 : 1024;      // [K'(256) V(256)] fp16, x2 planes when split
@@ -294,8 +295,8 @@ __global__ void __launch_bounds__(256) kv_partial_mma_kernel(const __half* __res
   constexpr int kLoB = 1024;                       // byte offset of the lo plane inside a row
   const int chunk = blockIdx.x, b = blockIdx.y, chunks = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int s0 = chunk * kKvChunk;
-  const int cnt = min(kKvChunk, S - s0);
+  const int s0 = chunk * kv_chunk;
+  const int cnt = min(kv_chunk, S - s0);
   const int nsteps = (cnt + kKvmTok - 1) / kKvmTok;
   const uint8_t* src = reinterpret_cast<const uint8_t*>(kv16) + ((long long)b * S + s0) * kRowB;
   const uint32_t sbase = smem_u32(kvm_smem);
@@ -457,16 +458,17 @@ __global__ void lse_finalize_kernel(const float* __restrict__ pm, const float* _
 }
 
 // column side of opp_sim_lse_cols: lse[b][s] = logsumexp over the row groups of (col_m, col_s).
-// Block = 32 columns x 8 group slices (coalesced 128 B rows; 8 independent load chains per column
-// instead of one thread walking all ~150 groups: the old form took 63 us for ONE image), merged
-// through shared memory.
-__global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __restrict__ cm,
+// Block = 32 columns x kLseColSlices group slices (coalesced 128 B rows; that many independent load
+// chains per column instead of one thread walking all ~150 groups: the first form took 63 us for
+// ONE image, 8 slices 22 us), merged through shared memory.
+constexpr int kLseColSlices = 32;
+__global__ void __launch_bounds__(32 * kLseColSlices) lse_col_finalize_kernel(const float* __restrict__ cm,
                                                                const float* __restrict__ cs,
                                                                float* __restrict__ lse, int batches,
                                                                int groups, int cols,
                                                                const unsigned char* __restrict__ col_mask) {
   pdl_sync();
-  __shared__ float m_s[8][32], s_s[8][32];
+  __shared__ float m_s[kLseColSlices][32], s_s[kLseColSlices][32];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   const int sidx = blockIdx.x * 32 + lane;
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __re
   if (sidx < cols) {
     const float* pm = cm + (long long)b * groups * cols + sidx;
     const float* ps = cs + (long long)b * groups * cols + sidx;
-    for (int g = slice; g < groups; g += 8) {
+    for (int g = slice; g < groups; g += kLseColSlices) {
       const float pg = pm[(long long)g * cols];
       if (pg == -INFINITY) continue;
       const float sg = ps[(long long)g * cols];
@@ -499,10 +501,10 @@ __global__ void __launch_bounds__(256) lse_col_finalize_kernel(const float* __re
     }
     float mm = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) mm = fmaxf(mm, m_s[k][lane]);
+    for (int k = 0; k < kLseColSlices; ++k) mm = fmaxf(mm, m_s[k][lane]);
     float tot = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < kLseColSlices; ++k)
       if (m_s[k][lane] != -INFINITY) tot += s_s[k][lane] * expf(m_s[k][lane] - mm);
     lse[idx] = mm + logf(tot);
   }
@@ -745,13 +747,20 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
   store_split1(x16 + row0 * ld, c, d, lo_off);
   // windows: `fine` holds the compact per-match windows of opp_conv_win, [m][5][8][ld]
   const __half* fb = windows ? fine + (long long)m * 40 * ld : fine + b * hf * wf * ld;
+  // all 25 window loads in flight before the first store (one block per match: the dependent
+  // load -> store pairs of the rolled loop were 25 serial round trips)
+  float v[25];
+#pragma unroll
   for (int ww = 0; ww < 25; ++ww) {
     const int y = jy * stride + ww / 5 - 2, x = jx * stride + ww % 5 - 2;
-    float v = 0.f;
+    v[ww] = 0.f;
     if (y >= 0 && y < hf && x >= 0 && x < wf)
-      v = load_split1(fb + (windows ? (long long)((ww / 5) * 8 + ww % 5) : (long long)y * wf + x) * ld, c, lo_off);
-    if (x32) x32[(row0 + 1 + ww) * 128 + c] = v;
-    store_split1(x16 + (row0 + 1 + ww) * ld, c, v, lo_off);
+      v[ww] = load_split1(fb + (windows ? (long long)((ww / 5) * 8 + ww % 5) : (long long)y * wf + x) * ld, c, lo_off);
+  }
+#pragma unroll
+  for (int ww = 0; ww < 25; ++ww) {
+    if (x32) x32[(row0 + 1 + ww) * 128 + c] = v[ww];
+    store_split1(x16 + (row0 + 1 + ww) * ld, c, v[ww], lo_off);
   }
 }
 
@@ -1316,13 +1325,24 @@ int opp_kpt_encode(const float* kpts, const float* stats, const float* desc, con
   return OPP_OK;
 }
 
+// tokens per CTA of kv_partial: 256 (least partial-state traffic for kv_finalize) unless that leaves
+// fewer than 64 CTAs in the grid (batch 1-2), then 128: half the serial loop per CTA
+static int kv_chunk_tokens(int s, int batch) {
+  const long long ctas = (long long)batch * ((s + kKvChunk - 1) / kKvChunk);
+  return ctas < 64 ? kKvChunk / 2 : kKvChunk;
+}
 int opp_kv_chunks(int s) { return (s + kKvChunk - 1) / kKvChunk; }
+int opp_kv_chunks_b(int s, int batch) {
+  const int c = kv_chunk_tokens(s, batch);
+  return (s + c - 1) / c;
+}
 
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream) {
   OPP_REQUIRE(kv16 && part, "null pointer");
   OPP_REQUIRE(d == 256, "kv_partial is built for d = 256 (8 heads x 32), got %d", d);
-  dim3 grid((s + kKvChunk - 1) / kKvChunk, batch);
+  const int kv_chunk = kv_chunk_tokens(s, batch);
+  dim3 grid((s + kv_chunk - 1) / kv_chunk, batch);
   const int smem = kKvmStages * kKvmTok * ((split ? 2048 : 1024) + 16);
   static unsigned long long attr_done = 0;   // per device
   int dev = 0;
@@ -1335,9 +1355,9 @@ int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int s
     attr_done |= 1ull << dev;
   }
   if (split)
-    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<true>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s));
+    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<true>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s, kv_chunk));
   else
-    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s));
+    OPP_CHECK_CUDA(opp::launch_pdl(kv_partial_mma_kernel<false>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)kv16, part, s, kv_chunk));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;
 }
@@ -1366,7 +1386,7 @@ int opp_lse_finalize(const float* part_m, const float* part_s, float* lse, long 
 int opp_lse_col_finalize(const float* col_m, const float* col_s, float* lse, int batches, int groups,
                          int cols, const unsigned char* col_mask, opp_stream_t stream) {
   OPP_REQUIRE(col_m && col_s && lse && batches > 0 && groups > 0 && cols > 0, "bad lse_col_finalize arguments");
-  OPP_CHECK_CUDA(opp::launch_pdl(lse_col_finalize_kernel, dim3(dim3((cols + 31) / 32, batches)), dim3(256), 0, (cudaStream_t)stream, 
+  OPP_CHECK_CUDA(opp::launch_pdl(lse_col_finalize_kernel, dim3(dim3((cols + 31) / 32, batches)), dim3(32 * kLseColSlices), 0, (cudaStream_t)stream, 
       col_m, col_s, lse, batches, groups, cols, col_mask));
   OPP_CHECK_CUDA(cudaGetLastError());
   return OPP_OK;

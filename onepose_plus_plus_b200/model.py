@@ -11,7 +11,9 @@ Scope: inference (``eval()``, no autograd), linear attention; extens
 path (resident bank, uint8 frames, lazy ``conf_matrix``, CUDA-graph replay) are documented at
 ``forward`` / ``set_bank`` / ``enable_cuda_graphs``.
 """
+import contextlib
 import math
+import operator
 import os
 
 import torch
@@ -212,6 +214,9 @@ def _pad16(c):
 # ---------------------------------------------------------------------------------------------
 # the model
 # ---------------------------------------------------------------------------------------------
+_VERSION_OF = operator.attrgetter("_version")
+
+
 class _OutPack:
     """The per-match outputs of a forward carved out of ONE byte buffer.  In CUDA-graph mode the
     graph owns the buffers it writes, so the caller gets copies: one clone of the pack (one
@@ -305,7 +310,7 @@ class _Engine(nn.Module):
         ts = self._sig_tensors
         if ts is None:
             ts = self._sig_tensors = list(self.state_dict(keep_vars=True).values())
-        return (self.precision, self._apply_epoch, sum(t._version for t in ts))
+        return (self.precision, self._apply_epoch, sum(map(_VERSION_OF, ts)))
 
     def load_state_dict(self, *args, **kwargs):
         self._sig_tensors = None
@@ -523,7 +528,7 @@ class _Engine(nn.Module):
         kv16 = self._buf(tag + "kv16", (B * ls, (2 if kv_split else 1) * 512), f16, dev)
         ops.linear_act(src, None, L["wkv"], kv16, B * ls, 2, 256, split, out_split=kv_split,
                        row_mask=src_mask)
-        part = self._buf(tag + "part", (B, ops.kv_chunks(ls), 8, 33, 32), torch.float32, dev)
+        part = self._buf(tag + "part", (B, ops.kv_chunks(ls, B), 8, 33, 32), torch.float32, dev)
         mt = self._buf(tag + "mt", (B, 256, pl * 256), f16, dev)
         ksum = self._buf(tag + "ksum", (B, 256), torch.float32, dev)
         ops.kv_state(kv16, part, L["merge32"], mt, ksum, B, ls, 256, ls, split, kv_split=kv_split)
@@ -1006,7 +1011,9 @@ class OnePosePlus_model(_Engine):
             qmask = (qmask.to(img.device) != 0).to(torch.uint8).reshape(-1).contiguous()
         self._fwd_count += 1
         # kernels are enqueued on the current stream of the tensors' device
-        with torch.no_grad(), torch.cuda.device(img.device):
+        # (switching the current device costs two driver calls per forward: only when it is not current)
+        on_dev = contextlib.nullcontext() if torch.cuda.current_device() == img.device.index else torch.cuda.device(img.device)
+        with torch.no_grad(), on_dev:
             dev = img.device
             self._ensure_plan(dev)
             if img.dtype != torch.uint8 and img.dtype != torch.float32:

@@ -138,15 +138,18 @@ def full_attention(q16, kv16, out, batch, l, s, heads, head_dim, split):
     return out
 
 
-def kv_chunks(s):
-    return _lib.load().opp_kv_chunks(s)
+def kv_chunks(s, batches=None):
+    """Chunks per batch element of the K'V partial states (size of the `part` buffer)."""
+    if batches is None:
+        return _lib.load().opp_kv_chunks(s)
+    return _lib.load().opp_kv_chunks_b(s, batches)
 
 
 def kv_state(kv16, part, merge_w, mt, ksum, batches, s, d, v_len, split, kv_split=None):
     """kv_split: plane mode of the kv16 rows when it differs from the mode of the mt output."""
     kv_split = split if kv_split is None else kv_split
     call("opp_kv_partial", ptr(kv16), ptr(part), batches, s, d, int(kv_split), stream())
-    call("opp_kv_finalize", ptr(part), ptr(merge_w), ptr(mt), ptr(ksum), batches, kv_chunks(s), d,
+    call("opp_kv_finalize", ptr(part), ptr(merge_w), ptr(mt), ptr(ksum), batches, kv_chunks(s, batches), d,
          float(v_len), int(split), stream())
 
 

@@ -417,7 +417,7 @@ def check_kv_state():
         kvf = torch.cat([_rand(B, S, d, seed=1).abs() + 0.1, _rand(B, S, d, seed=2)], 2)
         kv = _planes(kvf, split)
         mw = _rand(d, d, scale=0.06, seed=3)
-        chunks = _lib.load().opp_kv_chunks(S)
+        chunks = _lib.load().opp_kv_chunks_b(S, B)
         pl = 2 if split else 1
         part = torch.empty(B, chunks, 8, 33, 32, device=DEV)
         mt = torch.empty(B, d, pl * d, device=DEV, dtype=torch.half)
@@ -749,7 +749,7 @@ def check_kv_single_plane():
     ref[:, :d] = _elu1(ref[:, :d])
     _close("linear_act_out1", kv, ref, 6e-4, 1e-4)
     mw = _rand(d, d, scale=0.06, seed=3)
-    chunks = _lib.load().opp_kv_chunks(S)
+    chunks = _lib.load().opp_kv_chunks_b(S, B)
     part = torch.empty(B, chunks, 8, 33, 32, device=DEV)
     mt = torch.empty(B, d, 2 * d, device=DEV, dtype=torch.half)
     ksum = torch.empty(B, d, device=DEV)

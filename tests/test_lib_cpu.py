@@ -37,6 +37,8 @@ def test_version_and_tiles_without_gpu():
     g = lib.opp_sim_tiles(100)   # partial slots per column tile = epilogue warp groups (1 or 2)
     assert g in (1, 2) and lib.opp_sim_tiles(4096) == 16 * g and lib.opp_sim_tiles(5000) == 20 * g
     assert lib.opp_kv_chunks(4096) * 256 >= 4096
+    assert lib.opp_kv_chunks_b(4096, 64) == lib.opp_kv_chunks(4096)      # enough CTAs: 256-token chunks
+    assert lib.opp_kv_chunks_b(4096, 1) == 2 * lib.opp_kv_chunks(4096)   # batch 1: 128-token chunks
 
 
 def test_state_dict_is_the_reference_layout():
@@ -119,7 +121,7 @@ def _stub_ops(monkeypatch, calls, count_value):
     for n in names:
         monkeypatch.setattr(ops, n, stub(n))
     monkeypatch.setattr(ops, "sim_tiles", lambda c: 2 * ((c + 255) // 256))
-    monkeypatch.setattr(ops, "kv_chunks", lambda s_: (s_ + 127) // 128)
+    monkeypatch.setattr(ops, "kv_chunks", lambda s_, b_=None: (s_ + 127) // 128)
 
 
 def test_coarse_matching_host_flow(monkeypatch):
