@@ -9,6 +9,7 @@ tail -24 $O/bench.err | head -14; cut -c1-400 $O/bench.json
 timeout 1200 ncu --set full --clock-control none --profile-from-start off --csv --page raw \
     --log-file $O/ncu_b64_raw.csv python scripts/profile_step.py 64 > $O/ncu_b64.log 2>&1
 tail -1 $O/ncu_b64.log; ls -la $O/ncu_b64_raw.csv
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_small.py > $O/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $O/memcheck.log; tail -4 $O/memcheck.log
 timeout 300 python scripts/latency_probe.py 50 2>&1 | tail -1 | tee -a $O/latency.jsonl
 timeout 300 python scripts/segment_probe.py 50 2>&1 | tail -1 | tee -a $O/segments.jsonl
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
