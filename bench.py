@@ -376,7 +376,10 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), d, t0, time.time()
 
-    for _ in range(max(args.warmup, 3)):
+    # 5 untimed settle steps (allocator high-water marks, power state: the first timed region of a
+    # fresh process was seen 8 % slower than the later ones of the same run on one box), then the
+    # W >= 3 warm-up steps of the contract
+    for _ in range(5 + max(args.warmup, 3)):
         d = step_resident()
     _lib.LAUNCHES = 0
     ms, d, t0, t1 = timed(step_resident, args.steps)
@@ -563,6 +566,7 @@ def main():
                                    f"5000-pt bank (NCCL-broadcast once when N>1)",
                        "global_batch": B * world, "matches_per_image": m_per_img,
                        "l2": "per-step working set (activations >= 1 GB) exceeds the 126 MB L2; no explicit flush",
+                       "settle_steps": 5,
                        "conf_matrix": "materialised fp32 every step (reference API); see conf_lazy for the "
                                       "store-free mode"},
             "clocks": clocks,
