@@ -47,17 +47,57 @@ def parse():
 # clocks sampler (B200_PROFILING.md: sample nvidia-smi DURING the timed region)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons of the GPU while the timed region runs (B200_PROFILING.md's clocks
+    line).  Read through NVML in this process (the counters nvidia-smi prints; a poll costs tens of
+    microseconds) — a looping `nvidia-smi -lms 100` child was seen to slow the eager-mode timed region
+    it overlapped by 5-8 % on some boxes (driver lock held during its queries) while the later,
+    unsampled regions of the same run were not affected.  Falls back to `nvidia-smi -lms 200`."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+            ("sw_power_cap", 0x4))     # nvmlClocksEventReason* masks
 
     def __init__(self, index):
-        self.rows = []
+        self.rows = []      # (time, sm_mhz, max_mhz, set(reasons))
         self.proc = None
+        self.source = None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ent = vis.split(",")[index].strip()
+                phys = int(ent) if ent.isdigit() else None
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys) if phys is not None else pynvml.nvmlDeviceGetHandleByUUID(ent)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        mask = int(reasons_fn(h))
+                        self.rows.append((time.time(), sm, mx, {n for n, b in self.BITS if mask & b}))
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self._stop.wait(0.1)
+            poll_once_ok = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)) > 0
+            if poll_once_ok:
+                self.source = "nvml"
+                self.t = threading.Thread(target=poll, daemon=True)
+                self.t.start()
+                return
+        except Exception:  # noqa: BLE001  (no NVML: use the CLI)
+            pass
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 200"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -65,29 +105,30 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
-
-    def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 or ts > t1:
-                continue
             f = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(f[0]))
-                mx = float(f[1])
+                sm, mx = float(f[0]), float(f[1])
             except (ValueError, IndexError):
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), f[2:6]):
-                if v == "Active":
-                    reasons.add(name)
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((time.time(), sm, mx, {n for n, v in zip(names, f[2:6]) if v == "Active"}))
+
+    def stop(self, t0, t1):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"]}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, s_mhz, m_mhz, rs in list(self.rows):
+            if ts < t0 or ts > t1:
+                continue
+            sm.append(s_mhz)
+            mx = m_mhz
+            reasons |= rs
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1,9 +1,7 @@
 #!/bin/bash
+# quick check of a build: bench line as the driver runs it (defaults), then smoke()
 O=gpurun_out/${1:-q}
 mkdir -p $O
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 | tee $O/pytest_gpu.log
-timeout 500 python bench.py --steps 10 --warmup 3 --profile-ops --no-c5 --no-cpu-baseline > $O/bench.json 2> $O/bench.err
-head -14 $O/bench.err; cut -c1-330 $O/bench.json
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file $O/launches_b8.csv python scripts/profile_step.py 8 > $O/ncu_launches_b8.log 2>&1
-tail -1 $O/ncu_launches_b8.log
+timeout 900 python bench.py > $O/bench.json 2> $O/bench.err
+cut -c1-330 $O/bench.json; tail -2 $O/bench.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2 | tee $O/smoke.log
