@@ -169,11 +169,12 @@ int opp_full_attention(const void* q, const void* kv, void* out, int batch, int 
 
 /* Source side state of linear attention (linear_attention.py:55-57):
  * kv16 fp16 [B][S][planes*2d] holds K' = elu(k)+1 in columns [0,d) and V in [d,2d) of each plane.
- * part fp32 [B][chunks][H][33][32], chunks = opp_kv_chunks(S): per-chunk sum_s K'^T V (rows 0..31)
- * and sum_s K' (row 32) for each of the H = d/32 heads. */
+ * part fp32 [B][chunks][H][33][32], chunks = opp_kv_chunks_b(S, B): per-chunk sum_s K'^T V (rows
+ * 0..31) and sum_s K' (row 32) for each of the H = d/32 heads.  opp_kv_partial picks the chunk length
+ * from (S, B) — 256 tokens, 128 when that would leave fewer than 64 CTAs — and opp_kv_finalize must
+ * be given the matching chunk count: opp_kv_chunks_b(S, B).  opp_kv_chunks(S) = the 256-token count
+ * (what large batches use), kept for callers that size buffers once. */
 int opp_kv_chunks(int s);
-/* chunks per batch element as opp_kv_partial / opp_kv_finalize use them for this (S, batch): at
- * small batches the chunks are shorter so that more CTAs share the stream (size `part` with this) */
 int opp_kv_chunks_b(int s, int batch);
 int opp_kv_partial(const void* kv16, float* part, int batch, int s, int d, int split,
                    opp_stream_t stream);
