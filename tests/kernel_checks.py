@@ -85,7 +85,12 @@ def check_linear_ln():
                                                                   (1, 2600, 128, 128, False, False, True, False),
                                                                   (3, 500, 512, 256, False, True, False, False),
                                                                   (3, 700, 512, 256, False, True, False, True),
-                                                                  (1, 26 * 70, 256, 128, False, True, True, False)]:
+                                                                  (1, 26 * 70, 256, 128, False, True, True, False),
+                                                                  # N = 256 at a small grid = N-split cluster
+                                                                  # (DSMEM statistics exchange), fp32 output too
+                                                                  (1, 600, 256, 256, False, True, True, False),
+                                                                  # > 74 M tiles: the cta_group::2 pair path
+                                                                  (1, 12000, 256, 256, False, True, False, False)]:
             a0f = _rand(B * rows, k0, seed=1)
             wf = _rand(B if batched else 1, n, k0, scale=0.05, seed=3)
             gamma = 1 + 0.1 * _rand(n, seed=4)
