@@ -82,6 +82,7 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
  *   j_ids == NULL: `in` is the compact output [matches][win + 2][8][planes*c_in_pad] of a previous
  *         call; output (ly, lx) reads input rows ly..ly+2, columns lx..lx+2
  *   count: NULL = `matches` is exact; else the capacity, the real count is read on the device */
+int opp_conv_win_pitch(int win);   /* row pitch P of the output windows: out is [matches][win][P][planes*c_out_pad] */
 int opp_conv_win(const void* in, const void* w, const float* bias, void* out, const long long* b_ids,
                  const long long* j_ids, int matches, const int* count, int batch, int in_h, int in_w,
                  int c_in_pad, int c_out_pad, int win, int wc, int stride, int org, int act,

@@ -60,6 +60,7 @@ SIGNATURES = {
 PLAIN = {"opp_version": ([], c_int), "opp_num_sms": ([], c_int), "opp_sim_tiles": ([I], c_int),
          "opp_kv_chunks": ([I], c_int),
          "opp_kv_chunks_b": ([I, I], c_int),
+         "opp_conv_win_pitch": ([I], c_int),
          "opp_last_error": ([], ctypes.c_char_p)}
 
 

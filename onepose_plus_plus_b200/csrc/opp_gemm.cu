@@ -480,6 +480,19 @@ int opp_conv2d_nhwc(const void* in, const void* w, const float* bias, const void
   return launch<A_CONV, EpiConv>(maps, s, ep, (cudaStream_t)stream);
 }
 
+// Row pitch of the compact output windows of opp_conv_win(win).  7x7 windows: pitch 8 (two windows =
+// 112 accumulator rows, each a whole number of 1024-byte swizzle atoms in the A stage).  5x5 windows:
+// $OPP_WIN5_PACK=1 packs FIVE 5x5 boxes (125 rows, 25 x 128 B apart: 128-byte aligned only) instead
+// of three 5x8 ones (120 rows, 75 of them valid).
+int opp_conv_win_pitch(int win) {
+  static int pack5 = -1;
+  if (pack5 < 0) {
+    const char* e = getenv("OPP_WIN5_PACK");
+    pack5 = e ? atoi(e) : 0;
+  }
+  return (win == 5 && pack5) ? 5 : 8;
+}
+
 int opp_conv_win(const void* in, const void* w, const float* bias, void* out, const long long* b_ids,
                  const long long* j_ids, int matches, const int* count, int batch, int in_h, int in_w,
                  int c_in_pad, int c_out_pad, int win, int wc, int stride, int org, int act,
@@ -497,11 +510,12 @@ int opp_conv_win(const void* in, const void* w, const float* bias, void* out, co
   GemmShape s;
   memset(&s, 0, sizeof(s));
   s.batches = 1;
-  s.tile_w = 8;
+  const int pitch = opp_conv_win_pitch(win);
+  s.tile_w = pitch;
   s.tile_h = win;
-  s.tiles_x = 128 / (8 * win);   // windows per M tile: 2 (7x7) or 3 (5x5)
+  s.tiles_x = 128 / (pitch * win);   // windows per M tile: 2 (7x8), 3 (5x8) or 5 (5x5)
   s.tiles_y = 1;
-  s.rows = matches * 8 * win;
+  s.rows = matches * pitch * win;
   s.m_tiles = (matches + s.tiles_x - 1) / s.tiles_x;
   s.block_n = c_out_pad;
   s.n_tiles = 1;
@@ -512,7 +526,7 @@ int opp_conv_win(const void* in, const void* w, const float* bias, void* out, co
   s.conv_kw = 3;
   s.conv_pad = 1;
   s.conv_stride = 1;
-  s.out_w = 8;
+  s.out_w = pitch;
   s.out_h = win;
   s.split = split ? 1 : 0;
   const long long C = (long long)planes * c_in_pad;
@@ -521,7 +535,7 @@ int opp_conv_win(const void* in, const void* w, const float* bias, void* out, co
     const uint64_t iw = j_ids ? in_w : 8, ih = j_ids ? in_h : win + 2, ib = j_ids ? batch : matches;
     uint64_t dims[4] = {(uint64_t)C, iw, ih, ib};
     uint64_t str[3] = {(uint64_t)C, (uint64_t)(iw * C), (uint64_t)(ih * iw * C)};
-    uint32_t box[4] = {64, 8, (uint32_t)win, 1};
+    uint32_t box[4] = {64, (uint32_t)pitch, (uint32_t)win, 1};
     rc = make_map(&maps.a[0], in, 4, dims, str, box);
     if (rc) return rc;
     maps.a[1] = maps.a[2] = maps.a[3] = maps.a[0];
@@ -534,7 +548,7 @@ int opp_conv_win(const void* in, const void* w, const float* bias, void* out, co
   if (rc) return rc;
   EpiWin::Params ep{(__half*)out, (long long)c_out_pad * planes, split ? c_out_pad : 0, bias, act, slope,
                     b_ids, j_ids, wc, stride, org, in_h, in_w};
-  if (count) return launch<A_WIN, EpiWin, true>(maps, s, ep, (cudaStream_t)stream, count, 8 * win);
+  if (count) return launch<A_WIN, EpiWin, true>(maps, s, ep, (cudaStream_t)stream, count, pitch * win);
   return launch<A_WIN, EpiWin>(maps, s, ep, (cudaStream_t)stream);
 }
 

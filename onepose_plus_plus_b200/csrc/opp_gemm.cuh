@@ -1337,11 +1337,11 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
       const int bb = s.b_batched ? b : 0;
       const int nrow0 = n_tile * s.block_n;
       // A_WIN: input coordinates of the (up to three) windows of this tile, once per tile
-      int win_x[3] = {0, 0, 0}, win_y[3] = {0, 0, 0}, win_z[3] = {0, 0, 0};
+      int win_x[5] = {0, 0, 0, 0, 0}, win_y[5] = {0, 0, 0, 0, 0}, win_z[5] = {0, 0, 0, 0, 0};
       if constexpr (A_MODE == A_WIN) {
         const int cnt = s.rows / (s.tile_w * s.tile_h);
 #pragma unroll
-        for (int wi = 0; wi < 3; ++wi) {
+        for (int wi = 0; wi < 5; ++wi) {
           int m = m_tile * s.tiles_x + wi;
           m = m < cnt ? m : cnt - 1;
           win_z[wi] = m;
@@ -1382,12 +1382,12 @@ __device__ __forceinline__ void gemm_body(const TensorMaps& maps, const GemmShap
             }
           }
         } else if constexpr (A_MODE == A_WIN) {
-          // one TMA box (64 channels x 8 x tile_h) per window and plane; windows past the match
+          // one TMA box (64 channels x tile_w x tile_h) per window and plane; windows past the match
           // count re-read the last one (their rows are never stored)
           kb = kb_tap + cc * kBlockK;
           const int wbytes = s.tile_w * s.tile_h * (kBlockK * 2);
 #pragma unroll
-          for (int wi = 0; wi < 3; ++wi) {
+          for (int wi = 0; wi < 5; ++wi) {
             if (wi >= s.tiles_x) break;
             const int bx = win_x[wi] + kx, by = win_y[wi] + ky, bz = win_z[wi];
             if (elect_one()) {

@@ -745,8 +745,8 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
   const float d = desc3d[((desc_shared ? 0 : b) * 128 + c) * n + i];
   if (x32) x32[row0 * 128 + c] = d;
   store_split1(x16 + row0 * ld, c, d, lo_off);
-  // windows: `fine` holds the compact per-match windows of opp_conv_win, [m][5][8][ld]
-  const __half* fb = windows ? fine + (long long)m * 40 * ld : fine + b * hf * wf * ld;
+  // windows (= row pitch P, 8 or 5): `fine` holds the compact per-match windows of opp_conv_win, [m][5][P][ld]
+  const __half* fb = windows ? fine + (long long)m * 5 * windows * ld : fine + b * hf * wf * ld;
   // all 25 window loads in flight before the first store (one block per match: the dependent
   // load -> store pairs of the rolled loop were 25 serial round trips)
   float v[25];
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(128) fine_gather_kernel(
     const int y = jy * stride + ww / 5 - 2, x = jx * stride + ww % 5 - 2;
     v[ww] = 0.f;
     if (y >= 0 && y < hf && x >= 0 && x < wf)
-      v[ww] = load_split1(fb + (windows ? (long long)((ww / 5) * 8 + ww % 5) : (long long)y * wf + x) * ld, c, lo_off);
+      v[ww] = load_split1(fb + (windows ? (long long)((ww / 5) * windows + ww % 5) : (long long)y * wf + x) * ld, c, lo_off);
   }
 #pragma unroll
   for (int ww = 0; ww < 25; ++ww) {

@@ -508,7 +508,7 @@ class _Engine(nn.Module):
         t = self._buf("x1_h_win", (M, 7, 8, pl * w0.shape[0]), torch.float16, dev)
         ops.conv_win(x1_lat, w0, b0, t, 7, split, M, act=2, b_ids=b_ids, j_ids=j_ids, wc=wc, stride=stride,
                      org=-3, count=count)
-        out = self._buf("x1_out_win", (M, 5, 8, pl * w1.shape[0]), torch.float16, dev)
+        out = self._buf("x1_out_win", (M, 5, ops.conv_win_pitch(5), pl * w1.shape[0]), torch.float16, dev)
         return ops.conv_win(t, w1, b1, out, 5, split, M, count=count)
 
     def _windows_pay(self, M, B, hf, wf):

@@ -225,7 +225,13 @@ def fine_gather(fine, desc3d, b_ids, i_ids, j_ids, x32, x16, m, hf, wf, wc, stri
     """windows: `fine` is the compact [m, 5, 8, planes*128] window tensor of conv_win."""
     _chk(desc3d, torch.float32, "descriptors3d_db")
     call("opp_fine_gather", ptr(fine), ptr(desc3d), ptr(b_ids), ptr(i_ids), ptr(j_ids), ptr(x32),
-         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared), int(windows), ptr(count), stream())
+         ptr(x16), m, hf, wf, wc, stride, n, int(split), int(bank_shared),
+         (conv_win_pitch(5) if windows is True else int(windows)), ptr(count), stream())
+
+
+def conv_win_pitch(win):
+    """Row pitch of conv_win's compact output windows ([m, win, pitch, planes*Cout_pad])."""
+    return _lib.load().opp_conv_win_pitch(win)
 
 
 def conv_win(x, w, bias, out, win, split, m, act=0, slope=0.01, b_ids=None, j_ids=None, wc=0, stride=4,

@@ -264,7 +264,7 @@ def check_conv_win():
             bi = torch.cat([b_ids, b_ids.new_zeros(cap - M)]) if dyn else b_ids
             ji = torch.cat([j_ids, j_ids.new_zeros(cap - M)]) if dyn else j_ids
             t_w = torch.full((cap, 7, 8, pl * cmid_pad), float("nan"), device=DEV, dtype=torch.half)
-            o_w = torch.full((cap, 5, 8, pl * cout), float("nan"), device=DEV, dtype=torch.half)
+            o_w = torch.full((cap, 5, ops.conv_win_pitch(5), pl * cout), float("nan"), device=DEV, dtype=torch.half)
             ops.conv_win(x16, w0, b0, t_w, 7, split, cap, act=2, b_ids=bi, j_ids=ji, wc=wc, stride=4, org=-3,
                          count=count)
             ops.conv_win(t_w, w1, b1, o_w, 5, split, cap, count=count)
