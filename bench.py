@@ -84,7 +84,7 @@ class ClockSampler:
                         self.rows.append((time.time(), sm, mx, {n for n, b in self.BITS if mask & b}))
                     except Exception:  # noqa: BLE001
                         pass
-                    self._stop.wait(0.1)
+                    self._stop.wait(0.25)
             poll_once_ok = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)) > 0
             if poll_once_ok:
                 self.source = "nvml"
@@ -403,27 +403,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    step_ms = []
+
+    def timed(fn, steps, per_step=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = []
         t0 = time.time()
         e0.record()
         for _ in range(steps):
             d = fn()
+            if per_step:       # diagnostics only: an event record costs nothing on the stream
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if per_step:
+            prev = e0
+            for ev in marks:
+                step_ms.append(round(prev.elapsed_time(ev), 3))
+                prev = ev
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item(), d, t0, time.time()
 
-    # 5 untimed settle steps (allocator high-water marks, power state: the first timed region of a
-    # fresh process was seen 8 % slower than the later ones of the same run on one box), then the
-    # W >= 3 warm-up steps of the contract
-    for _ in range(5 + max(args.warmup, 3)):
+    # untimed settle phase (allocator high-water marks, power state: the first timed region of a fresh
+    # process was seen 8 % slower than the later ones of the same run on some boxes — the power-cap
+    # controller needs a second or two of the real load), then the W >= 3 warm-up steps of the contract
+    t_settle, n_settle = time.time(), 0
+    while n_settle < 5 or time.time() - t_settle < 2.5:     # >= 5 steps and >= 2.5 s under load
+        d = step_resident()
+        torch.cuda.synchronize()
+        n_settle += 1
+    for _ in range(max(args.warmup, 3)):
         d = step_resident()
     _lib.LAUNCHES = 0
-    ms, d, t0, t1 = timed(step_resident, args.steps)
+    ms, d, t0, t1 = timed(step_resident, args.steps, per_step=True)
     clocks = sampler.stop(t0, t1) if sampler else None
     launches = _lib.LAUNCHES
     m_per_img = d["b_ids"].numel() / B
@@ -607,7 +624,7 @@ def main():
                                    f"5000-pt bank (NCCL-broadcast once when N>1)",
                        "global_batch": B * world, "matches_per_image": m_per_img,
                        "l2": "per-step working set (activations >= 1 GB) exceeds the 126 MB L2; no explicit flush",
-                       "settle_steps": 5,
+                       "settle_steps": n_settle, "step_ms": step_ms,
                        "conf_matrix": "materialised fp32 every step (reference API); see conf_lazy for the "
                                       "store-free mode"},
             "clocks": clocks,
